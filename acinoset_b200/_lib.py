@@ -1,0 +1,188 @@
+"""ctypes binding of libacino_b200.so (C ABI declared in include/acino_b200.h).
+
+The shared library is the product; there is no CPU fallback.  Importing this module fails
+loudly if the library has not been built (``python -c 'import __graft_entry__ as g; g.build()'``
+or ``make``), and creating a handle fails loudly if there is no CUDA device.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacino_b200.so")
+
+N_ACTIVE = 25
+N_MARKERS = 20
+N_UPPER = 325
+MAX_CAMS = 16
+
+
+class AcinoError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA extension first (make, or __graft_entry__.build()). "
+            "acinoset_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    lib.acino_create.argtypes = [ctypes.POINTER(vp), ci]
+    lib.acino_create.restype = ci
+    lib.acino_destroy.argtypes = [vp]
+    lib.acino_destroy.restype = ci
+    lib.acino_last_error.argtypes = [vp]
+    lib.acino_last_error.restype = ctypes.c_char_p
+    lib.acino_version.argtypes = []
+    lib.acino_version.restype = ci
+    lib.acino_launch_count.argtypes = [vp]
+    lib.acino_launch_count.restype = ctypes.c_int64
+    lib.acino_set_cameras.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.acino_set_cameras.restype = ci
+    lib.acino_set_redescending.argtypes = [vp, cd, cd, cd]
+    lib.acino_set_redescending.restype = ci
+    lib.acino_fte_eval_dev.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp]
+    lib.acino_fte_eval_dev.restype = ci
+    lib.acino_fte_eval.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
+    lib.acino_fte_eval.restype = ci
+    lib.acino_fk_project_dev.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.acino_fk_project_dev.restype = ci
+    lib.acino_fk_project.argtypes = [vp, ci, vp, vp, vp]
+    lib.acino_fk_project.restype = ci
+    return lib
+
+
+lib = _load()
+
+# every symbol include/acino_b200.h declares (checked by tests/test_abi.py without a GPU)
+EXPORTED = [
+    "acino_create", "acino_destroy", "acino_last_error", "acino_version", "acino_launch_count",
+    "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
+    "acino_fk_project_dev", "acino_fk_project",
+]
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _host(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class Handle:
+    """One handle per GPU: owns the camera table, loss constants and a staging workspace."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        rc = lib.acino_create(ctypes.byref(self._h), int(device))
+        if rc != 0:
+            raise AcinoError(f"acino_create failed ({rc}): {lib.acino_last_error(None).decode()}")
+        self.device = int(device)
+        self.n_cams = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.acino_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise AcinoError(f"{what} failed ({rc}): {lib.acino_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(lib.acino_launch_count(self._h))
+
+    # ---- scene
+    def set_cameras(self, K, D, R, t):
+        K = _host(K, np.float64)
+        C = K.shape[0]
+        K = K.reshape(C, 9)
+        D = _host(D, np.float64).reshape(C, 4)
+        R = _host(R, np.float64).reshape(C, 9)
+        t = _host(t, np.float64).reshape(C, 3)
+        self._check(lib.acino_set_cameras(self._h, C, _np_ptr(K), _np_ptr(D), _np_ptr(R), _np_ptr(t)),
+                    "acino_set_cameras")
+        self.n_cams = C
+
+    def set_redescending(self, a, b, c):
+        self._check(lib.acino_set_redescending(self._h, float(a), float(b), float(c)), "acino_set_redescending")
+
+    # ---- host-buffer API (copies inside the call)
+    def fte_eval(self, x, meas, w, want_H=True, out=None):
+        x = _host(x, np.float32)
+        N = x.shape[0]
+        C = self.n_cams
+        x = _host(x, np.float32, (N, N_ACTIVE))
+        meas = _host(meas, np.float32, (N, C, N_MARKERS, 2))
+        w = _host(w, np.float32, (N, C, N_MARKERS))
+        if out is None:
+            cost = np.empty(N, np.float32)
+            g = np.empty((N, N_ACTIVE), np.float32)
+            H = np.empty((N, N_UPPER), np.float32) if want_H else None
+        else:
+            cost, g, H = out
+        self._check(lib.acino_fte_eval(self._h, N, _np_ptr(x), _np_ptr(meas), _np_ptr(w), _np_ptr(cost),
+                                       _np_ptr(g), _np_ptr(H)), "acino_fte_eval")
+        return cost, g, H
+
+    def fk_project(self, x, want_pos=True, want_uv=True):
+        x = _host(x, np.float32)
+        N = x.shape[0]
+        x = _host(x, np.float32, (N, N_ACTIVE))
+        pos = np.empty((N, N_MARKERS, 3), np.float32) if want_pos else None
+        uv = np.empty((N, self.n_cams, N_MARKERS, 2), np.float32) if want_uv else None
+        self._check(lib.acino_fk_project(self._h, N, _np_ptr(x), _np_ptr(pos), _np_ptr(uv)), "acino_fk_project")
+        return pos, uv
+
+    # ---- device-pointer API (torch tensors on this handle's device; stream-ordered)
+    def fte_eval_dev(self, x, meas, w, cost=None, g=None, H=None, stream=None):
+        import torch
+
+        N = x.shape[0]
+        for tns, shp in ((x, (N, N_ACTIVE)), (meas, (N, self.n_cams, N_MARKERS, 2)), (w, (N, self.n_cams, N_MARKERS))):
+            _check_dev(tns, shp, self.device)
+        for tns, shp in ((cost, (N,)), (g, (N, N_ACTIVE)), (H, (N, N_UPPER))):
+            if tns is not None:
+                _check_dev(tns, shp, self.device)
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(lib.acino_fte_eval_dev(self._h, N, _dp(x), _dp(meas), _dp(w), _dp(cost), _dp(g), _dp(H),
+                                           ctypes.c_void_p(s)), "acino_fte_eval_dev")
+
+    def fk_project_dev(self, x, pos=None, uv=None, stream=None):
+        import torch
+
+        N = x.shape[0]
+        _check_dev(x, (N, N_ACTIVE), self.device)
+        if pos is not None:
+            _check_dev(pos, (N, N_MARKERS, 3), self.device)
+        if uv is not None:
+            _check_dev(uv, (N, self.n_cams, N_MARKERS, 2), self.device)
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(lib.acino_fk_project_dev(self._h, N, _dp(x), _dp(pos), _dp(uv), ctypes.c_void_p(s)),
+                    "acino_fk_project_dev")
+
+
+def _dp(tns):
+    return ctypes.c_void_p(tns.data_ptr()) if tns is not None else None
+
+
+def _check_dev(tns, shape, device):
+    import torch
+
+    if not tns.is_cuda or tns.device.index != device:
+        raise ValueError(f"tensor must live on cuda:{device}")
+    if tns.dtype != torch.float32 or not tns.is_contiguous() or tuple(tns.shape) != tuple(shape):
+        raise ValueError(f"expected contiguous float32 tensor of shape {shape}, got {tns.dtype} {tuple(tns.shape)}")

@@ -1,0 +1,143 @@
+// Shared device-side definitions for libacino_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/acino_b200.h"
+
+namespace acino {
+
+constexpr int NA = ACINO_N_ACTIVE;    // 25 active pose parameters
+constexpr int NL = ACINO_N_MARKERS;   // 20 markers
+constexpr int NU = ACINO_N_UPPER;     // 325
+constexpr int NANG = 22;              // angle slots (active slots 3..24)
+constexpr int NJ = 14;                // joints in the rotation chain
+constexpr int NSP = 27;               // 21 spatial-inertia + 6 wrench components
+
+// One camera, fp32: world->camera rotation (row-major), translation, intrinsics, distortion.
+// Kannala-Brandt model of pt3d_to_2d (reference all_optimizations.py:193-209).
+struct CamF {
+    float R[9];
+    float t[3];
+    float fx, fy, cx, cy;
+    float D[4];
+};
+
+struct CamD {
+    double R[9];
+    double t[3];
+    double fx, fy, cx, cy;
+    double D[4];
+};
+
+struct LossF {
+    float a, b, c;        // break points
+    float ea, eb, ec;     // exp(a), exp(b), exp(c)
+    float p2c;            // -a^2/2
+    float k3;             // a (c-b) / 2
+    float inv_cb;         // 1/(c-b)
+    float p3c;            // a b - a^2/2
+    float p4;             // a b - a^2/2 + a (c-b)/2
+    float rho0;           // rho(0)
+};
+
+struct SceneF {
+    CamF cam[ACINO_MAX_CAMS];
+    LossF loss;
+    int n_cams;
+};
+
+__host__ __device__ inline int upper_index(int i, int j) {  // i <= j
+    return i * NA - (i * (i - 1)) / 2 + (j - i);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fisheye projection of a camera-frame point with its 2x3 Jacobian w.r.t. the camera-frame
+// point (closed form).  T = float or double.
+template <typename T>
+struct ProjOut {
+    T u, v;        // pixel WITHOUT the principal point: u = fx a s, v = fy b s
+    T ju[3];       // d u / d Xc
+    T jv[3];       // d v / d Xc
+};
+
+template <typename T> __device__ __forceinline__ T t_rsqrt(T x);
+template <> __device__ __forceinline__ float t_rsqrt<float>(float x) { return rsqrtf(x); }
+template <> __device__ __forceinline__ double t_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
+template <typename T> __device__ __forceinline__ T t_atan(T x);
+template <> __device__ __forceinline__ float t_atan<float>(float x) { return atanf(x); }
+template <> __device__ __forceinline__ double t_atan<double>(double x) { return atan(x); }
+template <typename T> __device__ __forceinline__ T t_rcp(T x);
+__device__ __forceinline__ float fast_rcp(float x) {  // MUFU.RCP, ~1 ulp
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <> __device__ __forceinline__ float t_rcp<float>(float x) { return fast_rcp(x); }
+template <> __device__ __forceinline__ double t_rcp<double>(double x) { return 1.0 / x; }
+
+template <typename T, bool WITH_JAC>
+__device__ __forceinline__ void fisheye_cam(const T x, const T y, const T z, const T fx, const T fy,
+                                            const T k1, const T k2, const T k3, const T k4,
+                                            ProjOut<T>& o) {
+    const T iz = t_rcp<T>(z);
+    const T a = x * iz;
+    const T b = y * iz;
+    const T r2 = a * a + b * b + T(1e-12);     // the "+1e-12" of all_optimizations.py:201
+    const T ir = t_rsqrt<T>(r2);
+    const T r = r2 * ir;
+    const T th = t_atan<T>(r);
+    const T th2 = th * th;
+    const T td = th * (T(1) + th2 * (k1 + th2 * (k2 + th2 * (k3 + th2 * k4))));
+    const T s = td * ir;
+    o.u = fx * (a * s);
+    o.v = fy * (b * s);
+    if (WITH_JAC) {
+        const T dtd = T(1) + th2 * (T(3) * k1 + th2 * (T(5) * k2 + th2 * (T(7) * k3 + th2 * (T(9) * k4))));
+        // q = (ds/dr)/r = (dtd/(1+r^2) - s) / r^2
+        const T q = (dtd * t_rcp<T>(T(1) + r2) - s) * (ir * ir);
+        const T aq = a * q;
+        const T m00 = s + a * aq;
+        const T m01 = b * aq;
+        const T m11 = s + b * b * q;
+        const T fxi = fx * iz;
+        const T fyi = fy * iz;
+        o.ju[0] = fxi * m00;
+        o.ju[1] = fxi * m01;
+        o.ju[2] = -fxi * (m00 * a + m01 * b);
+        o.jv[0] = fyi * m01;
+        o.jv[1] = fyi * m11;
+        o.jv[2] = -fyi * (m01 * a + m11 * b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Redescending loss (reference build.py:382-395, literal logistic blend) for e = |w r| >= 0:
+// returns rho(e), rho'(e) and the Gauss-Newton curvature weight
+//     psi(e) = max(rho'(e)/e, 1 - sigma_a(e))
+// i.e. the IRLS weight rho'/e floored by the (frozen-gate) curvature of the quadratic piece.
+// The floor takes over for e < ~0.45, where the literal blend has a tiny cusp (rho'(0+) < 0)
+// that makes rho'/e both negative and ill-conditioned in fp32; psi >= 0 everywhere.
+__device__ __forceinline__ void redescending(const LossF& L, const float e, float& rho, float& drho,
+                                             float& psi) {
+    const float E = __expf(-e);
+    const float sa = fast_rcp(fmaf(E, L.ea, 1.0f));
+    const float sb = fast_rcp(fmaf(E, L.eb, 1.0f));
+    const float sc = fast_rcp(fmaf(E, L.ec, 1.0f));
+    const float dsa = sa * (1.0f - sa);
+    const float dsb = sb * (1.0f - sb);
+    const float dsc = sc * (1.0f - sc);
+    const float p1 = 0.5f * e * e;
+    const float p2 = fmaf(L.a, e, L.p2c);
+    const float u = (L.c - e) * L.inv_cb;
+    const float p3 = fmaf(L.k3, 1.0f - u * u, L.p3c);
+    const float dp3 = L.a * u;
+    const float gab = sa - sb;
+    const float gbc = sb - sc;
+    rho = (1.0f - sa) * p1 + gab * p2 + gbc * p3 + sc * L.p4;
+    drho = (1.0f - sa) * e - dsa * p1 + (dsa - dsb) * p2 + gab * L.a + (dsb - dsc) * p3 + gbc * dp3 +
+           dsc * L.p4;
+    psi = e > 0.0f ? fmaxf(__fdividef(drho, e), 1.0f - sa) : 1.0f - sa;
+}
+
+}  // namespace acino

@@ -1,0 +1,222 @@
+// C ABI of libacino_b200.so (see include/acino_b200.h).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "acino_common.cuh"
+
+namespace acino {
+cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                            const float* w, float* cost, float* g, float* H, cudaStream_t stream);
+cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
+                              cudaStream_t stream);
+}  // namespace acino
+
+using namespace acino;
+
+struct acino_handle {
+    int device = 0;
+    SceneF scene;
+    CamD cam_d[ACINO_MAX_CAMS];
+    bool have_cams = false;
+    int64_t launches = 0;
+    std::string err;
+    // host-API staging (device)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+static thread_local std::string g_err;
+
+static int fail(acino_handle* h, int code, const std::string& msg) {
+    g_err = msg;
+    if (h) h->err = msg;
+    return code;
+}
+static int cuda_fail(acino_handle* h, cudaError_t e, const char* what) {
+    return fail(h, ACINO_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) return cuda_fail(h, _e, #call);       \
+    } while (0)
+
+static void set_loss(LossF& L, double a, double b, double c) {
+    L.a = (float)a; L.b = (float)b; L.c = (float)c;
+    L.ea = (float)std::exp(a); L.eb = (float)std::exp(b); L.ec = (float)std::exp(c);
+    L.p2c = (float)(-a * a / 2);
+    L.k3 = (float)(a * (c - b) / 2);
+    L.inv_cb = (float)(1.0 / (c - b));
+    L.p3c = (float)(a * b - a * a / 2);
+    L.p4 = (float)(a * b - a * a / 2 + a * (c - b) / 2);
+    auto step = [](double s, double x) { return 1.0 / (1.0 + std::exp(-(x - s))); };
+    const double sa = step(a, 0), sb = step(b, 0), sc = step(c, 0);
+    const double u = c / (c - b);
+    L.rho0 = (float)((sa - sb) * (-a * a / 2) + (sb - sc) * (a * b - a * a / 2 + (a * (c - b) / 2) * (1 - u * u)) +
+                     sc * (a * b - a * a / 2 + a * (c - b) / 2));
+}
+
+static inline size_t pad64(size_t n) { return (n + 63) & ~(size_t)63; }
+
+static int ensure_ws(acino_handle* h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return ACINO_OK;
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    CK(cudaMalloc(&h->ws, bytes));
+    h->ws_bytes = bytes;
+    return ACINO_OK;
+}
+
+extern "C" {
+
+int acino_version(void) { return 100; }
+
+const char* acino_last_error(const acino_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int64_t acino_launch_count(const acino_handle* h) { return h ? h->launches : 0; }
+
+int acino_create(acino_handle** out, int device) {
+    if (!out) return fail(nullptr, ACINO_ERR_ARG, "acino_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, ACINO_ERR_CUDA, std::string("acino_create: no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, ACINO_ERR_ARG, "acino_create: bad device index");
+    acino_handle* h = new acino_handle();
+    h->device = device;
+    memset(&h->scene, 0, sizeof(h->scene));
+    set_loss(h->scene.loss, 3.0, 10.0, 20.0);   // all_optimizations.py:25-27
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "acino_create");
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return ACINO_OK;
+}
+
+int acino_destroy(acino_handle* h) {
+    if (!h) return ACINO_OK;
+    cudaSetDevice(h->device);
+    if (h->ws) cudaFree(h->ws);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ACINO_OK;
+}
+
+int acino_set_cameras(acino_handle* h, int n_cams, const double* K, const double* D, const double* R,
+                      const double* t) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_set_cameras: NULL handle");
+    if (n_cams < 1 || n_cams > ACINO_MAX_CAMS || !K || !D || !R || !t)
+        return fail(h, ACINO_ERR_ARG, "acino_set_cameras: need 1..16 cameras and non-NULL K, D, R, t");
+    for (int c = 0; c < n_cams; ++c) {
+        CamD& cd = h->cam_d[c];
+        CamF& cf = h->scene.cam[c];
+        for (int i = 0; i < 9; ++i) { cd.R[i] = R[c * 9 + i]; cf.R[i] = (float)cd.R[i]; }
+        for (int i = 0; i < 3; ++i) { cd.t[i] = t[c * 3 + i]; cf.t[i] = (float)cd.t[i]; }
+        for (int i = 0; i < 4; ++i) { cd.D[i] = D[c * 4 + i]; cf.D[i] = (float)cd.D[i]; }
+        cd.fx = K[c * 9 + 0]; cd.fy = K[c * 9 + 4]; cd.cx = K[c * 9 + 2]; cd.cy = K[c * 9 + 5];
+        cf.fx = (float)cd.fx; cf.fy = (float)cd.fy; cf.cx = (float)cd.cx; cf.cy = (float)cd.cy;
+    }
+    h->scene.n_cams = n_cams;
+    h->have_cams = true;
+    return ACINO_OK;
+}
+
+int acino_set_redescending(acino_handle* h, double a, double b, double c) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_set_redescending: NULL handle");
+    if (!(a > 0 && b > a && c > b && c < 80.0))
+        return fail(h, ACINO_ERR_ARG, "acino_set_redescending: need 0 < a < b < c < 80");
+    set_loss(h->scene.loss, a, b, c);
+    return ACINO_OK;
+}
+
+int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const float* meas, const float* w,
+                       float* cost, float* g, float* H, void* cuda_stream) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fte_eval_dev: NULL handle");
+    if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_fte_eval_dev: cameras not set");
+    if (n_frames < 0 || (n_frames > 0 && (!x || !meas || !w)))
+        return fail(h, ACINO_ERR_ARG, "acino_fte_eval_dev: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    if (((uintptr_t)meas & 7u) != 0) return fail(h, ACINO_ERR_ARG, "acino_fte_eval_dev: meas must be 8-byte aligned");
+    CK(cudaSetDevice(h->device));
+    CK(launch_fte_eval(h->scene, n_frames, x, meas, w, cost, g, H, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* meas, const float* w,
+                   float* cost, float* g, float* H) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fte_eval: NULL handle");
+    if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_fte_eval: cameras not set");
+    if (n_frames < 0 || (n_frames > 0 && (!x || !meas || !w))) return fail(h, ACINO_ERR_ARG, "acino_fte_eval: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t N = (size_t)n_frames, C = (size_t)h->scene.n_cams;
+    const size_t nx = N * NA, nm = N * C * NL * 2, nw = N * C * NL, nc = N, ng = N * NA, nh = N * NU;
+    // sub-buffers start on 64-float (256 B) boundaries: the kernel loads meas as float2
+    const size_t ax = pad64(nx), am = pad64(nm), aw = pad64(nw), ac = pad64(nc), ag = pad64(ng);
+    const size_t total = (ax + am + aw + ac + ag + nh) * sizeof(float);
+    int rc = ensure_ws(h, total);
+    if (rc) return rc;
+    float* dx = (float*)h->ws;
+    float* dm = dx + ax;
+    float* dw = dm + am;
+    float* dc = dw + aw;
+    float* dg = dc + ac;
+    float* dH = dg + ag;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dx, x, nx * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dm, meas, nm * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dw, w, nw * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(launch_fte_eval(h->scene, n_frames, dx, dm, dw, cost ? dc : nullptr, g ? dg : nullptr, H ? dH : nullptr, s));
+    h->launches += 1;
+    if (cost) CK(cudaMemcpyAsync(cost, dc, nc * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (g) CK(cudaMemcpyAsync(g, dg, ng * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (H) CK(cudaMemcpyAsync(H, dH, nh * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_fk_project_dev(acino_handle* h, int n_frames, const float* x, float* pos, float* uv, void* cuda_stream) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fk_project_dev: NULL handle");
+    if (uv && !h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_fk_project_dev: cameras not set");
+    if (n_frames < 0 || (n_frames > 0 && !x)) return fail(h, ACINO_ERR_ARG, "acino_fk_project_dev: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    CK(launch_fk_project(h->scene, n_frames, x, pos, uv, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_fk_project(acino_handle* h, int n_frames, const float* x, float* pos, float* uv) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fk_project: NULL handle");
+    if (uv && !h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_fk_project: cameras not set");
+    if (n_frames < 0 || (n_frames > 0 && !x)) return fail(h, ACINO_ERR_ARG, "acino_fk_project: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t N = (size_t)n_frames, C = (size_t)h->scene.n_cams;
+    const size_t nx = N * NA, np = N * NL * 3, nu = N * C * NL * 2;
+    int rc = ensure_ws(h, (pad64(nx) + pad64(np) + nu) * sizeof(float));
+    if (rc) return rc;
+    float* dx = (float*)h->ws;
+    float* dp = dx + pad64(nx);
+    float* du = dp + pad64(np);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dx, x, nx * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(launch_fk_project(h->scene, n_frames, dx, pos ? dp : nullptr, uv ? du : nullptr, s));
+    h->launches += 1;
+    if (pos) CK(cudaMemcpyAsync(pos, dp, np * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (uv) CK(cudaMemcpyAsync(uv, du, nu * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+}  // extern "C"

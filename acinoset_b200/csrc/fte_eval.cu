@@ -1,0 +1,509 @@
+// fte_eval: per-frame reprojection cost, gradient and Gauss-Newton block of the FTE objective.
+//
+// Replaces (reference, /root/reference/src/all_optimizations.py): the SymPy FK chain :66-179,
+// pose_constraint :359-365, measurement_constraints :394-399 through pt3d_to_2d :193-209, the
+// measurement term of obj :494-497 with redescending_loss (build.py:382-395), and the
+// automatic differentiation IPOPT's ASL performs on those expression trees each iteration.
+//
+// Layout / mapping (B200, CUDA cores only - the contraction is tiny, irregular and sparse):
+//   one CTA = FT frames.  Phases, separated by __syncthreads():
+//   P1  FK            thread <-> frame           22 sincos, rotation chain in registers,
+//                                                writes marker positions (relative to the head)
+//                                                and one twist (omega, pivot x omega) per angle
+//   P2  projection    thread <-> (frame, marker) loops over cameras: fisheye projection, 2x3
+//                                                Jacobian, redescending loss; accumulates the
+//                                                marker's 3x3 normal block A_l, 3-vector b_l and
+//                                                cost in registers (no cross-thread reduction),
+//                                                then forms the marker's 6x6 "spatial inertia"
+//                                                B_l^T A_l B_l and wrench B_l^T b_l, B_l=[-[p]x I]
+//   P3  subtree sums  thread <-> (frame, comp)   composite-rigid-body style accumulation of the
+//                                                27 components up the kinematic tree (fixed order)
+//   P4  blocks        thread <-> (frame, angle)  y = I_subtree tau_beta; H[a][b] = tau_a . y for
+//                                                every ancestor angle a; g[b] = tau_b . wrench
+//   P5  write-out     coalesced copy of {cost, g[25], H[325]} from shared memory
+// d p_l / d angle = omega x (p_l - pivot) = B_l tau (twist about the head point), so
+// H = sum_l J_l^T A_l J_l collapses to tau_a^T I_{deeper subtree} tau_b: ~4 kFMA instead of
+// ~8 kFMA per frame for the chain rule and no 60x25 Jacobian is ever materialised.
+#include "acino_common.cuh"
+
+namespace acino {
+
+constexpr int FT = 16;                 // frames per CTA
+constexpr int NTHREADS = FT * NL;      // 320: one thread per (frame, marker) in P2
+constexpr int TAU_STRIDE = 7;          // 6 padded to 7: conflict-free across angle-lanes
+constexpr int OUT_STRIDE = 1 + NA + NU;  // 351 floats per frame: cost | g | H
+
+// joint of each angle slot (angle slot s <-> active slot 3+s):
+// phi0 phi1 phi3 | theta0..13 | psi0 psi1 psi3 psi4 psi5
+__constant__ int c_angle_joint[NANG] = {0, 1, 3, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 0, 1, 3, 4, 5};
+// ancestors-or-self of each joint as a 14-bit mask (rotation chain all_optimizations.py:101-128)
+__constant__ unsigned c_joint_anc[NJ] = {
+    0x0001, 0x0003, 0x0007, 0x000F, 0x001F, 0x003F,            // 0..5 : 0,1,2,3,4,5 chain
+    0x0047, 0x00C7,                                            // 6 (2<-6), 7 (6<-7)
+    0x0107, 0x0307,                                            // 8, 9
+    0x040F, 0x0C0F,                                            // 10 (3<-10), 11
+    0x100F, 0x300F};                                           // 12, 13
+
+struct __align__(16) Smem {
+    float x[FT][NA];                   // state
+    float p[FT][NL][3];                // marker positions relative to the head point
+    float tau[FT][NANG][TAU_STRIDE];   // (omega, v = pivot x omega) per angle
+    float costp[FT][NL];               // per-(frame, marker) cost partials
+    float Ij[FT][NJ][NSP];             // subtree spatial inertia + wrench per joint
+    union {
+        float Il[FT * NL][NSP];        // per-marker spatial inertia + wrench   (P2 -> P3)
+        float out[FT][OUT_STRIDE + 1]; // staged {cost, g, H}                   (P4 -> P5)
+    };
+};
+
+struct Col3 {
+    float x, y, z;
+};
+__device__ __forceinline__ Col3 operator*(float s, Col3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ Col3 operator+(Col3 a, Col3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ Col3 operator-(Col3 a, Col3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ Col3 fma3(float s, Col3 a, Col3 b) {
+    return {fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)};
+}
+__device__ __forceinline__ Col3 cross(Col3 a, Col3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+struct Mat3 {  // body->world rotation R_k_I stored by columns
+    Col3 c0, c1, c2;
+};
+// M <- M * Ry_a(th):  (c0,c2) <- (c c0 - s c2, s c0 + c c2)       [rot_y transposed, :75-82]
+__device__ __forceinline__ void rot_y(Mat3& M, float s, float c) {
+    const Col3 a = M.c0, b = M.c2;
+    M.c0 = fma3(c, a, (-s) * b);
+    M.c2 = fma3(s, a, c * b);
+}
+// M <- M * Rx_a(ph):  (c1,c2) <- (c c1 + s c2, -s c1 + c c2)      [rot_x transposed, :66-73]
+__device__ __forceinline__ void rot_x(Mat3& M, float s, float c) {
+    const Col3 a = M.c1, b = M.c2;
+    M.c1 = fma3(c, a, s * b);
+    M.c2 = fma3(-s, a, c * b);
+}
+// M <- M * Rz_a(ps):  (c0,c1) <- (c c0 + s c1, -s c0 + c c1)      [rot_z transposed, :84-91]
+__device__ __forceinline__ void rot_z(Mat3& M, float s, float c) {
+    const Col3 a = M.c0, b = M.c1;
+    M.c0 = fma3(c, a, s * b);
+    M.c1 = fma3(-s, a, c * b);
+}
+
+struct FkWriter {
+    float* p;    // [NL][3]
+    float* tau;  // [NANG][TAU_STRIDE]
+    __device__ __forceinline__ void marker(int l, Col3 v) const {
+        p[l * 3 + 0] = v.x;
+        p[l * 3 + 1] = v.y;
+        p[l * 3 + 2] = v.z;
+    }
+    // twist of angle slot s: axis omega (world), pivot (relative to head)
+    __device__ __forceinline__ void twist(int s, Col3 om, Col3 piv) const {
+        const Col3 v = cross(piv, om);
+        float* t = tau + s * TAU_STRIDE;
+        t[0] = om.x; t[1] = om.y; t[2] = om.z;
+        t[3] = v.x;  t[4] = v.y;  t[5] = v.z;
+    }
+    __device__ __forceinline__ void twist0(int s, Col3 om) const {  // pivot = head
+        float* t = tau + s * TAU_STRIDE;
+        t[0] = om.x; t[1] = om.y; t[2] = om.z;
+        t[3] = 0.f;  t[4] = 0.f;  t[5] = 0.f;
+    }
+};
+
+// angle slot ids
+enum { A_PHI0 = 0, A_PHI1 = 1, A_PHI3 = 2, A_TH0 = 3, A_PSI0 = 17, A_PSI1 = 18, A_PSI3 = 19, A_PSI4 = 20, A_PSI5 = 21 };
+
+// Cheetah forward kinematics of one frame: marker positions relative to the head point and the
+// world-frame twist of every angle.  Follows the chain RI_0..RI_13 (:101-128) and p_* (:138-165);
+// R_k_I = R_parent_I Ry_a(theta) Rx_a(phi) Rz_a(psi), and the world axis of each angle is the
+// matching column of the partially composed matrix (theta: column 1 before Ry; phi: column 0
+// after Ry; psi: column 2 after Rx).
+__device__ __forceinline__ void cheetah_fk(const float* __restrict__ x, const FkWriter& w) {
+    float sn[NANG], cs[NANG];
+#pragma unroll
+    for (int i = 0; i < NANG; ++i) sincosf(x[3 + i], &sn[i], &cs[i]);
+#define TH(k) sn[A_TH0 + (k)], cs[A_TH0 + (k)]
+    const Col3 zero = {0.f, 0.f, 0.f};
+    // joint 0: head
+    Mat3 M = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    w.twist0(A_TH0 + 0, M.c1);
+    rot_y(M, TH(0));
+    w.twist0(A_PHI0, M.c0);
+    rot_x(M, sn[A_PHI0], cs[A_PHI0]);
+    w.twist0(A_PSI0, M.c2);
+    rot_z(M, sn[A_PSI0], cs[A_PSI0]);
+    w.marker(0, 0.03f * M.c1);                          // l_eye
+    w.marker(1, -0.03f * M.c1);                         // r_eye
+    w.marker(2, 0.055f * (M.c0 - M.c2));                // nose
+    // joint 1: neck
+    w.twist0(A_TH0 + 1, M.c1);
+    rot_y(M, TH(1));
+    w.twist0(A_PHI1, M.c0);
+    rot_x(M, sn[A_PHI1], cs[A_PHI1]);
+    w.twist0(A_PSI1, M.c2);
+    rot_z(M, sn[A_PSI1], cs[A_PSI1]);
+    const Col3 neck = -0.28f * M.c0;
+    w.marker(3, neck);
+    // joint 2: front torso (pivot neck_base)
+    w.twist(A_TH0 + 2, M.c1, neck);
+    rot_y(M, TH(2));
+    const Mat3 M2 = M;
+    const Col3 spine = fma3(-0.37f, M2.c0, neck);
+    w.marker(4, spine);
+    const Col3 sh_mid = fma3(-0.04f, M2.c0, fma3(-0.10f, M2.c2, neck));
+    const Col3 lsh = fma3(0.08f, M2.c1, sh_mid);
+    const Col3 rsh = fma3(-0.08f, M2.c1, sh_mid);
+    w.marker(8, lsh);
+    w.marker(11, rsh);
+    // joints 6,7: left front leg; 8,9: right front leg (axis = column 1 of M2 throughout)
+    {
+        Mat3 Ml = M2;
+        w.twist(A_TH0 + 6, M2.c1, lsh);
+        rot_y(Ml, TH(6));
+        const Col3 knee = fma3(-0.24f, Ml.c2, lsh);
+        w.marker(9, knee);
+        w.twist(A_TH0 + 7, M2.c1, knee);
+        rot_y(Ml, TH(7));
+        w.marker(10, fma3(-0.28f, Ml.c2, knee));
+        Mat3 Mr = M2;
+        w.twist(A_TH0 + 8, M2.c1, rsh);
+        rot_y(Mr, TH(8));
+        const Col3 kneer = fma3(-0.24f, Mr.c2, rsh);
+        w.marker(12, kneer);
+        w.twist(A_TH0 + 9, M2.c1, kneer);
+        rot_y(Mr, TH(9));
+        w.marker(13, fma3(-0.28f, Mr.c2, kneer));
+    }
+    // joint 3: back torso (pivot spine)
+    w.twist(A_TH0 + 3, M.c1, spine);
+    rot_y(M, TH(3));
+    w.twist(A_PHI3, M.c0, spine);
+    rot_x(M, sn[A_PHI3], cs[A_PHI3]);
+    w.twist(A_PSI3, M.c2, spine);
+    rot_z(M, sn[A_PSI3], cs[A_PSI3]);
+    const Mat3 M3 = M;
+    const Col3 tailb = fma3(-0.37f, M3.c0, spine);
+    w.marker(5, tailb);
+    const Col3 hip_mid = fma3(0.12f, M3.c0, fma3(-0.06f, M3.c2, tailb));
+    const Col3 lhip = fma3(0.08f, M3.c1, hip_mid);
+    const Col3 rhip = fma3(-0.08f, M3.c1, hip_mid);
+    w.marker(14, lhip);
+    w.marker(17, rhip);
+    {
+        Mat3 Ml = M3;
+        w.twist(A_TH0 + 10, M3.c1, lhip);
+        rot_y(Ml, TH(10));
+        const Col3 knee = fma3(-0.32f, Ml.c2, lhip);
+        w.marker(15, knee);
+        w.twist(A_TH0 + 11, M3.c1, knee);
+        rot_y(Ml, TH(11));
+        w.marker(16, fma3(-0.25f, Ml.c2, knee));
+        Mat3 Mr = M3;
+        w.twist(A_TH0 + 12, M3.c1, rhip);
+        rot_y(Mr, TH(12));
+        const Col3 kneer = fma3(-0.32f, Mr.c2, rhip);
+        w.marker(18, kneer);
+        w.twist(A_TH0 + 13, M3.c1, kneer);
+        rot_y(Mr, TH(13));
+        w.marker(19, fma3(-0.25f, Mr.c2, kneer));
+    }
+    // joint 4: tail base (pivot tail_base), joint 5: tail mid (pivot tail1)
+    w.twist(A_TH0 + 4, M.c1, tailb);
+    rot_y(M, TH(4));
+    w.twist(A_PSI4, M.c2, tailb);
+    rot_z(M, sn[A_PSI4], cs[A_PSI4]);
+    const Col3 tail1 = fma3(-0.28f, M.c0, tailb);
+    w.marker(6, tail1);
+    w.twist(A_TH0 + 5, M.c1, tail1);
+    rot_y(M, TH(5));
+    w.twist(A_PSI5, M.c2, tail1);
+    rot_z(M, sn[A_PSI5], cs[A_PSI5]);
+    w.marker(7, fma3(-0.36f, M.c0, tail1));
+    (void)zero;
+#undef TH
+}
+
+template <bool WANT_H>
+__global__ void __launch_bounds__(NTHREADS, 2)
+fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
+                const float* __restrict__ xg, const float* __restrict__ meas,
+                const float* __restrict__ wts, float* __restrict__ cost_out,
+                float* __restrict__ g_out, float* __restrict__ H_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int f0 = blockIdx.x * FT;
+    const int nf = min(FT, n_frames - f0);
+    const int C = scene.n_cams;
+
+    // ---- P0: state -> smem (coalesced), zero-fill frames past the end
+    for (int i = tid; i < FT * NA; i += NTHREADS) {
+        const int f = i / NA;
+        (&S.x[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
+    }
+    __syncthreads();
+
+    // ---- P1: forward kinematics, one thread per frame
+    if (tid < FT) {
+        FkWriter w{&S.p[tid][0][0], &S.tau[tid][0][0]};
+        cheetah_fk(S.x[tid], w);
+    }
+    __syncthreads();
+
+    // ---- P2: projection + loss, one thread per (frame, marker), loop over cameras
+    {
+        const int f = tid / NL;
+        const int l = tid - f * NL;
+        const bool live = f < nf;
+        const float px = S.p[f][l][0], py = S.p[f][l][1], pz = S.p[f][l][2];
+        const float wx = S.x[f][0] + px, wy = S.x[f][1] + py, wz = S.x[f][2] + pz;
+        float a00 = 0.f, a01 = 0.f, a02 = 0.f, a11 = 0.f, a12 = 0.f, a22 = 0.f;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f, cst = 0.f;
+        const size_t base = ((size_t)(f0 + f) * C) * NL + l;
+        for (int c = 0; c < C; ++c) {
+            float um = 0.f, vm = 0.f, w = 0.f;
+            if (live) {
+                const float2 m = __ldg(reinterpret_cast<const float2*>(meas) + base + (size_t)c * NL);
+                w = __ldg(wts + base + (size_t)c * NL);
+                um = m.x;
+                vm = m.y;
+            }
+            const CamF& cam = scene.cam[c];
+            const float xc = fmaf(cam.R[0], wx, fmaf(cam.R[1], wy, fmaf(cam.R[2], wz, cam.t[0])));
+            const float yc = fmaf(cam.R[3], wx, fmaf(cam.R[4], wy, fmaf(cam.R[5], wz, cam.t[1])));
+            const float zc = fmaf(cam.R[6], wx, fmaf(cam.R[7], wy, fmaf(cam.R[8], wz, cam.t[2])));
+            ProjOut<float> pr;
+            fisheye_cam<float, true>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
+            // residuals in a centred frame: (fx a s) + (cx - u_meas); zero-weight rows are
+            // exactly the constant rho(0) whatever the measurement holds
+            const bool on = w != 0.f;
+            const float ru = on ? pr.u + (cam.cx - um) : 0.f;
+            const float rv = on ? pr.v + (cam.cy - vm) : 0.f;
+            float rho_u, d_u, psi_u, rho_v, d_v, psi_v;
+            redescending(scene.loss, fminf(fabsf(w * ru), 1e4f), rho_u, d_u, psi_u);
+            redescending(scene.loss, fminf(fabsf(w * rv), 1e4f), rho_v, d_v, psi_v);
+            cst += rho_u + rho_v;
+            // world-frame rows of the 2x3 Jacobian: J = Jc R
+            float Ju[3], Jv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                Ju[k] = fmaf(pr.ju[0], cam.R[k], fmaf(pr.ju[1], cam.R[3 + k], pr.ju[2] * cam.R[6 + k]));
+                Jv[k] = fmaf(pr.jv[0], cam.R[k], fmaf(pr.jv[1], cam.R[3 + k], pr.jv[2] * cam.R[6 + k]));
+            }
+            // d rho / d r = sign(r) rho'(|w r|) w   (rho' itself can be negative next to the cusp at 0)
+            const float gu = (ru < 0.f ? -d_u : d_u) * w, gv = (rv < 0.f ? -d_v : d_v) * w;
+            const float w2 = w * w;
+            const float eu = psi_u * w2, ev = psi_v * w2;
+            b0 = fmaf(gu, Ju[0], fmaf(gv, Jv[0], b0));
+            b1 = fmaf(gu, Ju[1], fmaf(gv, Jv[1], b1));
+            b2 = fmaf(gu, Ju[2], fmaf(gv, Jv[2], b2));
+            if (WANT_H) {
+                const float tu0 = eu * Ju[0], tu1 = eu * Ju[1], tu2 = eu * Ju[2];
+                const float tv0 = ev * Jv[0], tv1 = ev * Jv[1], tv2 = ev * Jv[2];
+                a00 = fmaf(tu0, Ju[0], fmaf(tv0, Jv[0], a00));
+                a01 = fmaf(tu0, Ju[1], fmaf(tv0, Jv[1], a01));
+                a02 = fmaf(tu0, Ju[2], fmaf(tv0, Jv[2], a02));
+                a11 = fmaf(tu1, Ju[1], fmaf(tv1, Jv[1], a11));
+                a12 = fmaf(tu1, Ju[2], fmaf(tv1, Jv[2], a12));
+                a22 = fmaf(tu2, Ju[2], fmaf(tv2, Jv[2], a22));
+            }
+        }
+        S.costp[f][l] = cst;
+        // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]
+        float* o = S.Il[tid];
+        if (WANT_H) {
+            // PA = [p]x A  (rows)
+            const float q00 = py * a02 - pz * a01, q01 = py * a12 - pz * a11, q02 = py * a22 - pz * a12;
+            const float q10 = pz * a00 - px * a02, q11 = pz * a01 - px * a12, q12 = pz * a02 - px * a22;
+            const float q20 = px * a01 - py * a00, q21 = px * a11 - py * a01, q22 = px * a12 - py * a02;
+            // TL = PA [p]x^T : TL_i0 = -pz q_i1 + py q_i2 ; TL_i1 = pz q_i0 - px q_i2 ; TL_i2 = -py q_i0 + px q_i1
+            o[0] = py * q02 - pz * q01;
+            o[1] = pz * q00 - px * q02;
+            o[2] = px * q01 - py * q00;
+            o[3] = pz * q10 - px * q12;
+            o[4] = px * q11 - py * q10;
+            o[5] = px * q21 - py * q20;
+            o[6] = q00; o[7] = q01; o[8] = q02;
+            o[9] = q10; o[10] = q11; o[11] = q12;
+            o[12] = q20; o[13] = q21; o[14] = q22;
+            o[15] = a00; o[16] = a01; o[17] = a02; o[18] = a11; o[19] = a12; o[20] = a22;
+        }
+        o[21] = py * b2 - pz * b1;
+        o[22] = pz * b0 - px * b2;
+        o[23] = px * b1 - py * b0;
+        o[24] = b0; o[25] = b1; o[26] = b2;
+    }
+    __syncthreads();
+
+    // ---- P3: subtree sums up the kinematic tree, one thread per (frame, component)
+    for (int task = tid; task < FT * NSP; task += NTHREADS) {
+        const int f = task / NSP;
+        const int k = task - f * NSP;
+        if (!WANT_H && k < 21) continue;
+        float v[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) v[l] = S.Il[f * NL + l][k];
+        const float s13 = v[19], s12 = v[18] + s13;
+        const float s11 = v[16], s10 = v[15] + s11;
+        const float s5 = v[7], s4 = v[6] + s5;
+        const float s3 = ((v[5] + v[14]) + v[17]) + ((s4 + s10) + s12);
+        const float s9 = v[13], s8 = v[12] + s9;
+        const float s7 = v[10], s6 = v[9] + s7;
+        const float s2 = ((v[4] + v[8]) + v[11]) + ((s3 + s6) + s8);
+        const float s1 = v[3] + s2;
+        const float s0 = ((v[0] + v[1]) + v[2]) + s1;
+        float* d = &S.Ij[f][0][k];
+        d[0 * NSP] = s0;  d[1 * NSP] = s1;  d[2 * NSP] = s2;   d[3 * NSP] = s3;
+        d[4 * NSP] = s4;  d[5 * NSP] = s5;  d[6 * NSP] = s6;   d[7 * NSP] = s7;
+        d[8 * NSP] = s8;  d[9 * NSP] = s9;  d[10 * NSP] = s10; d[11 * NSP] = s11;
+        d[12 * NSP] = s12; d[13 * NSP] = s13;
+    }
+    __syncthreads();   // Il is dead from here on; `out` aliases it
+
+    // ---- P4: blocks.  task (f, beta): beta < 22 angle columns, beta == 22 the translation block
+    for (int task = tid; task < FT * (NANG + 1); task += NTHREADS) {
+        const int f = task / (NANG + 1);
+        const int be = task - f * (NANG + 1);
+        float* out = S.out[f];
+        if (be == NANG) {
+            float c = 0.f;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) c += S.costp[f][l];
+            out[0] = c;
+            const float* I0 = S.Ij[f][0];
+            out[1] = I0[24]; out[2] = I0[25]; out[3] = I0[26];
+            if (WANT_H) {
+                float* H = out + 1 + NA;
+                H[upper_index(0, 0)] = I0[15]; H[upper_index(0, 1)] = I0[16]; H[upper_index(0, 2)] = I0[17];
+                H[upper_index(1, 1)] = I0[18]; H[upper_index(1, 2)] = I0[19]; H[upper_index(2, 2)] = I0[20];
+            }
+            continue;
+        }
+        const int jb = c_angle_joint[be];
+        const float* I = S.Ij[f][jb];
+        const float* tb = S.tau[f][be];
+        const float o0 = tb[0], o1 = tb[1], o2 = tb[2], v0 = tb[3], v1 = tb[4], v2 = tb[5];
+        out[1 + 3 + be] = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
+        if (!WANT_H) continue;
+        // y = I tau_beta ; I = [[TL, PA],[PA^T, A]]
+        const float yt0 = I[0] * o0 + I[1] * o1 + I[2] * o2 + I[6] * v0 + I[7] * v1 + I[8] * v2;
+        const float yt1 = I[1] * o0 + I[3] * o1 + I[4] * o2 + I[9] * v0 + I[10] * v1 + I[11] * v2;
+        const float yt2 = I[2] * o0 + I[4] * o1 + I[5] * o2 + I[12] * v0 + I[13] * v1 + I[14] * v2;
+        const float yb0 = I[6] * o0 + I[9] * o1 + I[12] * o2 + I[15] * v0 + I[16] * v1 + I[17] * v2;
+        const float yb1 = I[7] * o0 + I[10] * o1 + I[13] * o2 + I[16] * v0 + I[18] * v1 + I[19] * v2;
+        const float yb2 = I[8] * o0 + I[11] * o1 + I[14] * o2 + I[17] * v0 + I[19] * v1 + I[20] * v2;
+        float* H = out + 1 + NA;
+        const int sb = 3 + be;  // active slot of beta
+        H[upper_index(0, sb)] = yb0;
+        H[upper_index(1, sb)] = yb1;
+        H[upper_index(2, sb)] = yb2;
+        const unsigned anc = c_joint_anc[jb];
+        for (int al = 0; al < NANG; ++al) {
+            const int ja = c_angle_joint[al];
+            const int sa = 3 + al;
+            const bool a_anc_b = (anc >> ja) & 1u;              // joint(al) is an ancestor-or-self of joint(be)
+            const bool b_anc_a = (c_joint_anc[ja] >> jb) & 1u;
+            if (a_anc_b && (ja != jb || al <= be)) {
+                const float* ta = S.tau[f][al];
+                const float h = ta[0] * yt0 + ta[1] * yt1 + ta[2] * yt2 + ta[3] * yb0 + ta[4] * yb1 + ta[5] * yb2;
+                H[upper_index(min(sa, sb), max(sa, sb))] = h;
+            } else if (!a_anc_b && !b_anc_a && al < be) {
+                H[upper_index(sa, sb)] = 0.f;                  // unrelated subtrees
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P5: coalesced write-out
+    if (cost_out)
+        for (int f = tid; f < nf; f += NTHREADS) cost_out[f0 + f] = S.out[f][0];
+    if (g_out)
+        for (int i = tid; i < nf * NA; i += NTHREADS) {
+            const int f = i / NA, k = i - f * NA;
+            g_out[(size_t)f0 * NA + i] = S.out[f][1 + k];
+        }
+    if (WANT_H && H_out)
+        for (int i = tid; i < nf * NU; i += NTHREADS) {
+            const int f = i / NU, k = i - f * NU;
+            H_out[(size_t)f0 * NU + i] = S.out[f][1 + NA + k];
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// fk_project: pose_to_3d + project_points_fisheye for every camera (reprojection only).
+__global__ void __launch_bounds__(NTHREADS)
+fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, const float* __restrict__ xg,
+                  float* __restrict__ pos_out, float* __restrict__ uv_out) {
+    __shared__ float sx[FT][NA];
+    __shared__ float sp[FT][NL][3];
+    __shared__ float stau[FT][NANG][TAU_STRIDE];
+    const int tid = threadIdx.x;
+    const int f0 = blockIdx.x * FT;
+    const int nf = min(FT, n_frames - f0);
+    const int C = scene.n_cams;
+    for (int i = tid; i < FT * NA; i += NTHREADS) {
+        const int f = i / NA;
+        (&sx[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
+    }
+    __syncthreads();
+    if (tid < FT) {
+        FkWriter w{&sp[tid][0][0], &stau[tid][0][0]};
+        cheetah_fk(sx[tid], w);
+    }
+    __syncthreads();
+    const int f = tid / NL;
+    const int l = tid - f * NL;
+    if (f >= nf) return;
+    const float wx = sx[f][0] + sp[f][l][0], wy = sx[f][1] + sp[f][l][1], wz = sx[f][2] + sp[f][l][2];
+    if (pos_out) {
+        float* o = pos_out + ((size_t)(f0 + f) * NL + l) * 3;
+        o[0] = wx; o[1] = wy; o[2] = wz;
+    }
+    if (uv_out) {
+        for (int c = 0; c < C; ++c) {
+            const CamF& cam = scene.cam[c];
+            const float xc = fmaf(cam.R[0], wx, fmaf(cam.R[1], wy, fmaf(cam.R[2], wz, cam.t[0])));
+            const float yc = fmaf(cam.R[3], wx, fmaf(cam.R[4], wy, fmaf(cam.R[5], wz, cam.t[1])));
+            const float zc = fmaf(cam.R[6], wx, fmaf(cam.R[7], wy, fmaf(cam.R[8], wz, cam.t[2])));
+            ProjOut<float> pr;
+            fisheye_cam<float, false>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
+            float2 o = {pr.u + cam.cx, pr.v + cam.cy};
+            reinterpret_cast<float2*>(uv_out)[((size_t)(f0 + f) * C + c) * NL + l] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+size_t fte_eval_smem_bytes() { return sizeof(Smem); }
+
+cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                            const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    const int grid = (n_frames + FT - 1) / FT;
+    const size_t smem = sizeof(Smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fte_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (H)
+        fte_eval_kernel<true><<<grid, NTHREADS, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
+    else
+        fte_eval_kernel<false><<<grid, NTHREADS, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
+                              cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    const int grid = (n_frames + FT - 1) / FT;
+    fk_project_kernel<<<grid, NTHREADS, 0, stream>>>(scene, n_frames, x, pos, uv);
+    return cudaGetLastError();
+}
+
+}  // namespace acino

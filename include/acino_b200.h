@@ -1,0 +1,87 @@
+/*
+ * acino_b200.h - C ABI of libacino_b200.so: the B200 (sm_100a) implementation of
+ * AcinoSet's reprojection / trajectory-optimisation hot path.
+ *
+ * The reference (African-Robotics-Unit/AcinoSet) has no FFI of its own - its boundary is a
+ * set of Python callables.  Each entry point below names the reference
+ * function(s) whose arithmetic it replaces; the ctypes binding that puts these behind the
+ * reference's own names lives in acinoset_b200/_lib.py and is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error (acino_last_error() has the text);
+ *     nothing throws across the ABI;
+ *   - "_dev" entry points take DEVICE pointers and are stream-ordered (no hidden syncs);
+ *     entry points without the suffix take HOST pointers, copy in/out and synchronise;
+ *   - all arrays are dense row-major; the caller owns every buffer; the library owns only
+ *     the handle (camera table, loss constants, workspace);
+ *   - one handle per GPU; a handle is not thread-safe, different handles are independent;
+ *   - state vectors use the 25 "active" pose slots in the order of the reference's saved
+ *     result pickle (all_optimizations.py:540-556):
+ *       x,y,z, phi0,phi1,phi3, theta0..theta13, psi0,psi1,psi3,psi4,psi5.
+ */
+#ifndef ACINO_B200_H
+#define ACINO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACINO_N_ACTIVE   25    /* active pose parameters per frame                      */
+#define ACINO_N_MARKERS  20    /* cheetah markers, order of all_optimizations.py:170-178 */
+#define ACINO_N_UPPER    325   /* packed upper triangle of a 25x25 block, row-major      */
+#define ACINO_MAX_CAMS   16
+
+#define ACINO_OK              0
+#define ACINO_ERR_ARG        -1
+#define ACINO_ERR_CUDA       -2
+#define ACINO_ERR_STATE      -3
+
+typedef struct acino_handle acino_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int acino_create(acino_handle** out, int device);
+int acino_destroy(acino_handle* h);
+const char* acino_last_error(const acino_handle* h);   /* h may be NULL: last global error */
+int acino_version(void);
+/* number of kernel launches issued through this handle so far (bench.py "gpu_launches") */
+int64_t acino_launch_count(const acino_handle* h);
+
+/* ---- scene ---------------------------------------------------------------------------- */
+/* Camera table: K [C][3][3], D [C][4], R [C][3][3] (world->camera), t [C][3]; the arrays
+ * utils.load_scene returns (src/calib/utils.py:84-101), D reshaped (-1,4) as at
+ * all_optimizations.py:221. */
+int acino_set_cameras(acino_handle* h, int n_cams, const double* K, const double* D,
+                      const double* R, const double* t);
+/* Redescending-loss break points (a,b,c); default (3,10,20), all_optimizations.py:25-27. */
+int acino_set_redescending(acino_handle* h, double a, double b, double c);
+
+/* ---- FTE: residual + Jacobian evaluation (the north-star kernel) ------------------------
+ * Replaces, per frame n: pose_constraint (all_optimizations.py:359-365), measurement_constraints
+ * (:394-399) through pt3d_to_2d (:193-209), the measurement term of obj (:494-497) with
+ * misc.redescending_loss (build.py:382-395), and the automatic differentiation IPOPT's ASL
+ * does on them.
+ *   x    [N][25]        active pose state
+ *   meas [N][C][20][2]  measured pixels (u,v)
+ *   w    [N][C][20]     meas_err_weight (1/R if likelihood > thresh else 0, :302-308)
+ *   cost [N]            sum_{c,l,d} rho(w * r)
+ *   g    [N][25]        d cost / d x_n
+ *   H    [N][325]       packed upper triangle of sum psi(w r) w^2 J^T J  (psi = max(rho'/e, 1-sigma_a))
+ * Any of cost/g/H may be NULL (not written). */
+int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const float* meas,
+                       const float* w, float* cost, float* g, float* H, void* cuda_stream);
+int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* meas,
+                   const float* w, float* cost, float* g, float* H);
+
+/* Reprojection only: pose_to_3d (all_optimizations.py:186) + project_points_fisheye for every
+ * camera (calib.py:132-136; save_3d_cheetah_as_2d at all_optimizations.py:560).
+ *   pos [N][20][3] world marker positions (may be NULL), uv [N][C][20][2] pixels (may be NULL) */
+int acino_fk_project_dev(acino_handle* h, int n_frames, const float* x, float* pos, float* uv,
+                         void* cuda_stream);
+int acino_fk_project(acino_handle* h, int n_frames, const float* x, float* pos, float* uv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACINO_B200_H */

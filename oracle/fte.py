@@ -10,7 +10,7 @@ Follows /root/reference/src/all_optimizations.py
   * init_model_weights, Q      :245-252,310-315
   * obj                        :486-500   sum w_p slack_model^2 + sum redesc(w * slack_meas)
 Per-frame output of ``fte_eval``: cost_n, g_n = d cost_n / d x_n (25), and
-H_n = sum psi(e) w^2 J^T J (25x25, psi = IRLS weight of oracle/loss.py).
+H_n = sum psi(e) w^2 J^T J (25x25, psi = curvature weight of oracle/loss.py).
 """
 import numpy as np
 

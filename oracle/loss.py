@@ -58,20 +58,23 @@ def redescending_dloss(err, a=REDESC_A, b=REDESC_B, c=REDESC_C):
 
 
 def redescending_irls_weight(err, a=REDESC_A, b=REDESC_B, c=REDESC_C):
-    """Gauss-Newton curvature weight psi(err) = max(rho'(e)/e, 0), psi(0) = 0.
+    """Gauss-Newton curvature weight psi(e) = max(rho'(e)/e, 1 - sigma_a(e)), e = |err|.
 
-    This is the IRLS (iteratively re-weighted least squares) majoriser weight of the
-    robust term; clamped at 0 where the literal blend has negative slope (at the cusp
-    next to 0 and beyond c).  It is a solver design choice of the B200 LM loop (the
-    reference hands the exact objective to IPOPT with an L-BFGS Hessian,
+    rho'/e is the IRLS (iteratively re-weighted least squares) majoriser weight of the
+    robust term; it is floored by the frozen-gate curvature of the quadratic piece
+    (1 - sigma_a) e^2/2.  The floor takes over for e < ~0.45 where the literal blend has
+    a tiny cusp (rho'(0+) = -0.0616 < 0) that makes rho'/e negative and ill-conditioned;
+    psi >= 0 everywhere and psi -> 0 beyond c.  This is a solver design choice of the B200
+    LM loop (the reference hands the exact objective to IPOPT with an L-BFGS Hessian,
     all_optimizations.py:515); cost and gradient are exact.
     """
     err = np.asarray(err, dtype=np.float64)
     e = np.abs(err)
     _, d, _ = redescending_dloss(e, a, b, c)
+    floor = 1.0 - func_step(a, e)
     with np.errstate(divide="ignore", invalid="ignore"):
-        w = np.where(e > 0, d / np.where(e > 0, e, 1.0), 0.0)
-    return np.maximum(w, 0.0)
+        w = np.where(e > 0, d / np.where(e > 0, e, 1.0), -np.inf)
+    return np.maximum(w, floor)
 
 
 def cauchy_cost(f, f_scale=1.0):
