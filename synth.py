@@ -61,10 +61,11 @@ def make_trajectory(N, rng, fps=FPS, start=0):
 
 
 def make_measurements(P, cams, project, rng, noise_px=2.0, outlier_frac=0.05, low_lik_frac=0.10,
-                      max_theta_deg=60.0):
+                      max_theta_deg=60.0, uv_all=None):
     """P (N,L,3) world marker positions -> meas (N,C,L,2), likelihood (N,C,L).
 
-    project(P, K, D, R, t) -> (N,L,2).  N(0, noise_px) noise; outlier_frac of (n,c,l)
+    project(P, K, D, R, t) -> (N,L,2) (or pass uv_all (N,C,L,2) precomputed, e.g. by the
+    fk_project CUDA kernel).  N(0, noise_px) noise; outlier_frac of (n,c,l)
     replaced by uniform-in-image outliers; likelihood ~ U(0.5,1) except low_lik_frac set
     to U(0,0.5); any point with theta > max_theta, behind the camera or outside the image
     gets likelihood 0.
@@ -77,7 +78,10 @@ def make_measurements(P, cams, project, rng, noise_px=2.0, outlier_frac=0.05, lo
     low = rng.uniform(0, 1, (N, C, L)) < low_lik_frac
     lik[low] = rng.uniform(0.0, 0.5, int(low.sum()))
     for c in range(C):
-        uv = np.asarray(project(P, K[c], D[c], R[c], t[c]), dtype=np.float64)
+        if uv_all is not None:
+            uv = np.asarray(uv_all[:, c], dtype=np.float64)
+        else:
+            uv = np.asarray(project(P, K[c], D[c], R[c], t[c]), dtype=np.float64)
         Xc = P @ R[c].T + t[c]
         theta = np.arctan2(np.hypot(Xc[..., 0], Xc[..., 1]), Xc[..., 2])
         ok = (theta < np.deg2rad(max_theta_deg)) & (Xc[..., 2] > 0)
@@ -91,13 +95,20 @@ def make_measurements(P, cams, project, rng, noise_px=2.0, outlier_frac=0.05, lo
     return meas, lik
 
 
-def make_fte_problem(N, fk, project, seed=0, dlc_thresh=0.5, init_sigma=0.05, cams=None, start=0):
-    """Config 2/3/5 of BASELINE.json: returns dict(x_true, x0, meas, lik, w, cams, Ts)."""
+def make_fte_problem(N, fk, project, seed=0, dlc_thresh=0.5, init_sigma=0.05, cams=None, start=0,
+                     reproject=None):
+    """Config 2/3/5 of BASELINE.json: returns dict(x_true, x0, meas, lik, w, cams, Ts).
+
+    Either (fk, project) callables, or reproject(x) -> (P (N,L,3), uv (N,C,L,2))."""
     rng = np.random.default_rng(seed)
     cams = load_dummy_scene() if cams is None else cams
     x_true = make_trajectory(N, rng, start=start)
-    P = np.asarray(fk(x_true), dtype=np.float64)
-    meas, lik = make_measurements(P, cams, project, rng)
+    if reproject is not None:
+        P, uv_all = reproject(x_true)
+        meas, lik = make_measurements(np.asarray(P, dtype=np.float64), cams, None, rng, uv_all=uv_all)
+    else:
+        P = np.asarray(fk(x_true), dtype=np.float64)
+        meas, lik = make_measurements(P, cams, project, rng)
     w = np.where(lik > dlc_thresh, 1.0 / 5.0, 0.0)  # all_optimizations.py:243,302-308
     x0 = x_true + rng.normal(0.0, init_sigma, x_true.shape)
     return dict(x_true=x_true, x0=x0, meas=meas, lik=lik, w=w, cams=cams, Ts=1.0 / FPS,
