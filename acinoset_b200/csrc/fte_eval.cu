@@ -24,35 +24,74 @@
 // d p_l / d angle = omega x (p_l - pivot) = B_l tau (twist about the head point), so
 // H = sum_l J_l^T A_l J_l collapses to tau_a^T I_{deeper subtree} tau_b: ~4 kFMA instead of
 // ~8 kFMA per frame for the chain rule and no 60x25 Jacobian is ever materialised.
+#include <cstdlib>
+
 #include "acino_common.cuh"
 
 namespace acino {
 
-constexpr int FT = 16;                 // frames per CTA
-constexpr int NTHREADS = FT * NL;      // 320: one thread per (frame, marker) in P2
-constexpr int TAU_STRIDE = 7;          // 6 padded to 7: conflict-free across angle-lanes
-constexpr int OUT_STRIDE = 1 + NA + NU;  // 351 floats per frame: cost | g | H
+constexpr int TAU_STRIDE = 8;           // (omega, v) padded to 8 floats: one LDS.128 + one LDS.64
+constexpr int TAUF = NANG * TAU_STRIDE + 4;  // per-frame stride 180 = 20 (mod 32): conflict-free across frames
+constexpr int N_PAIR = NANG * (NANG + 1) / 2;  // 253 unordered angle pairs (incl. the diagonal)
 
 // joint of each angle slot (angle slot s <-> active slot 3+s):
 // phi0 phi1 phi3 | theta0..13 | psi0 psi1 psi3 psi4 psi5
-__constant__ int c_angle_joint[NANG] = {0, 1, 3, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 0, 1, 3, 4, 5};
-// ancestors-or-self of each joint as a 14-bit mask (rotation chain all_optimizations.py:101-128)
-__constant__ unsigned c_joint_anc[NJ] = {
-    0x0001, 0x0003, 0x0007, 0x000F, 0x001F, 0x003F,            // 0..5 : 0,1,2,3,4,5 chain
-    0x0047, 0x00C7,                                            // 6 (2<-6), 7 (6<-7)
-    0x0107, 0x0307,                                            // 8, 9
-    0x040F, 0x0C0F,                                            // 10 (3<-10), 11
-    0x100F, 0x300F};                                           // 12, 13
+constexpr int k_angle_joint[NANG] = {0, 1, 3, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 0, 1, 3, 4, 5};
+// parent of each joint in the rotation chain (all_optimizations.py:101-128)
+constexpr int k_joint_parent[NJ] = {-1, 0, 1, 2, 3, 4, 2, 6, 2, 8, 3, 10, 3, 12};
 
+constexpr bool joint_is_anc(int a, int k) {  // a ancestor-or-self of k
+    while (k >= 0) {
+        if (k == a) return true;
+        k = k_joint_parent[k];
+    }
+    return false;
+}
+
+// One entry per unordered pair of angle slots.  Related pairs (one joint is an ancestor-or-self of
+// the other): H = tau_al . y_be with `be` the deeper angle; bits 0-4 al, 5-9 be, 10-18 packed index.
+// Unrelated pairs (disjoint subtrees) are structural zeros: bit 31 set.  Zeros are sorted last.
+struct PairTable {
+    unsigned e[N_PAIR];
+    int joint[NANG];
+};
+constexpr PairTable make_pair_table() {
+    PairTable t{};
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int be = 0; be < NANG; ++be)
+            for (int al = 0; al < NANG; ++al) {
+                const int ja = k_angle_joint[al], jb = k_angle_joint[be];
+                const bool a_anc_b = joint_is_anc(ja, jb), b_anc_a = joint_is_anc(jb, ja);
+                const int sa = 3 + al, sb = 3 + be;
+                const int lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
+                const unsigned idx = (unsigned)(lo * NA - (lo * (lo - 1)) / 2 + (hi - lo));
+                if (pass == 0 && a_anc_b && (ja != jb || al <= be))
+                    t.e[n++] = (unsigned)al | ((unsigned)be << 5) | (idx << 10);
+                if (pass == 1 && !a_anc_b && !b_anc_a && al < be) t.e[n++] = 0x80000000u | (idx << 10);
+            }
+    for (int a = 0; a < NANG; ++a) t.joint[a] = k_angle_joint[a];
+    return t;
+}
+__constant__ PairTable c_tab = make_pair_table();
+
+template <int FT>
 struct __align__(16) Smem {
     float x[FT][NA];                   // state
     float p[FT][NL][3];                // marker positions relative to the head point
-    float tau[FT][NANG][TAU_STRIDE];   // (omega, v = pivot x omega) per angle
+    float2 sc[FT][NANG];               // (sin, cos) of every angle
     float costp[FT][NL];               // per-(frame, marker) cost partials
+    unsigned tab[N_PAIR + 3];          // pair table (copy of c_tab.e)
     float Ij[FT][NJ][NSP];             // subtree spatial inertia + wrench per joint
+    __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     union {
         float Il[FT * NL][NSP];        // per-marker spatial inertia + wrench   (P2 -> P3)
-        float out[FT][OUT_STRIDE + 1]; // staged {cost, g, H}                   (P4 -> P5)
+        struct {                       // staged outputs in their global layout  (P4 -> P5)
+            float H[FT][NU];
+            float g[FT][NA];
+            float cost[FT];
+            __align__(16) float y[FT][TAUF];   // y_beta = I_subtree tau_beta, stride 8
+        } o;
     };
 };
 
@@ -120,10 +159,14 @@ enum { A_PHI0 = 0, A_PHI1 = 1, A_PHI3 = 2, A_TH0 = 3, A_PSI0 = 17, A_PSI1 = 18, 
 // R_k_I = R_parent_I Ry_a(theta) Rx_a(phi) Rz_a(psi), and the world axis of each angle is the
 // matching column of the partially composed matrix (theta: column 1 before Ry; phi: column 0
 // after Ry; psi: column 2 after Rx).
-__device__ __forceinline__ void cheetah_fk(const float* __restrict__ x, const FkWriter& w) {
+__device__ __forceinline__ void cheetah_fk(const float2* __restrict__ sc, const FkWriter& w) {
     float sn[NANG], cs[NANG];
 #pragma unroll
-    for (int i = 0; i < NANG; ++i) sincosf(x[3 + i], &sn[i], &cs[i]);
+    for (int i = 0; i < NANG; ++i) {
+        const float2 v = sc[i];
+        sn[i] = v.x;
+        cs[i] = v.y;
+    }
 #define TH(k) sn[A_TH0 + (k)], cs[A_TH0 + (k)]
     const Col3 zero = {0.f, 0.f, 0.f};
     // joint 0: head
@@ -225,30 +268,41 @@ __device__ __forceinline__ void cheetah_fk(const float* __restrict__ x, const Fk
 #undef TH
 }
 
-template <bool WANT_H>
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int FT, bool WANT_H>
+__global__ void __launch_bounds__(FT * NL, (FT == 8) ? 5 : 2)
 fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
                 const float* __restrict__ xg, const float* __restrict__ meas,
                 const float* __restrict__ wts, float* __restrict__ cost_out,
                 float* __restrict__ g_out, float* __restrict__ H_out) {
+    constexpr int NT = FT * NL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    Smem<FT>& S = *reinterpret_cast<Smem<FT>*>(smem_raw);
     const int tid = threadIdx.x;
     const int f0 = blockIdx.x * FT;
     const int nf = min(FT, n_frames - f0);
     const int C = scene.n_cams;
 
-    // ---- P0: state -> smem (coalesced), zero-fill frames past the end
-    for (int i = tid; i < FT * NA; i += NTHREADS) {
+    // ---- P0: state -> smem (coalesced), zero-fill frames past the end; pair table -> smem
+    for (int i = tid; i < FT * NA; i += NT) {
         const int f = i / NA;
         (&S.x[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
     }
+    for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
     __syncthreads();
 
-    // ---- P1: forward kinematics, one thread per frame
+    // ---- P1a: sin/cos of the 22 angles, one thread per (angle, frame)
+    for (int t = tid; t < FT * NANG; t += NT) {
+        const int a = t / FT, f = t - a * FT;
+        float sn, cs;
+        sincosf(S.x[f][3 + a], &sn, &cs);
+        S.sc[f][a] = make_float2(sn, cs);
+    }
+    __syncthreads();
+
+    // ---- P1b: rotation chain, one thread per frame
     if (tid < FT) {
-        FkWriter w{&S.p[tid][0][0], &S.tau[tid][0][0]};
-        cheetah_fk(S.x[tid], w);
+        FkWriter w{&S.p[tid][0][0], &S.tau[tid][0]};
+        cheetah_fk(S.sc[tid], w);
     }
     __syncthreads();
 
@@ -337,10 +391,10 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
     }
     __syncthreads();
 
-    // ---- P3: subtree sums up the kinematic tree, one thread per (frame, component)
-    for (int task = tid; task < FT * NSP; task += NTHREADS) {
-        const int f = task / NSP;
-        const int k = task - f * NSP;
+    // ---- P3: subtree sums up the kinematic tree, one thread per (component, frame)
+    for (int task = tid; task < FT * NSP; task += NT) {
+        const int k = task / FT;
+        const int f = task - k * FT;
         if (!WANT_H && k < 21) continue;
         float v[NL];
 #pragma unroll
@@ -360,32 +414,33 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
         d[8 * NSP] = s8;  d[9 * NSP] = s9;  d[10 * NSP] = s10; d[11 * NSP] = s11;
         d[12 * NSP] = s12; d[13 * NSP] = s13;
     }
-    __syncthreads();   // Il is dead from here on; `out` aliases it
+    __syncthreads();   // Il is dead from here on; the staged outputs alias it
 
-    // ---- P4: blocks.  task (f, beta): beta < 22 angle columns, beta == 22 the translation block
-    for (int task = tid; task < FT * (NANG + 1); task += NTHREADS) {
-        const int f = task / (NANG + 1);
-        const int be = task - f * (NANG + 1);
-        float* out = S.out[f];
+    // ---- P4a: y_beta = I_subtree(beta) tau_beta, g, translation rows.  task (beta, frame);
+    //      beta == 22 is the translation block
+    for (int task = tid; task < FT * (NANG + 1); task += NT) {
+        const int be = task / FT;
+        const int f = task - be * FT;
+        float* g = S.o.g[f];
+        float* H = S.o.H[f];
         if (be == NANG) {
             float c = 0.f;
 #pragma unroll
             for (int l = 0; l < NL; ++l) c += S.costp[f][l];
-            out[0] = c;
+            S.o.cost[f] = c;
             const float* I0 = S.Ij[f][0];
-            out[1] = I0[24]; out[2] = I0[25]; out[3] = I0[26];
+            g[0] = I0[24]; g[1] = I0[25]; g[2] = I0[26];
             if (WANT_H) {
-                float* H = out + 1 + NA;
                 H[upper_index(0, 0)] = I0[15]; H[upper_index(0, 1)] = I0[16]; H[upper_index(0, 2)] = I0[17];
                 H[upper_index(1, 1)] = I0[18]; H[upper_index(1, 2)] = I0[19]; H[upper_index(2, 2)] = I0[20];
             }
             continue;
         }
-        const int jb = c_angle_joint[be];
-        const float* I = S.Ij[f][jb];
-        const float* tb = S.tau[f][be];
-        const float o0 = tb[0], o1 = tb[1], o2 = tb[2], v0 = tb[3], v1 = tb[4], v2 = tb[5];
-        out[1 + 3 + be] = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
+        const float* I = S.Ij[f][c_tab.joint[be]];
+        const float4 t0 = *reinterpret_cast<const float4*>(&S.tau[f][be * TAU_STRIDE]);
+        const float2 t1 = *reinterpret_cast<const float2*>(&S.tau[f][be * TAU_STRIDE + 4]);
+        const float o0 = t0.x, o1 = t0.y, o2 = t0.z, v0 = t0.w, v1 = t1.x, v2 = t1.y;
+        g[3 + be] = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
         if (!WANT_H) continue;
         // y = I tau_beta ; I = [[TL, PA],[PA^T, A]]
         const float yt0 = I[0] * o0 + I[1] * o1 + I[2] * o2 + I[6] * v0 + I[7] * v1 + I[8] * v2;
@@ -394,63 +449,91 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
         const float yb0 = I[6] * o0 + I[9] * o1 + I[12] * o2 + I[15] * v0 + I[16] * v1 + I[17] * v2;
         const float yb1 = I[7] * o0 + I[10] * o1 + I[13] * o2 + I[16] * v0 + I[18] * v1 + I[19] * v2;
         const float yb2 = I[8] * o0 + I[11] * o1 + I[14] * o2 + I[17] * v0 + I[19] * v1 + I[20] * v2;
-        float* H = out + 1 + NA;
-        const int sb = 3 + be;  // active slot of beta
-        H[upper_index(0, sb)] = yb0;
-        H[upper_index(1, sb)] = yb1;
-        H[upper_index(2, sb)] = yb2;
-        const unsigned anc = c_joint_anc[jb];
-        for (int al = 0; al < NANG; ++al) {
-            const int ja = c_angle_joint[al];
-            const int sa = 3 + al;
-            const bool a_anc_b = (anc >> ja) & 1u;              // joint(al) is an ancestor-or-self of joint(be)
-            const bool b_anc_a = (c_joint_anc[ja] >> jb) & 1u;
-            if (a_anc_b && (ja != jb || al <= be)) {
-                const float* ta = S.tau[f][al];
-                const float h = ta[0] * yt0 + ta[1] * yt1 + ta[2] * yt2 + ta[3] * yb0 + ta[4] * yb1 + ta[5] * yb2;
-                H[upper_index(min(sa, sb), max(sa, sb))] = h;
-            } else if (!a_anc_b && !b_anc_a && al < be) {
-                H[upper_index(sa, sb)] = 0.f;                  // unrelated subtrees
+        *reinterpret_cast<float4*>(&S.o.y[f][be * TAU_STRIDE]) = make_float4(yt0, yt1, yt2, yb0);
+        *reinterpret_cast<float2*>(&S.o.y[f][be * TAU_STRIDE + 4]) = make_float2(yb1, yb2);
+        const int sb = 3 + be;  // active slot of beta: rows 0..2 (translation) of column sb
+        H[sb] = yb0;
+        H[NA + sb - 1] = yb1;
+        H[2 * NA + sb - 3] = yb2;
+    }
+    __syncthreads();
+
+    // ---- P4b: one task per (angle pair, frame): H[al][be] = tau_al . y_be, or a structural zero
+    if (WANT_H) {
+        for (int task = tid; task < FT * N_PAIR; task += NT) {
+            const int p = task / FT;
+            const int f = task - p * FT;
+            const unsigned e = S.tab[p];
+            const int idx = (e >> 10) & 0x1FF;
+            float h = 0.f;
+            if (!(e >> 31)) {
+                const int al = e & 31, be = (e >> 5) & 31;
+                const float4 a0 = *reinterpret_cast<const float4*>(&S.tau[f][al * TAU_STRIDE]);
+                const float2 a1 = *reinterpret_cast<const float2*>(&S.tau[f][al * TAU_STRIDE + 4]);
+                const float4 y0 = *reinterpret_cast<const float4*>(&S.o.y[f][be * TAU_STRIDE]);
+                const float2 y1 = *reinterpret_cast<const float2*>(&S.o.y[f][be * TAU_STRIDE + 4]);
+                h = a0.x * y0.x + a0.y * y0.y + a0.z * y0.z + a0.w * y0.w + a1.x * y1.x + a1.y * y1.y;
             }
+            S.o.H[f][idx] = h;
         }
     }
     __syncthreads();
 
-    // ---- P5: coalesced write-out
+    // ---- P5: write-out.  The staged blocks have the global layout: straight vector copies
     if (cost_out)
-        for (int f = tid; f < nf; f += NTHREADS) cost_out[f0 + f] = S.out[f][0];
-    if (g_out)
-        for (int i = tid; i < nf * NA; i += NTHREADS) {
-            const int f = i / NA, k = i - f * NA;
-            g_out[(size_t)f0 * NA + i] = S.out[f][1 + k];
+        for (int f = tid; f < nf; f += NT) cost_out[f0 + f] = S.o.cost[f];
+    if (g_out) {
+        float* dst = g_out + (size_t)f0 * NA;
+        const float* src = &S.o.g[0][0];
+        if (nf == FT) {
+            for (int i = tid; i < FT * NA / 4; i += NT)
+                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+            for (int i = tid; i < nf * NA; i += NT) dst[i] = src[i];
         }
-    if (WANT_H && H_out)
-        for (int i = tid; i < nf * NU; i += NTHREADS) {
-            const int f = i / NU, k = i - f * NU;
-            H_out[(size_t)f0 * NU + i] = S.out[f][1 + NA + k];
+    }
+    if (WANT_H && H_out) {
+        float* dst = H_out + (size_t)f0 * NU;
+        const float* src = &S.o.H[0][0];
+        if (nf == FT) {
+            for (int i = tid; i < FT * NU / 4; i += NT)
+                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+            for (int i = tid; i < nf * NU; i += NT) dst[i] = src[i];
         }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // fk_project: pose_to_3d + project_points_fisheye for every camera (reprojection only).
-__global__ void __launch_bounds__(NTHREADS)
+constexpr int FTP = 8;
+__global__ void __launch_bounds__(FTP * NL)
 fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, const float* __restrict__ xg,
                   float* __restrict__ pos_out, float* __restrict__ uv_out) {
-    __shared__ float sx[FT][NA];
-    __shared__ float sp[FT][NL][3];
-    __shared__ float stau[FT][NANG][TAU_STRIDE];
+    constexpr int NT = FTP * NL;
+    __shared__ float sx[FTP][NA];
+    __shared__ float2 ssc[FTP][NANG];
+    __shared__ float sp[FTP][NL][3];
+    __shared__ __align__(16) float stau[FTP][TAUF];
     const int tid = threadIdx.x;
-    const int f0 = blockIdx.x * FT;
-    const int nf = min(FT, n_frames - f0);
+    const int f0 = blockIdx.x * FTP;
+    const int nf = min(FTP, n_frames - f0);
     const int C = scene.n_cams;
-    for (int i = tid; i < FT * NA; i += NTHREADS) {
+    for (int i = tid; i < FTP * NA; i += NT) {
         const int f = i / NA;
         (&sx[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
     }
     __syncthreads();
-    if (tid < FT) {
-        FkWriter w{&sp[tid][0][0], &stau[tid][0][0]};
-        cheetah_fk(sx[tid], w);
+    for (int t = tid; t < FTP * NANG; t += NT) {
+        const int a = t / FTP, f = t - a * FTP;
+        float sn, cs;
+        sincosf(sx[f][3 + a], &sn, &cs);
+        ssc[f][a] = make_float2(sn, cs);
+    }
+    __syncthreads();
+    if (tid < FTP) {
+        FkWriter w{&sp[tid][0][0], &stau[tid][0]};
+        cheetah_fk(ssc[tid], w);
     }
     __syncthreads();
     const int f = tid / NL;
@@ -476,33 +559,47 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 }
 
 // ------------------------------------------------------------------------------------------
-size_t fte_eval_smem_bytes() { return sizeof(Smem); }
-
-cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                            const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
-    if (n_frames <= 0) return cudaSuccess;
+template <int FT>
+static cudaError_t launch_fte_eval_ft(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                                      const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     const int grid = (n_frames + FT - 1) / FT;
-    const size_t smem = sizeof(Smem);
+    const size_t smem = sizeof(Smem<FT>);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fte_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fte_eval_kernel<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (H)
-        fte_eval_kernel<true><<<grid, NTHREADS, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, true><<<grid, FT * NL, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
     else
-        fte_eval_kernel<false><<<grid, NTHREADS, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, false><<<grid, FT * NL, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
     return cudaGetLastError();
+}
+
+static int g_ft = 8;   // frames per CTA (8 or 16); ACINO_FTE_FT overrides for experiments
+
+cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                            const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    static bool env_read = false;
+    if (!env_read) {
+        const char* e = getenv("ACINO_FTE_FT");
+        if (e && atoi(e) == 16) g_ft = 16;
+        if (e && atoi(e) == 8) g_ft = 8;
+        env_read = true;
+    }
+    if (g_ft == 16) return launch_fte_eval_ft<16>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    return launch_fte_eval_ft<8>(scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    const int grid = (n_frames + FT - 1) / FT;
-    fk_project_kernel<<<grid, NTHREADS, 0, stream>>>(scene, n_frames, x, pos, uv);
+    const int grid = (n_frames + FTP - 1) / FTP;
+    fk_project_kernel<<<grid, FTP * NL, 0, stream>>>(scene, n_frames, x, pos, uv);
     return cudaGetLastError();
 }
 
