@@ -51,6 +51,14 @@ def _load():
     lib.acino_fk_project_dev.restype = ci
     lib.acino_fk_project.argtypes = [vp, ci, vp, vp, vp]
     lib.acino_fk_project.restype = ci
+    lib.acino_project_points.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
+    lib.acino_project_points.restype = ci
+    lib.acino_undistort_points.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.acino_undistort_points.restype = ci
+    lib.acino_triangulate_points.argtypes = [vp, ci] + [vp] * 11
+    lib.acino_triangulate_points.restype = ci
+    lib.acino_triangulate_pairwise.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+    lib.acino_triangulate_pairwise.restype = ci
     return lib
 
 
@@ -60,7 +68,8 @@ lib = _load()
 EXPORTED = [
     "acino_create", "acino_destroy", "acino_last_error", "acino_version", "acino_launch_count",
     "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
-    "acino_fk_project_dev", "acino_fk_project",
+    "acino_fk_project_dev", "acino_fk_project", "acino_project_points", "acino_undistort_points",
+    "acino_triangulate_points", "acino_triangulate_pairwise",
 ]
 
 
@@ -146,6 +155,56 @@ class Handle:
         uv = np.empty((N, self.n_cams, N_MARKERS, 2), np.float32) if want_uv else None
         self._check(lib.acino_fk_project(self._h, N, _np_ptr(x), _np_ptr(pos), _np_ptr(uv)), "acino_fk_project")
         return pos, uv
+
+    # ---- camera geometry (fp64, host buffers)
+    @staticmethod
+    def _cam(K, D, R=None, t=None):
+        K = _host(K, np.float64).reshape(9)
+        D = _host(D, np.float64).reshape(4)
+        R = None if R is None else _host(R, np.float64).reshape(9)
+        t = None if t is None else _host(t, np.float64).reshape(3)
+        return K, D, R, t
+
+    def project_points(self, X, K, D, R, t):
+        X = _host(X, np.float64).reshape(-1, 3)
+        K, D, R, t = self._cam(K, D, R, t)
+        uv = np.empty((X.shape[0], 2), np.float64)
+        self._check(lib.acino_project_points(self._h, X.shape[0], _np_ptr(X), _np_ptr(K), _np_ptr(D), _np_ptr(R),
+                                             _np_ptr(t), _np_ptr(uv)), "acino_project_points")
+        return uv
+
+    def undistort_points(self, uv, K, D):
+        uv = _host(uv, np.float64).reshape(-1, 2)
+        K, D, _, _ = self._cam(K, D)
+        out = np.empty_like(uv)
+        self._check(lib.acino_undistort_points(self._h, uv.shape[0], _np_ptr(uv), _np_ptr(K), _np_ptr(D), _np_ptr(out)),
+                    "acino_undistort_points")
+        return out
+
+    def triangulate_points(self, uv1, uv2, cam1, cam2):
+        uv1 = _host(uv1, np.float64).reshape(-1, 2)
+        uv2 = _host(uv2, np.float64).reshape(-1, 2)
+        if uv1.shape != uv2.shape:
+            raise ValueError("img_pts_1 and img_pts_2 must hold the same number of points")
+        K1, D1, R1, t1 = self._cam(*cam1)
+        K2, D2, R2, t2 = self._cam(*cam2)
+        X = np.empty((uv1.shape[0], 3), np.float64)
+        self._check(lib.acino_triangulate_points(self._h, uv1.shape[0], _np_ptr(uv1), _np_ptr(uv2), _np_ptr(K1),
+                                                 _np_ptr(D1), _np_ptr(R1), _np_ptr(t1), _np_ptr(K2), _np_ptr(D2),
+                                                 _np_ptr(R2), _np_ptr(t2), _np_ptr(X)), "acino_triangulate_points")
+        return X
+
+    def triangulate_pairwise(self, uv, valid):
+        uv = _host(uv, np.float64)
+        N, C, L, _ = uv.shape
+        if C != self.n_cams:
+            raise ValueError(f"uv has {C} cameras, the handle has {self.n_cams}")
+        valid = _host(valid, np.uint8, (N, C, L))
+        pos = np.empty((N, L, 3), np.float64)
+        cnt = np.empty((N, L), np.int32)
+        self._check(lib.acino_triangulate_pairwise(self._h, N, L, _np_ptr(uv), _np_ptr(valid), _np_ptr(pos), _np_ptr(cnt)),
+                    "acino_triangulate_pairwise")
+        return pos, cnt
 
     # ---- device-pointer API (torch tensors on this handle's device; stream-ordered)
     def fte_eval_dev(self, x, meas, w, cost=None, g=None, H=None, stream=None):

@@ -1,0 +1,79 @@
+"""Drop-in camera-geometry entry points with the reference's names and signatures
+(/root/reference/src/calib/calib.py), running on libacino_b200.so.
+
+    project_points_fisheye(obj_pts, k, d, r, t) -> (n,2) float64            calib.py:132-136
+    triangulate_points_fisheye(img_pts_1, img_pts_2, k1,d1,r1,t1, k2,d2,r2,t2) -> (n,3)   :121-130
+    get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr, triangulate_func)
+        -> DataFrame[frame, marker, x, y, z]                                :394-423
+The SBA entry points of the same reference module live in acinoset_b200.sba and are re-exported
+here under their reference names.
+"""
+import numpy as np
+
+from . import fte as _fte
+
+
+def project_points_fisheye(obj_pts, k, d, r, t, device=0):
+    """Fisheye projection of (n,3) or (3,) world points; d may be (4,) or (4,1), t (3,1) or (3,).
+    No geometry validation: a point behind the camera is projected like any other (as in the
+    reference)."""
+    obj_pts = np.asarray(obj_pts, dtype=np.float64).reshape((-1, 3))
+    return _fte.get_handle(device).project_points(obj_pts, k, np.asarray(d).reshape(-1)[:4], r, t)
+
+
+def undistort_points_fisheye(pts, k, d, device=0):
+    """cv2.fisheye.undistortPoints(pts, k, d) (normalised coordinates, default criteria)."""
+    pts = np.asarray(pts, dtype=np.float64)
+    out = _fte.get_handle(device).undistort_points(pts.reshape(-1, 2), k, np.asarray(d).reshape(-1)[:4])
+    return out.reshape(pts.shape)
+
+
+def triangulate_points_fisheye(img_pts_1, img_pts_2, k1, d1, r1, t1, k2, d2, r2, t2, device=0):
+    """Two-view DLT after fisheye undistortion; inputs of any shape are read as (-1,2);
+    a single point returns shape (1,3) (calib.py:293-296)."""
+    h = _fte.get_handle(device)
+    return h.triangulate_points(np.asarray(img_pts_1, dtype=np.float64).reshape(-1, 2),
+                                np.asarray(img_pts_2, dtype=np.float64).reshape(-1, 2),
+                                (k1, np.asarray(d1).reshape(-1)[:4], r1, t1),
+                                (k2, np.asarray(d2).reshape(-1)[:4], r2, t2))
+
+
+def triangulate_pairwise_dense(uv, valid, k_arr, d_arr, r_arr, t_arr, device=0):
+    """Dense-tensor TRI: uv (N,C,L,2), valid (N,C,L) -> (pos (N,L,3) NaN-filled, count (N,L))."""
+    h = _fte.set_scene(k_arr, d_arr, r_arr, t_arr, device)
+    return h.triangulate_pairwise(uv, valid)
+
+
+def get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr, triangulate_func=None, device=0):
+    """Reference signature.  ``triangulate_func`` is accepted for compatibility; the adjacent
+    pairs (i, i+1) are triangulated by one fused kernel (undistort + DLT + fixed-order mean).
+    Prints the same "Found N pairwise points ..." lines as the reference."""
+    import pandas as pd
+
+    df = points_2d_df
+    n_cameras = len(k_arr)
+    if len(df) and "lab" in str(df["frame"].iloc[0]):   # calib.py:398-400 (label-file frame names)
+        df = df.copy()
+        df["frame"] = df["frame"].str.replace(r".*img", "", regex=True).str.replace(".png", "", regex=False)
+    frames, f_idx = np.unique(df["frame"].to_numpy(), return_inverse=True)
+    markers, m_idx = np.unique(df["marker"].to_numpy().astype(str), return_inverse=True)
+    cams = df["camera"].to_numpy().astype(np.int64)
+    N, L = len(frames), len(markers)
+    uv = np.zeros((N, n_cameras, L, 2), np.float64)
+    valid = np.zeros((N, n_cameras, L), np.uint8)
+    inside = (cams >= 0) & (cams < n_cameras)
+    uv[f_idx[inside], cams[inside], m_idx[inside], 0] = df["x"].to_numpy(dtype=np.float64)[inside]
+    uv[f_idx[inside], cams[inside], m_idx[inside], 1] = df["y"].to_numpy(dtype=np.float64)[inside]
+    valid[f_idx[inside], cams[inside], m_idx[inside]] = 1
+    for c in range(n_cameras - 1):
+        n_pair = int(np.count_nonzero(valid[:, c] & valid[:, c + 1]))
+        if n_pair:
+            print(f"Found {n_pair} pairwise points between camera {c} and {c + 1}")
+        else:
+            print(f"No pairwise points between camera {c} and {c + 1}")
+    if N * L == 0:
+        return pd.DataFrame(columns=["frame", "marker", "x", "y", "z"])
+    pos, cnt = triangulate_pairwise_dense(uv, valid, k_arr, d_arr, r_arr, t_arr, device)
+    fi, mi = np.nonzero(cnt > 0)
+    return pd.DataFrame({"frame": frames[fi], "marker": markers[mi],
+                         "x": pos[fi, mi, 0], "y": pos[fi, mi, 1], "z": pos[fi, mi, 2]})

@@ -11,6 +11,12 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
                             const float* w, float* cost, float* g, float* H, cudaStream_t stream);
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream);
+cudaError_t launch_project_points_f64(const CamD& cam, int n, const double* X, double* uv, cudaStream_t s);
+cudaError_t launch_undistort_points_f64(const CamD& cam, int n, const double* uv, double* out, cudaStream_t s);
+cudaError_t launch_triangulate_points_f64(const CamD& c1, const CamD& c2, int n, const double* uv1, const double* uv2,
+                                          double* out, cudaStream_t s);
+cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_frames, int L, const double* uv,
+                                            const unsigned char* valid, double* pos, int* count, cudaStream_t s);
 }  // namespace acino
 
 using namespace acino;
@@ -215,6 +221,106 @@ int acino_fk_project(acino_handle* h, int n_frames, const float* x, float* pos, 
     h->launches += 1;
     if (pos) CK(cudaMemcpyAsync(pos, dp, np * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (uv) CK(cudaMemcpyAsync(uv, du, nu * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+static CamD make_cam(const double* K, const double* D, const double* R, const double* t) {
+    CamD c;
+    for (int i = 0; i < 9; ++i) c.R[i] = R ? R[i] : (i % 4 == 0 ? 1.0 : 0.0);
+    for (int i = 0; i < 3; ++i) c.t[i] = t ? t[i] : 0.0;
+    for (int i = 0; i < 4; ++i) c.D[i] = D[i];
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    return c;
+}
+
+int acino_project_points(acino_handle* h, int n, const double* X, const double* K, const double* D, const double* R,
+                         const double* t, double* uv) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_project_points: NULL handle");
+    if (n < 0 || !K || !D || !R || !t || (n > 0 && (!X || !uv))) return fail(h, ACINO_ERR_ARG, "acino_project_points: bad arguments");
+    if (n == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nx = pad64((size_t)n * 3), nu = (size_t)n * 2;
+    int rc = ensure_ws(h, (nx + nu) * sizeof(double));
+    if (rc) return rc;
+    double* dX = (double*)h->ws;
+    double* dU = dX + nx;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dX, X, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_project_points_f64(make_cam(K, D, R, t), n, dX, dU, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(uv, dU, nu * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_undistort_points(acino_handle* h, int n, const double* uv, const double* K, const double* D, double* xn) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_undistort_points: NULL handle");
+    if (n < 0 || !K || !D || (n > 0 && (!uv || !xn))) return fail(h, ACINO_ERR_ARG, "acino_undistort_points: bad arguments");
+    if (n == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nu = pad64((size_t)n * 2);
+    int rc = ensure_ws(h, 2 * nu * sizeof(double));
+    if (rc) return rc;
+    double* dU = (double*)h->ws;
+    double* dO = dU + nu;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dU, uv, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_undistort_points_f64(make_cam(K, D, nullptr, nullptr), n, dU, dO, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(xn, dO, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_triangulate_points(acino_handle* h, int n, const double* uv1, const double* uv2, const double* K1,
+                             const double* D1, const double* R1, const double* t1, const double* K2, const double* D2,
+                             const double* R2, const double* t2, double* X) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_triangulate_points: NULL handle");
+    if (n < 0 || !K1 || !D1 || !R1 || !t1 || !K2 || !D2 || !R2 || !t2 || (n > 0 && (!uv1 || !uv2 || !X)))
+        return fail(h, ACINO_ERR_ARG, "acino_triangulate_points: bad arguments");
+    if (n == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nu = pad64((size_t)n * 2);
+    int rc = ensure_ws(h, (2 * nu + (size_t)n * 3) * sizeof(double));
+    if (rc) return rc;
+    double* d1 = (double*)h->ws;
+    double* d2 = d1 + nu;
+    double* dX = d2 + nu;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(d1, uv1, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d2, uv2, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_triangulate_points_f64(make_cam(K1, D1, R1, t1), make_cam(K2, D2, R2, t2), n, d1, d2, dX, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(X, dX, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_triangulate_pairwise(acino_handle* h, int n_frames, int n_markers, const double* uv, const uint8_t* valid,
+                               double* pos, int32_t* count) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_triangulate_pairwise: NULL handle");
+    if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_triangulate_pairwise: cameras not set");
+    if (n_frames < 0 || n_markers < 0 || ((size_t)n_frames * n_markers > 0 && (!uv || !valid || !pos)))
+        return fail(h, ACINO_ERR_ARG, "acino_triangulate_pairwise: bad arguments");
+    const size_t N = (size_t)n_frames, L = (size_t)n_markers, C = (size_t)h->scene.n_cams;
+    if (N * L == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nu = pad64(N * C * L * 2), np = pad64(N * L * 3);
+    const size_t nv = (N * C * L + 7) / 8 * 8, ncnt = N * L;
+    int rc = ensure_ws(h, (nu + np) * sizeof(double) + ncnt * sizeof(int) + nv);
+    if (rc) return rc;
+    double* dU = (double*)h->ws;
+    double* dP = dU + nu;
+    int* dC = (int*)(dP + np);
+    unsigned char* dV = (unsigned char*)(dC + ncnt);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dU, uv, N * C * L * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dV, valid, N * C * L, cudaMemcpyHostToDevice, s));
+    CK(launch_triangulate_pairwise_f64(h->cam_d, (int)C, n_frames, n_markers, dU, dV, dP, dC, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(pos, dP, N * L * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (count) CK(cudaMemcpyAsync(count, dC, ncnt * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return ACINO_OK;
 }

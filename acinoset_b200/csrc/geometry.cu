@@ -1,0 +1,253 @@
+// Camera-geometry kernels: fisheye projection of arbitrary 3-D points, OpenCV-compatible fisheye
+// undistortion, two-view DLT triangulation and the adjacent-pair TRI driver.
+//
+// Replaces (reference, /root/reference/src/calib/calib.py):
+//   project_points_fisheye            :132-136  (cv2.Rodrigues + cv2.fisheye.projectPoints)
+//   triangulate_points_fisheye        :121-130  (cv2.fisheye.undistortPoints x2 + cv2.triangulatePoints)
+//   get_pairwise_3d_points_from_df    :394-423  (adjacent pairs, inner merge, unweighted mean)
+// OpenCV is an un-vendored dependency of the reference; the algorithms are restated from their
+// published form and pinned to cv2 4.13.0 outputs in tests/golden/.
+// All of this is fp64 by default: the reference returns float64 and the work is tiny; an fp32
+// instantiation exists for the fused paths.  One thread per point; no reductions across threads,
+// fixed pair order 0-1, 1-2, ... and fixed summation order => bit-reproducible.
+#include "acino_common.cuh"
+
+namespace acino {
+
+template <typename T>
+struct CamT {
+    T R[9];
+    T t[3];
+    T fx, fy, cx, cy;
+    T D[4];
+};
+
+template <typename T>
+__device__ __forceinline__ CamT<T> load_cam(const CamD& c) {
+    CamT<T> o;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o.R[i] = (T)c.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o.t[i] = (T)c.t[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.D[i] = (T)c.D[i];
+    o.fx = (T)c.fx; o.fy = (T)c.fy; o.cx = (T)c.cx; o.cy = (T)c.cy;
+    return o;
+}
+
+// ---- projection -------------------------------------------------------------------------
+template <typename T>
+__global__ void project_points_kernel(const CamD camd, const int n, const T* __restrict__ X, T* __restrict__ uv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CamT<T> cam = load_cam<T>(camd);
+    const T x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+    const T xc = cam.R[0] * x + cam.R[1] * y + cam.R[2] * z + cam.t[0];
+    const T yc = cam.R[3] * x + cam.R[4] * y + cam.R[5] * z + cam.t[1];
+    const T zc = cam.R[6] * x + cam.R[7] * y + cam.R[8] * z + cam.t[2];
+    ProjOut<T> pr;
+    fisheye_cam<T, false>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
+    uv[2 * i] = pr.u + cam.cx;
+    uv[2 * i + 1] = pr.v + cam.cy;
+}
+
+// ---- cv2.fisheye.undistortPoints (no R / P, default criteria: <= 10 Newton steps, eps 1e-8) ---
+template <typename T>
+__device__ __forceinline__ void undistort_point(const CamT<T>& cam, const T u, const T v, T& xo, T& yo) {
+    const T pwx = (u - cam.cx) / cam.fx;
+    const T pwy = (v - cam.cy) / cam.fy;
+    T thd = sqrt(pwx * pwx + pwy * pwy);
+    const T half_pi = T(1.5707963267948966);
+    thd = fmin(fmax(-half_pi, thd), half_pi);
+    const T eps = T(1e-8);
+    bool converged = false;
+    T th = thd;
+    T scale = T(0);
+    if (fabs(thd) > eps) {
+        for (int j = 0; j < 10; ++j) {
+            const T th2 = th * th, th4 = th2 * th2, th6 = th4 * th2, th8 = th6 * th2;
+            const T k0 = cam.D[0] * th2, k1 = cam.D[1] * th4, k2 = cam.D[2] * th6, k3 = cam.D[3] * th8;
+            const T fix = (th * (T(1) + k0 + k1 + k2 + k3) - thd) / (T(1) + T(3) * k0 + T(5) * k1 + T(7) * k2 + T(9) * k3);
+            th = th - fix;
+            if (fabs(fix) < eps) {
+                converged = true;
+                break;
+            }
+        }
+        scale = tan(th) / thd;
+    } else {
+        converged = true;
+    }
+    const bool flipped = (thd < T(0) && th > T(0)) || (thd > T(0) && th < T(0));
+    if (converged && !flipped) {
+        xo = pwx * scale;
+        yo = pwy * scale;
+    } else {
+        xo = T(-1000000.0);
+        yo = T(-1000000.0);
+    }
+}
+
+template <typename T>
+__global__ void undistort_points_kernel(const CamD camd, const int n, const T* __restrict__ uv, T* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CamT<T> cam = load_cam<T>(camd);
+    T x, y;
+    undistort_point<T>(cam, uv[2 * i], uv[2 * i + 1], x, y);
+    out[2 * i] = x;
+    out[2 * i + 1] = y;
+}
+
+// ---- two-view DLT (cv2.triangulatePoints): smallest right singular vector of the 4x4 system,
+//      by one-sided Jacobi (Hestenes) sweeps on the columns - no A^T A squaring ------------------
+template <typename T>
+__device__ __forceinline__ void dlt_pair(const CamT<T>& c1, const CamT<T>& c2, const T x1, const T y1, const T x2,
+                                         const T y2, T X[3]) {
+    T A[4][4], V[4][4];
+    // rows: x P[2] - P[0], y P[2] - P[1] with P = [R | t], no row normalisation
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const T p10 = j < 3 ? c1.R[j] : c1.t[0], p11 = j < 3 ? c1.R[3 + j] : c1.t[1], p12 = j < 3 ? c1.R[6 + j] : c1.t[2];
+        const T p20 = j < 3 ? c2.R[j] : c2.t[0], p21 = j < 3 ? c2.R[3 + j] : c2.t[1], p22 = j < 3 ? c2.R[6 + j] : c2.t[2];
+        A[0][j] = x1 * p12 - p10;
+        A[1][j] = y1 * p12 - p11;
+        A[2][j] = x2 * p22 - p20;
+        A[3][j] = y2 * p22 - p21;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) V[i][j] = (i == j) ? T(1) : T(0);
+    }
+    const T tiny = sizeof(T) == 8 ? T(1e-300) : T(1e-30);
+    for (int sweep = 0; sweep < 12; ++sweep) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                T al = T(0), be = T(0), ga = T(0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    al += A[i][p] * A[i][p];
+                    be += A[i][q] * A[i][q];
+                    ga += A[i][p] * A[i][q];
+                }
+                if (fabs(ga) > tiny) {
+                    const T zeta = (be - al) / (T(2) * ga);
+                    const T tt = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+                    const T c = T(1) / sqrt(T(1) + tt * tt);
+                    const T s = c * tt;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const T ap = A[i][p], aq = A[i][q];
+                        A[i][p] = c * ap - s * aq;
+                        A[i][q] = s * ap + c * aq;
+                        const T vp = V[i][p], vq = V[i][q];
+                        V[i][p] = c * vp - s * vq;
+                        V[i][q] = s * vp + c * vq;
+                    }
+                }
+            }
+    }
+    int best = 0;
+    T bn = T(0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        T nn = T(0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nn += A[i][j] * A[i][j];
+        if (j == 0 || nn < bn) {
+            bn = nn;
+            best = j;
+        }
+    }
+    T v0 = V[0][0], v1 = V[1][0], v2 = V[2][0], v3 = V[3][0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+        if (best == j) {
+            v0 = V[0][j]; v1 = V[1][j]; v2 = V[2][j]; v3 = V[3][j];
+        }
+    X[0] = v0 / v3;
+    X[1] = v1 / v3;
+    X[2] = v2 / v3;
+}
+
+template <typename T>
+__global__ void triangulate_points_kernel(const CamD cam1d, const CamD cam2d, const int n, const T* __restrict__ uv1,
+                                          const T* __restrict__ uv2, T* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CamT<T> c1 = load_cam<T>(cam1d), c2 = load_cam<T>(cam2d);
+    T x1, y1, x2, y2, X[3];
+    undistort_point<T>(c1, uv1[2 * i], uv1[2 * i + 1], x1, y1);
+    undistort_point<T>(c2, uv2[2 * i], uv2[2 * i + 1], x2, y2);
+    dlt_pair<T>(c1, c2, x1, y1, x2, y2, X);
+    out[3 * i] = X[0];
+    out[3 * i + 1] = X[1];
+    out[3 * i + 2] = X[2];
+}
+
+// ---- TRI driver: dense form of get_pairwise_3d_points_from_df ---------------------------------
+struct CamTableD {
+    CamD cam[ACINO_MAX_CAMS];
+    int n_cams;
+};
+
+template <typename T>
+__global__ void triangulate_pairwise_kernel(const __grid_constant__ CamTableD tab, const int n_frames, const int L,
+                                            const T* __restrict__ uv, const unsigned char* __restrict__ valid,
+                                            T* __restrict__ pos, int* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (frame, marker)
+    if (i >= (long long)n_frames * L) return;
+    const int n = (int)(i / L), l = (int)(i - (long long)n * L);
+    const int C = tab.n_cams;
+    T acc[3] = {T(0), T(0), T(0)};
+    int cnt = 0;
+    for (int c = 0; c + 1 < C; ++c) {
+        const size_t ia = ((size_t)n * C + c) * L + l, ib = ((size_t)n * C + c + 1) * L + l;
+        if (!valid[ia] || !valid[ib]) continue;
+        const CamT<T> c1 = load_cam<T>(tab.cam[c]), c2 = load_cam<T>(tab.cam[c + 1]);
+        T x1, y1, x2, y2, X[3];
+        undistort_point<T>(c1, uv[2 * ia], uv[2 * ia + 1], x1, y1);
+        undistort_point<T>(c2, uv[2 * ib], uv[2 * ib + 1], x2, y2);
+        dlt_pair<T>(c1, c2, x1, y1, x2, y2, X);
+        acc[0] += X[0];
+        acc[1] += X[1];
+        acc[2] += X[2];
+        ++cnt;
+    }
+    const T nanv = sizeof(T) == 8 ? (T)__longlong_as_double(0x7ff8000000000000LL) : (T)__int_as_float(0x7fc00000);
+    pos[3 * i] = cnt ? acc[0] / (T)cnt : nanv;
+    pos[3 * i + 1] = cnt ? acc[1] / (T)cnt : nanv;
+    pos[3 * i + 2] = cnt ? acc[2] / (T)cnt : nanv;
+    if (count) count[i] = cnt;
+}
+
+// ---- launchers --------------------------------------------------------------------------------
+static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+
+cudaError_t launch_project_points_f64(const CamD& cam, int n, const double* X, double* uv, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    project_points_kernel<double><<<nblk(n, 128), 128, 0, s>>>(cam, n, X, uv);
+    return cudaGetLastError();
+}
+cudaError_t launch_undistort_points_f64(const CamD& cam, int n, const double* uv, double* out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    undistort_points_kernel<double><<<nblk(n, 128), 128, 0, s>>>(cam, n, uv, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_triangulate_points_f64(const CamD& c1, const CamD& c2, int n, const double* uv1, const double* uv2,
+                                          double* out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    triangulate_points_kernel<double><<<nblk(n, 64), 64, 0, s>>>(c1, c2, n, uv1, uv2, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_frames, int L, const double* uv,
+                                            const unsigned char* valid, double* pos, int* count, cudaStream_t s) {
+    if (n_frames <= 0 || L <= 0) return cudaSuccess;
+    CamTableD tab;
+    for (int c = 0; c < n_cams; ++c) tab.cam[c] = cams[c];
+    tab.n_cams = n_cams;
+    triangulate_pairwise_kernel<double><<<nblk((long long)n_frames * L, 64), 64, 0, s>>>(tab, n_frames, L, uv, valid, pos, count);
+    return cudaGetLastError();
+}
+
+}  // namespace acino

@@ -81,6 +81,33 @@ int acino_fk_project_dev(acino_handle* h, int n_frames, const float* x, float* p
                          void* cuda_stream);
 int acino_fk_project(acino_handle* h, int n_frames, const float* x, float* pos, float* uv);
 
+/* ---- camera geometry (fp64, host pointers) -------------------------------------------------
+ * Single-camera arguments: K [3][3], D [4], R [3][3] (world->camera), t [3]. */
+
+/* project_points_fisheye(obj_pts, k, d, r, t) (calib.py:132-136): X [n][3] -> uv [n][2].
+ * No skew, no behind-camera guard, exactly like cv2.fisheye.projectPoints / pt3d_to_2d. */
+int acino_project_points(acino_handle* h, int n, const double* X, const double* K, const double* D,
+                         const double* R, const double* t, double* uv);
+
+/* cv2.fisheye.undistortPoints(pts, K, D) as called at calib.py:124-125 (no R/P, default criteria):
+ * uv [n][2] pixels -> xn [n][2] normalised coordinates; non-converged points come back as -1e6. */
+int acino_undistort_points(acino_handle* h, int n, const double* uv, const double* K, const double* D,
+                           double* xn);
+
+/* triangulate_points_fisheye(img_pts_1, img_pts_2, k1,d1,r1,t1, k2,d2,r2,t2) (calib.py:121-130):
+ * uv1, uv2 [n][2] -> X [n][3]. */
+int acino_triangulate_points(acino_handle* h, int n, const double* uv1, const double* uv2,
+                             const double* K1, const double* D1, const double* R1, const double* t1,
+                             const double* K2, const double* D2, const double* R2, const double* t2,
+                             double* X);
+
+/* get_pairwise_3d_points_from_df (calib.py:394-423) on dense tensors, cameras from
+ * acino_set_cameras: uv [N][C][L][2], valid [N][C][L] (1 = the row survives the caller's likelihood
+ * filter) -> pos [N][L][3] = unweighted mean of the adjacent-pair (c, c+1) triangulations in the
+ * order 0-1, 1-2, ... (NaN where no pair saw the point), count [N][L] (may be NULL). */
+int acino_triangulate_pairwise(acino_handle* h, int n_frames, int n_markers, const double* uv,
+                               const uint8_t* valid, double* pos, int32_t* count);
+
 #ifdef __cplusplus
 }
 #endif
