@@ -59,6 +59,21 @@ def _load():
     lib.acino_triangulate_points.restype = ci
     lib.acino_triangulate_pairwise.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     lib.acino_triangulate_pairwise.restype = ci
+    i64 = ctypes.c_int64
+    lib.acino_lm_prepare_dev.argtypes = [vp, ci, i64, i64] + [vp] * 9
+    lib.acino_lm_prepare_dev.restype = ci
+    lib.acino_lm_assemble_dev.argtypes = [vp, ci, i64, i64, ci, vp, vp, vp, vp, cd, vp, vp, vp, vp]
+    lib.acino_lm_assemble_dev.restype = ci
+    lib.acino_lm_step_dev.argtypes = [vp, ci, i64, i64] + [vp] * 12
+    lib.acino_lm_step_dev.restype = ci
+    lib.acino_lm_reduce_dev.argtypes = [vp, ci] + [vp] * 7
+    lib.acino_lm_reduce_dev.restype = ci
+    lib.acino_bcr_factor_dev.argtypes = [vp, ci] + [vp] * 8
+    lib.acino_bcr_factor_dev.restype = ci
+    lib.acino_bcr_update_dev.argtypes = [vp, ci] + [vp] * 7
+    lib.acino_bcr_update_dev.restype = ci
+    lib.acino_bcr_backsub_dev.argtypes = [vp, ci] + [vp] * 7
+    lib.acino_bcr_backsub_dev.restype = ci
     return lib
 
 
@@ -70,6 +85,8 @@ EXPORTED = [
     "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
     "acino_fk_project_dev", "acino_fk_project", "acino_project_points", "acino_undistort_points",
     "acino_triangulate_points", "acino_triangulate_pairwise",
+    "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
+    "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
 ]
 
 
@@ -232,6 +249,22 @@ class Handle:
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         self._check(lib.acino_fk_project_dev(self._h, N, _dp(x), _dp(pos), _dp(uv), ctypes.c_void_p(s)),
                     "acino_fk_project_dev")
+
+
+    # ---- raw device-pointer calls used by acinoset_b200.lm (arguments are torch tensors / scalars)
+    def call_dev(self, name, *args, stream=None):
+        import torch
+
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        conv = []
+        for a in args:
+            if a is None:
+                conv.append(None)
+            elif hasattr(a, "data_ptr"):
+                conv.append(ctypes.c_void_p(a.data_ptr()))
+            else:
+                conv.append(a)
+        self._check(getattr(lib, name)(self._h, *conv, ctypes.c_void_p(s)), name)
 
 
 def _dp(tns):

@@ -17,6 +17,23 @@ cudaError_t launch_triangulate_points_f64(const CamD& c1, const CamD& c2, int n,
                                           double* out, cudaStream_t s);
 cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_frames, int L, const double* uv,
                                             const unsigned char* valid, double* pos, int* count, cudaStream_t s);
+cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, const double* x_ext, const float* g,
+                              const double* sw, const double* lo, const double* hi, double* gtot, unsigned char* fixed,
+                              double* cost_s, cudaStream_t s);
+cudaError_t launch_lm_assemble(int n_frames, long long frame0, long long ng, int n_blocks, const float* H,
+                               const double* gtot, const unsigned char* fixed, const double* sw, double lambda, double* D,
+                               double* Lc, double* rhs, cudaStream_t s);
+cudaError_t launch_lm_step(int n_frames, long long frame0, long long ng, const double* x_ext, const double* d_ext,
+                           const double* gtot, const float* H, const double* sw, const double* lo, const double* hi,
+                           double* xt_ext, float* xt32, double* pred, double* step, cudaStream_t s);
+cudaError_t launch_lm_reduce(int n, const float* a0, const double* a1, const double* a2, const double* a3,
+                             const double* m, double* out, cudaStream_t s);
+cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const double* Lc, double* P, double* Q,
+                              double* rhs, int* info, cudaStream_t s);
+cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
+                              double* rhs, cudaStream_t s);
+cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* D, const double* P, const double* Q,
+                               const double* rhs, double* x, cudaStream_t s);
 }  // namespace acino
 
 using namespace acino;
@@ -322,6 +339,83 @@ int acino_triangulate_pairwise(acino_handle* h, int n_frames, int n_markers, con
     CK(cudaMemcpyAsync(pos, dP, N * L * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (count) CK(cudaMemcpyAsync(count, dC, ncnt * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+#define DEV_ENTER(name)                                                         \
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, name ": NULL handle");          \
+    CK(cudaSetDevice(h->device));                                               \
+    cudaStream_t s = (cudaStream_t)cuda_stream
+
+int acino_lm_prepare_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t ng, const double* x_ext, const float* g,
+                         const double* sw, const double* lo, const double* hi, double* gtot, uint8_t* fixed,
+                         double* cost_s, void* cuda_stream) {
+    DEV_ENTER("acino_lm_prepare_dev");
+    if (n_frames < 0 || !x_ext || !g || !sw || !lo || !hi || !gtot || !fixed || !cost_s)
+        return fail(h, ACINO_ERR_ARG, "acino_lm_prepare_dev: bad arguments");
+    CK(launch_lm_prepare(n_frames, frame0, ng, x_ext, g, sw, lo, hi, gtot, fixed, cost_s, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_lm_assemble_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t ng, int n_blocks, const float* H,
+                          const double* gtot, const uint8_t* fixed, const double* sw, double lambda, double* D, double* Lc,
+                          double* rhs, void* cuda_stream) {
+    DEV_ENTER("acino_lm_assemble_dev");
+    if (n_frames < 0 || n_blocks * 3 < n_frames || !H || !gtot || !fixed || !sw || !D || !Lc || !rhs)
+        return fail(h, ACINO_ERR_ARG, "acino_lm_assemble_dev: bad arguments");
+    CK(launch_lm_assemble(n_frames, frame0, ng, n_blocks, H, gtot, fixed, sw, lambda, D, Lc, rhs, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_lm_step_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t ng, const double* x_ext, const double* d_ext,
+                      const double* gtot, const float* H, const double* sw, const double* lo, const double* hi,
+                      double* xt_ext, float* xt32, double* pred, double* step, void* cuda_stream) {
+    DEV_ENTER("acino_lm_step_dev");
+    if (n_frames < 0 || !x_ext || !d_ext || !gtot || !H || !sw || !lo || !hi || !xt_ext || !xt32 || !pred || !step)
+        return fail(h, ACINO_ERR_ARG, "acino_lm_step_dev: bad arguments");
+    CK(launch_lm_step(n_frames, frame0, ng, x_ext, d_ext, gtot, H, sw, lo, hi, xt_ext, xt32, pred, step, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_lm_reduce_dev(acino_handle* h, int n, const float* a0, const double* a1, const double* a2, const double* a3,
+                        const double* m, double* out, void* cuda_stream) {
+    DEV_ENTER("acino_lm_reduce_dev");
+    if (n < 0 || !out) return fail(h, ACINO_ERR_ARG, "acino_lm_reduce_dev: bad arguments");
+    CK(launch_lm_reduce(n, a0, a1, a2, a3, m, out, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, double* D, const double* Lc, double* P,
+                         double* Q, double* rhs, int32_t* info, void* cuda_stream) {
+    DEV_ENTER("acino_bcr_factor_dev");
+    if (n_elim < 0 || (n_elim > 0 && (!elim || !D || !Lc || !P || !Q || !rhs || !info)))
+        return fail(h, ACINO_ERR_ARG, "acino_bcr_factor_dev: bad arguments");
+    CK(launch_bcr_factor(n_elim, elim, D, Lc, P, Q, rhs, info, s));
+    h->launches += n_elim > 0;
+    return ACINO_OK;
+}
+
+int acino_bcr_update_dev(acino_handle* h, int n_surv, const int32_t* surv, double* D, double* Lc, const double* P,
+                         const double* Q, double* rhs, void* cuda_stream) {
+    DEV_ENTER("acino_bcr_update_dev");
+    if (n_surv < 0 || (n_surv > 0 && (!surv || !D || !Lc || !P || !Q || !rhs)))
+        return fail(h, ACINO_ERR_ARG, "acino_bcr_update_dev: bad arguments");
+    CK(launch_bcr_update(n_surv, surv, D, Lc, P, Q, rhs, s));
+    h->launches += n_surv > 0;
+    return ACINO_OK;
+}
+
+int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* D, const double* P,
+                          const double* Q, const double* rhs, double* x, void* cuda_stream) {
+    DEV_ENTER("acino_bcr_backsub_dev");
+    if (n_elim < 0 || (n_elim > 0 && (!elim || !D || !P || !Q || !rhs || !x)))
+        return fail(h, ACINO_ERR_ARG, "acino_bcr_backsub_dev: bad arguments");
+    CK(launch_bcr_backsub(n_elim, elim, D, P, Q, rhs, x, s));
+    h->launches += n_elim > 0;
     return ACINO_OK;
 }
 

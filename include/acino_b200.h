@@ -108,6 +108,45 @@ int acino_triangulate_points(acino_handle* h, int n, const double* uv1, const do
 int acino_triangulate_pairwise(acino_handle* h, int n_frames, int n_markers, const double* uv,
                                const uint8_t* valid, double* pos, int32_t* count);
 
+/* ---- FTE solve building blocks (device pointers, stream-ordered) ------------------------------
+ * Together they replace `opt.solve(m)` (all_optimizations.py:503-524): a projected
+ * Levenberg-Marquardt loop on  F(x) = sum rho(w r) + sum_{n>=3,p} q_p (third difference / Ts^2)^2
+ * (backwards_euler_pos/_vel + constant_acc, :369-391; weights 1/Q, :245-252,310-315) with the 21
+ * pose bounds of :403-483.  The loop itself (and the one all_gather per iteration when frames are
+ * sharded over GPUs) is driven from acinoset_b200/fte.py.
+ *
+ * Frames are addressed globally: this rank holds global frames [frame0, frame0 + n_frames) of
+ * n_frames_global; x_ext / d_ext are [(n_frames + 6)][25] fp64 with 3 halo frames on each side.
+ * sw[25] = 2 q_p / Ts^4, lo/hi[25] the box bounds (+-inf where free).  Super-blocks hold 3 frames
+ * (75 unknowns): D, Lc, P, Q are [M][75][75] fp64 row-major, rhs / x [M][75]. */
+int acino_lm_prepare_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t n_frames_global,
+                         const double* x_ext, const float* g, const double* sw, const double* lo,
+                         const double* hi, double* gtot, uint8_t* fixed, double* cost_s,
+                         void* cuda_stream);
+int acino_lm_assemble_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t n_frames_global,
+                          int n_blocks, const float* H, const double* gtot, const uint8_t* fixed,
+                          const double* sw, double lambda, double* D, double* Lc, double* rhs,
+                          void* cuda_stream);
+int acino_lm_step_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t n_frames_global,
+                      const double* x_ext, const double* d_ext, const double* gtot, const float* H,
+                      const double* sw, const double* lo, const double* hi, double* xt_ext,
+                      float* xt32, double* pred, double* step, void* cuda_stream);
+/* out[0..3] = fixed-order fp64 sums of a0 (float), a1, a2, a3; out[4] = max of m (NULL = skipped) */
+int acino_lm_reduce_dev(acino_handle* h, int n, const float* a0, const double* a1, const double* a2,
+                        const double* a3, const double* m, double* out, void* cuda_stream);
+
+/* Block cyclic reduction of a block-tridiagonal SPD chain (schedule: acinoset_b200/bcr.py).
+ * elim / surv are [n][3] int32 rows (block, left, right) / (block, eliminated-left, eliminated-right),
+ * -1 = none.  factor overwrites D_e with W = chol(D_e)^-1 and rhs_e with z; info != 0 flags a
+ * non-positive pivot (block index + 1). */
+int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, double* D, const double* Lc,
+                         double* P, double* Q, double* rhs, int32_t* info, void* cuda_stream);
+int acino_bcr_update_dev(acino_handle* h, int n_surv, const int32_t* surv, double* D, double* Lc,
+                         const double* P, const double* Q, double* rhs, void* cuda_stream);
+int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* D,
+                          const double* P, const double* Q, const double* rhs, double* x,
+                          void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,143 @@
+"""GPU: BCR chain solver vs dense solve; LM building blocks vs the oracle; full FTE solve vs the
+fp64 CPU restatement of the same algorithm (oracle/lm.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle(dummy_cams):
+    import acinoset_b200 as ab
+
+    K, D, R, t, _ = dummy_cams
+    h = ab.Handle(0)
+    h.set_cameras(K, D, R, t)
+    yield h
+    h.close()
+
+
+def _spd_chain(M, rng, B=75):
+    D = np.zeros((M, B, B))
+    Lc = np.zeros((M, B, B))
+    W = rng.normal(0, 1, (M, B, B))
+    V = rng.normal(0, 0.5, (M, B, B))
+    for i in range(M):
+        D[i] = W[i].T @ W[i] + V[i].T @ V[i] + np.eye(B)
+        if i > 0:
+            Lc[i] = W[i].T @ V[i - 1] * 0.3
+            D[i] += 0.1 * Lc[i] @ Lc[i].T
+            D[i - 1] += 0.1 * Lc[i].T @ Lc[i]
+    return D, Lc, rng.normal(0, 1, (M, B))
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 8, 33, 100])
+def test_bcr_cuda_matches_dense(handle, M):
+    import torch
+    from acinoset_b200 import lm
+    from oracle import bcr as obcr
+
+    rng = np.random.default_rng(M)
+    D, Lc, rhs = _spd_chain(M, rng)
+    xd = np.linalg.solve(obcr.dense_from_chain(D, Lc), rhs.ravel()).reshape(M, -1)
+    dev = torch.device("cuda:0")
+    Dd, Ld, rd = (torch.from_numpy(a).to(dev) for a in (D, Lc, rhs))
+    x = torch.zeros(M, 75, dtype=torch.float64, device=dev)
+    cs = lm.ChainSolver(handle, M)
+    cs.solve(Dd, Ld, rd, x)
+    torch.cuda.synchronize()
+    assert int(cs.info.item()) == 0
+    assert np.abs(x.cpu().numpy() - xd).max() < 1e-9 * max(1.0, np.abs(xd).max())
+
+
+def test_bcr_cuda_pinned_matches_oracle(handle):
+    import torch
+    from acinoset_b200 import bcr, lm
+    from oracle import bcr as obcr
+
+    M = 21
+    rng = np.random.default_rng(7)
+    D, Lc, rhs = _spd_chain(M, rng)
+    levels, _ = bcr.make_schedule(M, True, True)
+    D2, L2, r2 = D.copy(), Lc.copy(), rhs.copy()
+    obcr.bcr_reduce(D2, L2, r2, levels)
+    dev = torch.device("cuda:0")
+    Dd, Ld, rd = (torch.from_numpy(a).to(dev) for a in (D, Lc, rhs))
+    cs = lm.ChainSolver(handle, M, pinned=True)
+    cs.reduce(Dd, Ld, rd)
+    torch.cuda.synchronize()
+    for a, b in ((Dd[0], D2[0]), (Dd[M - 1], D2[M - 1]), (Ld[M - 1], L2[M - 1]), (rd[0], r2[0]), (rd[M - 1], r2[M - 1])):
+        assert np.abs(a.cpu().numpy() - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+
+
+def test_lm_assemble_matches_oracle_system(handle, dummy_cams):
+    """prepare + assemble reproduce B + lam diag(B) and -g of the oracle (dense comparison)."""
+    import synth
+    import torch
+    from acinoset_b200 import lm
+    from oracle import bcr as obcr, fisheye, fte, lm as olm, skeleton
+
+    N = 31
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=21, cams=dummy_cams)
+    K, D, R, t, _ = dummy_cams
+    x0 = p["x0"].copy()
+    lo, hi = skeleton.active_bounds()
+    for pp in range(12, 20):  # whole columns on a bound (no smoothness gradient): some get frozen
+        x0[:, pp] = hi[pp] if pp % 2 else lo[pp]
+    x0 = np.clip(x0, lo, hi)
+    sol = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"])
+    s = sol.st[0]
+    s["x_ext"][3:3 + N] = torch.from_numpy(x0).cuda()
+    s["x32"].copy_(s["x_ext"][3:3 + N].float())
+    sol._eval(s)
+    sol._prepare(s)
+    lam = 0.37
+    sol.h.call_dev("acino_lm_assemble_dev", N, 0, N, sol.M, s["H"], s["gtot"], s["fixed"], sol.sw, lam, sol.D, sol.Lc, sol.rhs)
+    torch.cuda.synchronize()
+    A = obcr.dense_from_chain(sol.D.cpu().numpy(), sol.Lc.cpu().numpy())[:N * 25, :N * 25]
+    rhs = sol.rhs.cpu().numpy().ravel()[:N * 25]
+    # oracle system from the SAME fp32-rounded evaluation inputs
+    x32 = x0.astype(np.float32).astype(np.float64)
+    c, g, H = fte.fte_eval(x32, p["meas"].astype(np.float32).astype(np.float64), p["w"].astype(np.float32).astype(np.float64), K, D, R, t)
+    q = fte.model_weights_active()
+    gt = (g + fte.smooth_grad(x0, p["Ts"], q)).ravel()
+    B = (olm.assemble(H, N) + olm.smooth_matrix(N, p["Ts"], q)).toarray()
+    xv = x0.ravel()
+    fixed = ((xv <= np.tile(lo, N)) & (gt > 0)) | ((xv >= np.tile(hi, N)) & (gt < 0))
+    assert fixed.sum() >= 1
+    assert np.array_equal(s["fixed"].cpu().numpy().ravel().astype(bool), fixed)
+    Aref = B + lam * np.diag(np.diag(B))
+    Aref[fixed, :] = 0
+    Aref[:, fixed] = 0
+    Aref[fixed, fixed] = 1
+    rref = -gt.copy()
+    rref[fixed] = 0
+    scale = np.sqrt(np.outer(np.diag(Aref), np.diag(Aref)))
+    assert (np.abs(A - Aref) / scale).max() < 2e-5       # data blocks come from the fp32 kernel
+    assert np.abs(rhs - rref).max() < 2e-4 * np.abs(rref).max()
+    # smoothness cost
+    cs = float(s["cost_s"].sum().item())
+    assert abs(cs - fte.smooth_cost(x0, p["Ts"], q)) < 1e-9 * max(1.0, cs)
+
+
+@pytest.mark.parametrize("N", [48, 200])
+def test_fte_solve_matches_cpu_restatement(handle, dummy_cams, N):
+    """Solve parity: final objective within 1e-4 relative and marker positions within
+    1e-3 m of the fp64 CPU restatement running the same algorithm."""
+    import synth
+    from acinoset_b200 import lm
+    from oracle import fisheye, lm as olm, skeleton
+
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=5, cams=dummy_cams)
+    x_ref, info_ref = olm.solve(p, p["x0"], max_iter=40)
+    sol = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"])
+    x, info = sol.solve(p["x0"], max_iter=40)
+    assert info["bcr_info"] == 0
+    assert abs(info["F"] - info_ref["F"]) < 1e-4 * abs(info_ref["F"])
+    P, Pr = skeleton.cheetah_fk_active(x), skeleton.cheetah_fk_active(x_ref)
+    assert np.abs(P - Pr).max() < 1e-3
+    # and it actually solved the problem: close to the ground truth
+    Pt = skeleton.cheetah_fk_active(p["x_true"])
+    assert np.sqrt(((P - Pt) ** 2).sum(-1).mean()) < 0.01
+    lo, hi = skeleton.active_bounds()
+    assert (x >= lo - 1e-12).all() and (x <= hi + 1e-12).all()
