@@ -1,0 +1,49 @@
+"""torchrun worker: sharded FTE solve over WORLD_SIZE GPUs vs the single-GPU solve (rank 0)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import acinoset_b200 as ab
+    import synth
+    from acinoset_b200 import lm
+    from oracle import fisheye, skeleton
+
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+    cams = synth.load_dummy_scene()
+    K, D, R, t, _ = cams
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=17, cams=cams)
+    h = ab.Handle(local)
+    h.set_cameras(K, D, R, t)
+    f0, n = lm.shard_frames(N, world)[rank]
+    sol = lm.FTESolver(h, p["meas"][f0:f0 + n], p["w"][f0:f0 + n], p["Ts"], frame0=f0, n_global=N, rank=rank, world=world)
+    x, info = sol.solve(p["x0"][f0:f0 + n], max_iter=40)
+    xs = [torch.zeros(lm.shard_frames(N, world)[r][1], 25, dtype=torch.float64, device=f"cuda:{local}") for r in range(world)]
+    dist.all_gather(xs, torch.from_numpy(x).to(f"cuda:{local}"))
+    ok = True
+    if rank == 0:
+        xg = torch.cat(xs).cpu().numpy()
+        sol1 = lm.FTESolver(h, p["meas"], p["w"], p["Ts"])
+        x1, info1 = sol1.solve(p["x0"], max_iter=40)
+        dF = abs(info["F"] - info1["F"]) / abs(info1["F"])
+        dx = np.abs(xg - x1).max()
+        print(f"world {world}: F {info['F']:.6f} vs single {info1['F']:.6f} (rel {dF:.2e}); iters {info['iters']} vs {info1['iters']}; max|dx| {dx:.2e}; bcr_info {info['bcr_info']}")
+        ok = dF < 1e-9 and dx < 1e-6 and info["bcr_info"] == 0
+    flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
