@@ -11,6 +11,7 @@ here under their reference names.
 import numpy as np
 
 from . import fte as _fte
+from .rotations import rodrigues_to_mat, rodrigues_to_vec
 
 
 def project_points_fisheye(obj_pts, k, d, r, t, device=0):
@@ -18,6 +19,9 @@ def project_points_fisheye(obj_pts, k, d, r, t, device=0):
     No geometry validation: a point behind the camera is projected like any other (as in the
     reference)."""
     obj_pts = np.asarray(obj_pts, dtype=np.float64).reshape((-1, 3))
+    # calib.py:134: r -> cv2.Rodrigues -> rvec -> (inside cv2.fisheye.projectPoints) matrix again, which
+    # projects a slightly non-orthonormal scene matrix onto SO(3); reproduced on the host (9 numbers)
+    r = rodrigues_to_mat(rodrigues_to_vec(r))
     return _fte.get_handle(device).project_points(obj_pts, k, np.asarray(d).reshape(-1)[:4], r, t)
 
 
@@ -77,3 +81,19 @@ def get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr, tri
     fi, mi = np.nonzero(cnt > 0)
     return pd.DataFrame({"frame": frames[fi], "marker": markers[mi],
                          "x": pos[fi, mi, 0], "y": pos[fi, mi, 1], "z": pos[fi, mi, 2]})
+
+
+_SBA_NAMES = (
+    "create_bundle_adjustment_jacobian_sparsity_matrix", "prepare_calib_board_data_for_bundle_adjustment",
+    "prepare_manual_points_for_bundle_adjustment", "params_to_points_only", "cost_func_points_only",
+    "bundle_adjust_board_points_only", "bundle_adjust_points_only", "params_to_points_extrinsics",
+    "cost_func_points_extrinsics", "bundle_adjust_board_points_and_extrinsics", "bundle_adjust_points_and_extrinsics",
+)
+
+
+def __getattr__(name):   # the reference keeps the SBA functions in calib.py too
+    if name in _SBA_NAMES:
+        from . import sba
+
+        return getattr(sba, name)
+    raise AttributeError(name)

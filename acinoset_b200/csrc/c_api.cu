@@ -34,6 +34,23 @@ cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc
                               double* rhs, cudaStream_t s);
 cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* D, const double* P, const double* Q,
                                const double* rhs, double* x, cudaStream_t s);
+cudaError_t launch_sba_cams(int C, const double* params, const double* R, const double* t, const double* K,
+                            const double* D, void* cams, cudaStream_t s);
+size_t sba_cam_bytes();
+cudaError_t launch_sba_eval(int n_obs, const void* cams, const double* pts, const float* uv, const int* cam_idx,
+                            const int* pt_idx, double f_scale, double* res, double* Jc, double* Jp, double* wgt,
+                            double* cost, cudaStream_t s);
+int sba_schur_grid(int n_pts);
+cudaError_t launch_sba_schur(int n_pts, int C, const int* pt_ptr, const int* obs, const int* cam_idx, const double* res,
+                             const double* Jc, const double* Jp, const double* wgt, double lam, double* partial, double* S,
+                             double* rhs, cudaStream_t s);
+cudaError_t launch_sba_dense_solve(int n, double* S, double* x, int* info, cudaStream_t s);
+cudaError_t launch_sba_backsub(int n_pts, int C, const int* pt_ptr, const int* obs, const int* cam_idx, const double* res,
+                               const double* Jc, const double* Jp, const double* wgt, double lam, const double* dc,
+                               const double* pts, double* pts_trial, double* dp, cudaStream_t s);
+cudaError_t launch_sba_pred(int n_obs, const int* cam_idx, const int* pt_idx, const double* res, const double* Jc,
+                            const double* Jp, const double* wgt, const double* dc, const double* dp, double* pred,
+                            cudaStream_t s);
 }  // namespace acino
 
 using namespace acino;
@@ -416,6 +433,76 @@ int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, cons
         return fail(h, ACINO_ERR_ARG, "acino_bcr_backsub_dev: bad arguments");
     CK(launch_bcr_backsub(n_elim, elim, D, P, Q, rhs, x, s));
     h->launches += n_elim > 0;
+    return ACINO_OK;
+}
+
+int64_t acino_sba_cam_bytes(void) { return (int64_t)sba_cam_bytes(); }
+
+int64_t acino_sba_schur_partial_size(int n_pts, int n_cams) {
+    const int64_t n = 6 * (int64_t)n_cams;
+    return (int64_t)sba_schur_grid(n_pts) * (n * n + 2 * n);
+}
+
+int acino_sba_cams_dev(acino_handle* h, int n_cams, const double* params, const double* R, const double* t,
+                       const double* K, const double* D, void* cams, void* cuda_stream) {
+    DEV_ENTER("acino_sba_cams_dev");
+    if (n_cams < 1 || n_cams > 10 || !K || !D || !cams || (!params && (!R || !t)))
+        return fail(h, ACINO_ERR_ARG, "acino_sba_cams_dev: need 1..10 cameras, K, D and params or (R, t)");
+    CK(launch_sba_cams(n_cams, params, R, t, K, D, cams, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_sba_eval_dev(acino_handle* h, int n_obs, const void* cams, const double* pts, const float* uv,
+                       const int32_t* cam_idx, const int32_t* pt_idx, double f_scale, double* res, double* Jc, double* Jp,
+                       double* wgt, double* cost, void* cuda_stream) {
+    DEV_ENTER("acino_sba_eval_dev");
+    if (n_obs < 0 || !cams || !pts || !uv || !cam_idx || !pt_idx || !res || !(f_scale > 0) || (Jp && !wgt) || (Jc && !Jp))
+        return fail(h, ACINO_ERR_ARG, "acino_sba_eval_dev: bad arguments");
+    CK(launch_sba_eval(n_obs, cams, pts, uv, cam_idx, pt_idx, f_scale, res, Jc, Jp, wgt, cost, s));
+    h->launches += n_obs > 0;
+    return ACINO_OK;
+}
+
+int acino_sba_schur_dev(acino_handle* h, int n_pts, int n_cams, const int32_t* pt_ptr, const int32_t* obs,
+                        const int32_t* cam_idx, const double* res, const double* Jc, const double* Jp, const double* wgt,
+                        double lam, double* partial, double* S, double* rhs, void* cuda_stream) {
+    DEV_ENTER("acino_sba_schur_dev");
+    if (n_pts < 1 || n_cams < 1 || n_cams > 10 || !pt_ptr || !obs || !cam_idx || !res || !Jc || !Jp || !wgt || !partial || !S || !rhs)
+        return fail(h, ACINO_ERR_ARG, "acino_sba_schur_dev: bad arguments");
+    CK(launch_sba_schur(n_pts, n_cams, pt_ptr, obs, cam_idx, res, Jc, Jp, wgt, lam, partial, S, rhs, s));
+    h->launches += 2;
+    return ACINO_OK;
+}
+
+int acino_sba_dense_solve_dev(acino_handle* h, int n, double* S, double* x, int32_t* info, void* cuda_stream) {
+    DEV_ENTER("acino_sba_dense_solve_dev");
+    if (n < 1 || n > 96 || !S || !x || !info) return fail(h, ACINO_ERR_ARG, "acino_sba_dense_solve_dev: bad arguments");
+    CK(launch_sba_dense_solve(n, S, x, info, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_sba_backsub_dev(acino_handle* h, int n_pts, int n_cams, const int32_t* pt_ptr, const int32_t* obs,
+                          const int32_t* cam_idx, const double* res, const double* Jc, const double* Jp, const double* wgt,
+                          double lam, const double* dc, const double* pts, double* pts_trial, double* dp,
+                          void* cuda_stream) {
+    DEV_ENTER("acino_sba_backsub_dev");
+    if (n_pts < 0 || !pt_ptr || !obs || !cam_idx || !res || !Jp || !wgt || !pts || !pts_trial)
+        return fail(h, ACINO_ERR_ARG, "acino_sba_backsub_dev: bad arguments");
+    CK(launch_sba_backsub(n_pts, n_cams, pt_ptr, obs, cam_idx, res, Jc, Jp, wgt, lam, dc, pts, pts_trial, dp, s));
+    h->launches += n_pts > 0;
+    return ACINO_OK;
+}
+
+int acino_sba_pred_dev(acino_handle* h, int n_obs, const int32_t* cam_idx, const int32_t* pt_idx, const double* res,
+                       const double* Jc, const double* Jp, const double* wgt, const double* dc, const double* dp,
+                       double* pred, void* cuda_stream) {
+    DEV_ENTER("acino_sba_pred_dev");
+    if (n_obs < 0 || !cam_idx || !pt_idx || !res || !Jp || !wgt || !dp || !pred)
+        return fail(h, ACINO_ERR_ARG, "acino_sba_pred_dev: bad arguments");
+    CK(launch_sba_pred(n_obs, cam_idx, pt_idx, res, Jc, Jp, wgt, dc, dp, pred, s));
+    h->launches += n_obs > 0;
     return ACINO_OK;
 }
 

@@ -1,0 +1,390 @@
+"""Sparse bundle adjustment on the GPU behind the reference's entry points
+(/root/reference/src/calib/calib.py:196-390 and app.py:201-223).
+
+Same names, argument order, shapes and return values as the reference:
+    create_bundle_adjustment_jacobian_sparsity_matrix   calib.py:196-207
+    prepare_calib_board_data_for_bundle_adjustment      calib.py:210-263
+    prepare_manual_points_for_bundle_adjustment         calib.py:266-304
+    params_to_points_only / cost_func_points_only       calib.py:307-316
+    params_to_points_extrinsics / cost_func_points_extrinsics   calib.py:345-359
+    bundle_adjust_points_only / bundle_adjust_board_points_only calib.py:319-341
+    bundle_adjust_points_and_extrinsics / bundle_adjust_board_points_and_extrinsics  calib.py:362-390
+    sba_board_points_fisheye                             app.py:201-223
+The reference minimises  0.5 sum C^2 ln(1 + (f/C)^2)  (SciPy least_squares, loss='cauchy',
+f_scale=C) with a finite-difference Jacobian over one OpenCV call per observation; here the
+residuals, analytic Jacobian blocks, the per-point Schur complement and the 6C x 6C solve run in
+libacino_b200.so (csrc/sba.cu) inside a Levenberg-Marquardt loop.  ``project_func`` /
+``triangulate_func`` arguments are accepted for signature compatibility.
+"""
+import time
+
+import numpy as np
+
+from . import calib as _calib
+from . import fte as _fte
+from . import _lib
+
+
+from .rotations import rodrigues_to_mat, rodrigues_to_vec  # noqa: E402,F401
+
+
+# ---- problem assembly (host) -----------------------------------------------------------------------
+def create_bundle_adjustment_jacobian_sparsity_matrix(n_cameras, n_params_per_camera, camera_indices, n_points,
+                                                      point_indices):
+    """calib.py:196-207, reproduced as is (including its camera-major column layout)."""
+    from scipy.sparse import lil_matrix
+
+    m = camera_indices.size * 2
+    n = n_cameras * n_params_per_camera + n_points * 3
+    A = lil_matrix((m, n), dtype=int)
+    i = np.arange(camera_indices.size)
+    for s in range(n_params_per_camera):
+        A[2 * i, camera_indices * n_params_per_camera + s] = 1
+        A[2 * i + 1, camera_indices * n_params_per_camera + s] = 1
+    for s in range(3):
+        A[2 * i, n_cameras * n_params_per_camera + point_indices * 3 + s] = 1
+        A[2 * i + 1, n_cameras * n_params_per_camera + point_indices * 3 + s] = 1
+    return A
+
+
+def prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr, r_arr, t_arr,
+                                                   triangulate_func=None):
+    """calib.py:210-263.  Views (file names) seen by >= 2 cameras; 54 new points per view, initial
+    estimate triangulated from the FIRST TWO cameras that see the view.  All views of one camera pair
+    are triangulated by a single kernel launch.  View order = sorted names (the reference iterates a
+    Python set; the cost is order-invariant)."""
+    n_cam = len(img_pts_arr)
+    fnames_arr = [list(f) for f in fnames_arr]
+    counts = {}
+    for fnames in fnames_arr:
+        for f in fnames:
+            counts[f] = counts.get(f, 0) + 1
+    views = sorted(f for f, v in counts.items() if v >= 2)
+    ppi = board_shape[0] * board_shape[1]
+    lookup = [{f: i for i, f in enumerate(fn)} for fn in fnames_arr]
+    points_2d, point_3d_indices, camera_indices = [], [], []
+    pair_views = {}
+    for v, fname in enumerate(views):
+        seen = [c for c in range(n_cam) if fname in lookup[c]]
+        for c in seen:
+            points_2d.append(np.asarray(img_pts_arr[c][lookup[c][fname]], dtype=np.float32).reshape(ppi, 2))
+            point_3d_indices.append(np.arange(v * ppi, (v + 1) * ppi))
+            camera_indices.append(np.full(ppi, c))
+        pair_views.setdefault((seen[0], seen[1]), []).append(v)
+    points_3d = np.zeros((len(views) * ppi, 3), dtype=np.float64)
+    for (a, b), vs in pair_views.items():
+        pa = np.concatenate([np.asarray(img_pts_arr[a][lookup[a][views[v]]], dtype=np.float64).reshape(ppi, 2) for v in vs])
+        pb = np.concatenate([np.asarray(img_pts_arr[b][lookup[b][views[v]]], dtype=np.float64).reshape(ppi, 2) for v in vs])
+        X = _calib.triangulate_points_fisheye(pa, pb, k_arr[a], d_arr[a], r_arr[a], t_arr[a], k_arr[b], d_arr[b],
+                                              r_arr[b], t_arr[b])
+        for j, v in enumerate(vs):
+            points_3d[v * ppi:(v + 1) * ppi] = X[j * ppi:(j + 1) * ppi]
+    if not views:
+        return (np.zeros((0, 2), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    return (np.concatenate(points_2d).astype(np.float32), points_3d.astype(np.float32),
+            np.concatenate(point_3d_indices).astype(np.int64), np.concatenate(camera_indices).astype(np.int64))
+
+
+def prepare_manual_points_for_bundle_adjustment(img_pts_arr, k_arr, d_arr, r_arr, t_arr, triangulate_func=None):
+    """calib.py:266-304: img_pts_arr (n_points, n_cameras, 2) with NaN where unseen."""
+    pts = np.asarray(img_pts_arr, dtype=np.float64).swapaxes(0, 1)
+    n_cam, n_pts = pts.shape[0], pts.shape[1]
+    seen = ~np.isnan(pts).any(axis=2)                       # (n_cam, n_pts)
+    keep = np.nonzero(seen.sum(axis=0) > 1)[0]
+    points_2d, point_3d_indices, camera_indices = [], [], []
+    first_two = {}
+    for new_idx, i in enumerate(keep):
+        cams = np.nonzero(seen[:, i])[0]
+        for c in cams:
+            points_2d.append(pts[c, i])
+            camera_indices.append(c)
+            point_3d_indices.append(new_idx)
+        first_two.setdefault((cams[0], cams[1]), []).append((new_idx, i))
+    points_3d = np.zeros((len(keep), 3))
+    for (a, b), lst in first_two.items():
+        idx_new = [x[0] for x in lst]
+        idx_old = [x[1] for x in lst]
+        X = _calib.triangulate_points_fisheye(pts[a, idx_old], pts[b, idx_old], k_arr[a], d_arr[a], r_arr[a], t_arr[a],
+                                              k_arr[b], d_arr[b], r_arr[b], t_arr[b])
+        points_3d[idx_new] = X
+    return (np.array(points_2d, dtype=np.float32).reshape(-1, 2), points_3d.astype(np.float32),
+            np.array(point_3d_indices, dtype=np.int64), np.array(camera_indices, dtype=np.int64))
+
+
+def params_to_points_only(params, n_points):
+    return np.asarray(params).reshape((n_points, 3))
+
+
+def params_to_points_extrinsics(params, n_cameras, n_points):
+    params = np.asarray(params, dtype=np.float64)
+    r_end = n_cameras * 3
+    t_end = r_end + n_cameras * 3
+    r_arr = np.array([rodrigues_to_mat(r) for r in params[:r_end].reshape((n_cameras, 3))], dtype=np.float64)
+    t_arr = params[r_end:t_end].reshape((n_cameras, 3, 1))
+    obj_pts = params[t_end:].reshape((n_points, 3))
+    return obj_pts, r_arr, t_arr
+
+
+# ---- device problem ----------------------------------------------------------------------------------
+class SBAProblem:
+    """Observations + cameras resident on one GPU; evaluates residuals / Jacobian blocks and runs LM."""
+
+    def __init__(self, points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, device=0,
+                 with_extrinsics=True, f_scale=1.0):
+        import torch
+
+        self.torch = torch
+        self.h = _fte.get_handle(device)
+        self.dev = torch.device("cuda", device)
+        self.C = len(k_arr)
+        if self.C > 10:
+            raise ValueError("SBA supports up to 10 cameras")
+        self.n_obs = int(len(point_3d_indices))
+        self.n_pts = int(n_points)
+        self.with_ext = with_extrinsics
+        self.f_scale = float(f_scale)
+        dev, f64 = self.dev, torch.float64
+        pidx = np.asarray(point_3d_indices, dtype=np.int64)
+        cidx = np.asarray(camera_indices, dtype=np.int64)
+        self.uv = torch.as_tensor(np.ascontiguousarray(points_2d, dtype=np.float32).reshape(-1, 2)).to(dev)
+        self.cam_idx = torch.as_tensor(cidx.astype(np.int32)).to(dev)
+        self.pt_idx = torch.as_tensor(pidx.astype(np.int32)).to(dev)
+        order = np.argsort(pidx, kind="stable").astype(np.int32)        # CSR by point, cameras ascending
+        ptr = np.zeros(self.n_pts + 1, dtype=np.int32)
+        np.cumsum(np.bincount(pidx, minlength=self.n_pts), out=ptr[1:])
+        self.obs = torch.as_tensor(order).to(dev)
+        self.pt_ptr = torch.as_tensor(ptr).to(dev)
+        self.K = torch.as_tensor(np.asarray(k_arr, dtype=np.float64).reshape(self.C, 9)).to(dev)
+        self.D = torch.as_tensor(np.asarray(d_arr, dtype=np.float64).reshape(self.C, 4)).to(dev)
+        cam_bytes = int(_lib.lib.acino_sba_cam_bytes())
+        self.cams = [torch.zeros(self.C * cam_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        n = self.n_obs
+
+        def buf(*shape):
+            return torch.zeros(*shape, dtype=f64, device=dev)
+
+        self.st = [dict(params=buf(6 * self.C), pts=buf(self.n_pts, 3), res=buf(n, 2), Jc=buf(n, 2, 6), Jp=buf(n, 2, 3),
+                        wgt=buf(n, 2), cost=buf(n), cams=self.cams[i]) for i in range(2)]
+        self.pred = buf(n)
+        self.dp = buf(self.n_pts, 3)
+        self.S = buf(6 * self.C, 6 * self.C)
+        self.dc = buf(6 * self.C)
+        self.partial = buf(int(_lib.lib.acino_sba_schur_partial_size(self.n_pts, self.C)))
+        self.out5 = buf(5)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.Rfix = self.tfix = None
+
+    def set_fixed_cameras(self, r_arr, t_arr):
+        t_ = self.torch
+        # the reference's project_func converts every r to a Rodrigues vector and back (calib.py:134):
+        # a slightly non-orthonormal scene matrix is projected onto SO(3) exactly like cv2.Rodrigues does
+        r_arr = np.array([rodrigues_to_mat(rodrigues_to_vec(r)) for r in np.asarray(r_arr, dtype=np.float64).reshape(-1, 3, 3)])
+        self.Rfix = t_.as_tensor(np.asarray(r_arr, dtype=np.float64).reshape(self.C, 9)).to(self.dev)
+        self.tfix = t_.as_tensor(np.asarray(t_arr, dtype=np.float64).reshape(self.C, 3)).to(self.dev)
+
+    # -- evaluation
+    def _eval(self, s, want_j=True):
+        if self.with_ext:
+            self.h.call_dev("acino_sba_cams_dev", self.C, s["params"], None, None, self.K, self.D, s["cams"])
+        else:
+            self.h.call_dev("acino_sba_cams_dev", self.C, None, self.Rfix, self.tfix, self.K, self.D, s["cams"])
+        self.h.call_dev("acino_sba_eval_dev", self.n_obs, s["cams"], s["pts"], self.uv, self.cam_idx, self.pt_idx,
+                        self.f_scale, s["res"], (s["Jc"] if self.with_ext else None) if want_j else None,
+                        s["Jp"] if want_j else None, s["wgt"] if want_j else None, s["cost"])
+
+    def _sum(self, a1, a2=None):
+        self.h.call_dev("acino_lm_reduce_dev", self.n_obs, None, a1, a2, None, None, self.out5)
+        o = self.out5.cpu().numpy()
+        return float(o[1]), float(o[2])
+
+    def residuals(self, params_c, pts):
+        """f (2 n_obs,) at the given parameters (no Jacobian)."""
+        t_ = self.torch
+        s = self.st[1]
+        if self.with_ext:
+            s["params"].copy_(t_.as_tensor(np.asarray(params_c, dtype=np.float64)).to(self.dev))
+        s["pts"].copy_(t_.as_tensor(np.asarray(pts, dtype=np.float64).reshape(-1, 3)).to(self.dev))
+        self._eval(s, want_j=False)
+        return s["res"].cpu().numpy().ravel()
+
+    def jacobian_blocks(self, params_c, pts):
+        """(res (n,2), Jc (n,2,6) or None, Jp (n,2,3), wgt (n,2)) at the given parameters."""
+        t_ = self.torch
+        s = self.st[1]
+        if self.with_ext:
+            s["params"].copy_(t_.as_tensor(np.asarray(params_c, dtype=np.float64)).to(self.dev))
+        s["pts"].copy_(t_.as_tensor(np.asarray(pts, dtype=np.float64).reshape(-1, 3)).to(self.dev))
+        self._eval(s, want_j=True)
+        return (s["res"].cpu().numpy(), s["Jc"].cpu().numpy() if self.with_ext else None, s["Jp"].cpu().numpy(),
+                s["wgt"].cpu().numpy())
+
+    # -- LM
+    def solve(self, params_c0, pts0, max_nfev=1000, ftol=1e-10, xtol=1e-8, lam0=1e-3, verbose=0):
+        t_ = self.torch
+        s, t = self.st
+        if self.with_ext:
+            s["params"].copy_(t_.as_tensor(np.asarray(params_c0, dtype=np.float64)).to(self.dev))
+        s["pts"].copy_(t_.as_tensor(np.asarray(pts0, dtype=np.float64).reshape(-1, 3)).to(self.dev))
+        self._eval(s)
+        F, _ = self._sum(s["cost"])
+        f0 = s["res"].cpu().numpy().ravel().copy()
+        F0 = F
+        lam = lam0
+        nfev, it = 1, 0
+        status = "max_nfev"
+        n6 = 6 * self.C
+        while nfev < max_nfev:
+            it += 1
+            accepted = False
+            for _ in range(15):
+                if self.with_ext:
+                    self.h.call_dev("acino_sba_schur_dev", self.n_pts, self.C, self.pt_ptr, self.obs, self.cam_idx, s["res"],
+                                    s["Jc"], s["Jp"], s["wgt"], float(lam), self.partial, self.S, self.dc)
+                    self.h.call_dev("acino_sba_dense_solve_dev", n6, self.S, self.dc, self.info)
+                self.h.call_dev("acino_sba_backsub_dev", self.n_pts, self.C, self.pt_ptr, self.obs, self.cam_idx, s["res"],
+                                s["Jc"] if self.with_ext else None, s["Jp"], s["wgt"], float(lam),
+                                self.dc if self.with_ext else None, s["pts"], t["pts"], self.dp)
+                self.h.call_dev("acino_sba_pred_dev", self.n_obs, self.cam_idx, self.pt_idx, s["res"],
+                                s["Jc"] if self.with_ext else None, s["Jp"], s["wgt"], self.dc if self.with_ext else None,
+                                self.dp, self.pred)
+                if self.with_ext:
+                    # dc is camera-major [rvec_a | t_a]; the parameter vector is [all rvecs | all t]
+                    t_.add(s["params"], self.dc.view(self.C, 2, 3).transpose(0, 1).reshape(-1), out=t["params"])
+                self._eval(t)
+                nfev += 1
+                Ft, pred = self._sum(t["cost"], self.pred)
+                rho = (F - Ft) / pred if pred > 0 else -1.0
+                if verbose >= 2:
+                    print(f"   it {it:4d} nfev {nfev:4d} lam {lam:9.2e} cost {F:.6e} -> {Ft:.6e} pred {pred:9.2e} rho {rho:6.3f}")
+                if Ft < F and rho > 1e-4:
+                    accepted = True
+                    dF = F - Ft
+                    xs = float(t_.sqrt((self.dp ** 2).sum() + ((self.dc ** 2).sum() if self.with_ext else 0.0)).item())
+                    xn = float(t_.sqrt((t["pts"] ** 2).sum() + ((t["params"] ** 2).sum() if self.with_ext else 0.0)).item())
+                    F = Ft
+                    s, t = t, s
+                    lam = max(lam / 3, 1e-15) if rho > 0.75 else (lam * 2 if rho < 0.25 else lam)
+                    break
+                lam *= 4
+                if nfev >= max_nfev:
+                    break
+            if not accepted:
+                status = "no_progress" if nfev < max_nfev else "max_nfev"
+                break
+            if dF < ftol * F:
+                status = "ftol"
+                break
+            if xs < xtol * (xtol + xn):
+                status = "xtol"
+                break
+        self.st = [s, t]
+        t_.cuda.synchronize(self.dev)
+        return dict(params=s["params"].cpu().numpy(), pts=s["pts"].cpu().numpy(), fun=s["res"].cpu().numpy().ravel(),
+                    f0=f0, cost0=F0, cost=F, nfev=nfev, iters=it, status=status, info=int(self.info.item()))
+
+
+# ---- reference-named entry points ------------------------------------------------------------------
+def cost_func_points_only(params, n_points, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr, points_2d,
+                          project_func=None):
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, with_extrinsics=False)
+    prob.set_fixed_cameras(r_arr, t_arr)
+    return prob.residuals(None, params_to_points_only(params, n_points))
+
+
+def cost_func_points_extrinsics(params, n_cameras, n_points, point_3d_indices, camera_indices, k_arr, d_arr, points_2d,
+                                project_func=None):
+    params = np.asarray(params, dtype=np.float64)
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points)
+    return prob.residuals(params[:6 * n_cameras], params[6 * n_cameras:])
+
+
+def jac_points_extrinsics(params, n_cameras, n_points, point_3d_indices, camera_indices, k_arr, d_arr, points_2d,
+                          project_func=None):
+    """Analytic Jacobian of cost_func_points_extrinsics as a scipy.sparse CSR matrix in the reference's
+    parameter layout - a drop-in ``jac=`` for scipy.optimize.least_squares."""
+    from scipy.sparse import csr_matrix
+
+    params = np.asarray(params, dtype=np.float64)
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points)
+    _, Jc, Jp, _ = prob.jacobian_blocks(params[:6 * n_cameras], params[6 * n_cameras:])
+    n = len(point_3d_indices)
+    ci = np.asarray(camera_indices, dtype=np.int64)
+    pi = np.asarray(point_3d_indices, dtype=np.int64)
+    rows = np.repeat(np.arange(2 * n), 9).reshape(n, 2, 9)
+    cols = np.empty((n, 2, 9), dtype=np.int64)
+    vals = np.empty((n, 2, 9))
+    for k in range(3):
+        cols[:, :, k] = (3 * ci + k)[:, None]
+        cols[:, :, 3 + k] = (3 * n_cameras + 3 * ci + k)[:, None]
+        cols[:, :, 6 + k] = (6 * n_cameras + 3 * pi + k)[:, None]
+    vals[:, :, 0:6] = Jc
+    vals[:, :, 6:9] = Jp
+    return csr_matrix((vals.ravel(), (rows.ravel(), cols.ravel())), shape=(2 * n, 6 * n_cameras + 3 * n_points))
+
+
+def bundle_adjust_points_only(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr,
+                              project_func=None, f_scale=50, verbose=0):
+    """calib.py:327-341: cauchy f_scale=50, ftol=1e-15, max_nfev=500 -> (obj_pts, residuals)."""
+    n_points = len(points_3d)
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, with_extrinsics=False,
+                      f_scale=f_scale)
+    prob.set_fixed_cameras(r_arr, t_arr)
+    t0 = time.time()
+    out = prob.solve(None, np.asarray(points_3d, dtype=np.float64), max_nfev=500, ftol=1e-15, verbose=verbose)
+    print("Optimization took {0:.0f} seconds".format(time.time() - t0))
+    residuals = dict(before=out["f0"], after=out["fun"])
+    return out["pts"], residuals
+
+
+def bundle_adjust_board_points_only(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr, r_arr, t_arr, triangulate_func=None,
+                                    project_func=None):
+    p2, p3, pi, ci = prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr,
+                                                                    r_arr, t_arr, triangulate_func)
+    return bundle_adjust_points_only(p2, p3, pi, ci, k_arr, d_arr, r_arr, t_arr, project_func)
+
+
+def bundle_adjust_points_and_extrinsics(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr,
+                                        project_func=None, verbose=0, return_info=False):
+    """calib.py:369-390: cauchy f_scale=1, ftol=1e-10, max_nfev=1000
+    -> (obj_pts (n,3), r_arr (C,3,3), t_arr (C,3,1), residuals dict(before, after))."""
+    n_points = len(points_3d)
+    n_cameras = len(k_arr)
+    r_vecs = np.array([rodrigues_to_vec(r) for r in r_arr], dtype=np.float64).flatten()
+    t_vecs = np.asarray(t_arr, dtype=np.float64).flatten()
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points)
+    t0 = time.time()
+    out = prob.solve(np.concatenate([r_vecs, t_vecs]), np.asarray(points_3d, dtype=np.float64), max_nfev=1000, ftol=1e-10,
+                     verbose=verbose)
+    print("Optimization took {0:.0f} seconds".format(time.time() - t0))
+    obj_pts, r_new, t_new = params_to_points_extrinsics(np.concatenate([out["params"], out["pts"].ravel()]), n_cameras,
+                                                        n_points)
+    residuals = dict(before=out["f0"], after=out["fun"])
+    if return_info:
+        return obj_pts, r_new, t_new, residuals, out
+    return obj_pts, r_new, t_new, residuals
+
+
+def bundle_adjust_board_points_and_extrinsics(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr, r_arr, t_arr,
+                                              triangulate_func=None, project_func=None):
+    p2, p3, pi, ci = prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr,
+                                                                    r_arr, t_arr, triangulate_func)
+    return bundle_adjust_points_and_extrinsics(p2, p3, pi, ci, k_arr, d_arr, r_arr, t_arr, project_func)
+
+
+def sba_board_points_fisheye(scene_fpath, points_fpaths, out_fpath, manual_points_fpath=None,
+                             manual_points_only=False):
+    """app.py:201-223: load points + scene, refine extrinsics, save the ``*_sba.json`` scene."""
+    from . import utils
+
+    img_pts_arr, fnames_arr = [], []
+    board_shape = None
+    for fp in points_fpaths:
+        points, fnames, board_shape, _, _ = utils.load_points(fp)
+        img_pts_arr.append(points)
+        fnames_arr.append(fnames)
+    k_arr, d_arr, r_arr, t_arr, cam_res = utils.load_scene(scene_fpath)
+    assert len(k_arr) == len(img_pts_arr)
+    obj_pts, r_new, t_new, res = bundle_adjust_board_points_and_extrinsics(img_pts_arr, fnames_arr, board_shape, k_arr,
+                                                                           d_arr, r_arr, t_arr)
+    utils.save_scene(out_fpath, k_arr, d_arr, r_new, t_new, cam_res)
+    return res

@@ -147,6 +147,46 @@ int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, cons
                           const double* P, const double* Q, const double* rhs, double* x,
                           void* cuda_stream);
 
+/* ---- sparse bundle adjustment building blocks (fp64, device pointers, stream-ordered) ---------
+ * Replace cost_func_points_extrinsics / cost_func_points_only (calib.py:312-316,355-359) and the
+ * finite-difference Jacobian + TRF step SciPy's least_squares performs on them (calib.py:335,381).
+ * Parameter layout = the reference's (calib.py:345-352, 373-375):
+ *   params = [rvec_0..rvec_{C-1} | t_0..t_{C-1}] (6C doubles), points [n_pts][3] separately.
+ * Observation i: pixel uv[i] (float32 like points_2d, calib.py:259), camera cam_idx[i], point
+ * pt_idx[i]; residual order [u0,v0,u1,v1,...].  Per observation: res [2], Jc [2][6] (d/d rvec,
+ * d/d t of its camera), Jp [2][3] (d/d its point), wgt [2] = Cauchy rho'((f/f_scale)^2),
+ * cost = 0.5 f_scale^2 ln(1 + (f/f_scale)^2) summed over the two coordinates (SciPy's loss). */
+int64_t acino_sba_cam_bytes(void);                 /* size of one opaque device camera record */
+/* params != NULL: cameras from the parameter vector (Rodrigues + derivative); else from R, t */
+int acino_sba_cams_dev(acino_handle* h, int n_cams, const double* params, const double* R,
+                       const double* t, const double* K, const double* D, void* cams,
+                       void* cuda_stream);
+/* Jp == NULL: residuals (+ cost) only; Jc == NULL: points-only problem */
+int acino_sba_eval_dev(acino_handle* h, int n_obs, const void* cams, const double* pts,
+                       const float* uv, const int32_t* cam_idx, const int32_t* pt_idx, double f_scale,
+                       double* res, double* Jc, double* Jp, double* wgt, double* cost,
+                       void* cuda_stream);
+/* Schur complement onto the 6C x 6C camera system with Marquardt damping lam; points in CSR form
+ * (pt_ptr [n_pts+1], obs [n_obs] observation ids grouped by point).  partial: workspace of
+ * acino_sba_schur_partial_size(n_pts, n_cams) doubles.  S [6C][6C], rhs [6C]. */
+int64_t acino_sba_schur_partial_size(int n_pts, int n_cams);
+int acino_sba_schur_dev(acino_handle* h, int n_pts, int n_cams, const int32_t* pt_ptr,
+                        const int32_t* obs, const int32_t* cam_idx, const double* res, const double* Jc,
+                        const double* Jp, const double* wgt, double lam, double* partial, double* S,
+                        double* rhs, void* cuda_stream);
+/* x <- S^-1 x, n <= 96 (Cholesky in one CTA); info != 0: non-positive pivot */
+int acino_sba_dense_solve_dev(acino_handle* h, int n, double* S, double* x, int32_t* info,
+                              void* cuda_stream);
+/* per point: dp = -(V + lam diag V)^-1 (gv + sum W^T dc); pts_trial = pts + dp (dc / Jc may be NULL) */
+int acino_sba_backsub_dev(acino_handle* h, int n_pts, int n_cams, const int32_t* pt_ptr,
+                          const int32_t* obs, const int32_t* cam_idx, const double* res, const double* Jc,
+                          const double* Jp, const double* wgt, double lam, const double* dc,
+                          const double* pts, double* pts_trial, double* dp, void* cuda_stream);
+/* per observation model reduction -(w r J d) - 1/2 w (J d)^2 */
+int acino_sba_pred_dev(acino_handle* h, int n_obs, const int32_t* cam_idx, const int32_t* pt_idx,
+                       const double* res, const double* Jc, const double* Jp, const double* wgt,
+                       const double* dc, const double* dp, double* pred, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

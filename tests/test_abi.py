@@ -112,3 +112,13 @@ def test_dlc_tables_to_dense(tmp_path):
     # frame 1, camera 1, spine = row 1 of the second table: x = 6*1+3+100, y = +4
     assert meas[0, 1, 1, 0] == 109 and meas[0, 1, 1, 1] == 110 and abs(lik[0, 1, 1] - 0.2) < 1e-6
     assert abs(lik[2, 0, 0] - 0.9) < 1e-6
+
+
+def test_rotation_conversions_match_cv2_golden():
+    from conftest import golden
+    from acinoset_b200 import rotations
+
+    g = golden("fisheye.npz")
+    for rv, Rm, rb in zip(g["rvec"], g["rmat"], g["rvec_back"]):
+        assert np.abs(rotations.rodrigues_to_mat(rv) - Rm).max() < 1e-14
+        assert np.abs(rotations.rodrigues_to_vec(Rm) - rb).max() < 1e-12
