@@ -70,3 +70,114 @@ def unpack_upper(Hu):
     H[..., iu[0], iu[1]] = Hu
     H[..., iu[1], iu[0]] = Hu
     return H
+
+
+# ---- full trajectory estimation: reference entry point -------------------------------------------
+def derived_velocities(x, Ts):
+    """dx, ddx of the output pickle from the optimised x (backward-Euler collocation,
+    all_optimizations.py:369-383; the free leading values follow SURVEY.md appendix B6)."""
+    x = np.asarray(x, dtype=np.float64)
+    N = x.shape[0]
+    dx = np.zeros_like(x)
+    ddx = np.zeros_like(x)
+    if N > 1:
+        dx[1:] = (x[1:] - x[:-1]) / Ts
+    if N > 2:
+        ddx[2:] = (dx[2:] - dx[1:-1]) / Ts
+        ddx[1] = ddx[2]
+        ddx[0] = ddx[1]
+    if N > 1:
+        dx[0] = dx[1] - Ts * ddx[1]
+    return dx, ddx
+
+
+def initial_guess(points_3d_df, start_frame, end_frame, N):
+    """Reference initialisation (all_optimizations.py:269-277,333-337): linear regression of the
+    triangulated nose over frames -> x,y,z lines; psi0 = atan2(y_slope, x_slope); all else 0."""
+    from scipy.stats import linregress
+
+    nose = points_3d_df[points_3d_df["marker"] == "nose"][["frame", "x", "y", "z"]].values.astype(np.float64)
+    if len(nose) < 2:
+        raise ValueError("need at least two triangulated nose points to initialise the trajectory")
+    xs, xi, *_ = linregress(nose[:, 0], nose[:, 1])
+    ys, yi, *_ = linregress(nose[:, 0], nose[:, 2])
+    zs, zi, *_ = linregress(nose[:, 0], nose[:, 3])
+    frame_est = np.arange(end_frame)
+    x0 = np.zeros((N, N_ACTIVE))
+    x0[:, 0] = (frame_est * xs + xi)[start_frame:start_frame + N]
+    x0[:, 1] = (frame_est * ys + yi)[start_frame:start_frame + N]
+    x0[:, 2] = (frame_est * zs + zi)[start_frame:start_frame + N]
+    x0[:, 20] = np.arctan2(ys, xs)        # psi0 (slot 31 of the 45-vector, all_optimizations.py:337)
+    return x0
+
+
+def fte_solve(points_2d_df, k_arr, d_arr, r_arr, t_arr, start_frame, end_frame, dlc_thresh, fps, device=0,
+              markers=None, x0=None, verbose=False, **lm_kwargs):
+    """The compute of ``fte()`` (all_optimizations.py:22-566) without the file I/O.
+
+    points_2d_df: long-form DataFrame [frame, camera, marker, x, y, likelihood]; frames
+    [start_frame, end_frame) (0-based).  Returns dict(positions (N,20,3), x, dx, ddx (N,25),
+    start_frame, info) - the schema of the reference's fte.pickle (:540-559)."""
+    from . import calib, lm, utils
+
+    markers = MARKERS if markers is None else list(markers)
+    N = int(end_frame - start_frame)
+    Ts = 1.0 / fps
+    d4 = np.asarray(d_arr, dtype=np.float64).reshape(-1, 4)
+    h = set_scene(k_arr, d4, r_arr, t_arr, device)
+    if x0 is None:
+        pts3d = calib.get_pairwise_3d_points_from_df(points_2d_df[points_2d_df["likelihood"] > dlc_thresh], k_arr, d4,
+                                                     r_arr, t_arr, calib.triangulate_points_fisheye, device=device)
+        x0 = initial_guess(pts3d, start_frame, end_frame, N)
+    meas, lik = utils.dlc_df_to_dense(points_2d_df, len(k_arr), markers, start_frame, N)
+    w = meas_weights(lik, dlc_thresh)
+    solver = lm.FTESolver(h, meas, w, Ts)
+    x, info = solver.solve(x0, verbose=verbose, **lm_kwargs)
+    positions = pose_to_3d(x, device).astype(np.float64)
+    dx, ddx = derived_velocities(x, Ts)
+    return dict(positions=positions, x=x, dx=dx, ddx=ddx, start_frame=start_frame, info=info)
+
+
+def fte(DATA_DIR, start_frame, end_frame, dlc_thresh, fps=None, device=0, verbose=False):
+    """Reference signature (all_optimizations.py:22): reads ``DATA_DIR/dlc/*.h5|csv`` and the scene
+    file found above DATA_DIR, solves, and writes ``DATA_DIR/fte/fte.pickle``
+    {positions, x, dx, ddx, start_frame}.  ``start_frame`` is 1-based like the reference's CLI;
+    ``end_frame`` = -1 means the last frame.  fps is read from ``DATA_DIR/cam*.mp4`` when not given."""
+    import os
+    import pickle
+    from glob import glob
+    from time import time
+
+    from . import utils
+
+    t0 = time()
+    assert os.path.exists(DATA_DIR)
+    out_dir = os.path.join(DATA_DIR, "fte")
+    dlc_dir = os.path.join(DATA_DIR, "dlc")
+    assert os.path.exists(dlc_dir)
+    os.makedirs(out_dir, exist_ok=True)
+    paths = sorted(glob(os.path.join(dlc_dir, "*.h5"))) or sorted(glob(os.path.join(dlc_dir, "*.csv")))
+    df = utils.load_dlc_points_as_df(paths, verbose=False)
+    k_arr, d_arr, r_arr, t_arr, cam_res, n_cams, scene_fpath = utils.find_scene_file(DATA_DIR, verbose=False)
+    tot_frames = int(df["frame"].max()) + 1
+    if fps is None:
+        import cv2
+
+        vids = sorted(glob(os.path.join(DATA_DIR, "cam[1-9].mp4")))
+        assert vids, "fps not given and no cam[1-9].mp4 next to the data"
+        cap = cv2.VideoCapture(vids[0])
+        fps = cap.get(cv2.CAP_PROP_FPS)
+        cap.release()
+    assert end_frame <= tot_frames, f"end_frame must be less than or equal to {tot_frames}"
+    end_frame = tot_frames if end_frame == -1 else end_frame
+    start_frame -= 1          # 0 based indexing (all_optimizations.py:59)
+    assert start_frame >= 0
+    print("\nInitialization took {0:.2f} seconds\n".format(time() - t0))
+    t0 = time()
+    out = fte_solve(df, k_arr, d_arr, r_arr, t_arr, start_frame, end_frame, dlc_thresh, fps, device=device, verbose=verbose)
+    print("\nOptimization took {0:.2f} seconds\n".format(time() - t0))
+    out_fpath = os.path.join(out_dir, "fte.pickle")
+    with open(out_fpath, "wb") as f:
+        pickle.dump({k: out[k] for k in ("positions", "x", "dx", "ddx", "start_frame")}, f)
+    print(f"Saved {out_fpath}")
+    return out
