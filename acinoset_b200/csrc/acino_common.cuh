@@ -21,6 +21,7 @@ struct CamF {
     float t[3];
     float fx, fy, cx, cy;
     float D[4];
+    float D3[4];          // 3 k1, 5 k2, 7 k3, 9 k4 (derivative of the distortion polynomial)
 };
 
 struct CamD {
@@ -39,6 +40,8 @@ struct LossF {
     float p3c;            // a b - a^2/2
     float p4;             // a b - a^2/2 + a (c-b)/2
     float rho0;           // rho(0)
+    float kappa;          // a / (2 (c - b))
+    float m2kappa;        // -2 kappa
 };
 
 struct SceneF {
@@ -138,6 +141,60 @@ __device__ __forceinline__ void redescending(const LossF& L, const float e, floa
     drho = (1.0f - sa) * e - dsa * p1 + (dsa - dsb) * p2 + gab * L.a + (dsb - dsc) * p3 + gbc * dp3 +
            dsc * L.p4;
     psi = e > 0.0f ? fmaxf(__fdividef(drho, e), 1.0f - sa) : 1.0f - sa;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused-kernel variants (fp32, instruction-count optimised; same arithmetic, fewer operations).
+
+__device__ __forceinline__ float fast_rsqrt(float x) {   // MUFU.RSQ, no denormal fix-up (x >= 1e-12 here)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// atan(r) for r >= 0 given ir = 1/r: degree-7 polynomial in z^2 on z = min(r, 1/r) in [0,1]
+// (Chebyshev-node fit, max abs error 1.2e-7), atan(r) = pi/2 - atan(1/r) for r > 1.
+__device__ __forceinline__ float atan_pos(float r, float ir) {
+    const float z = fminf(r, ir);
+    const float s = z * z;
+    float p = 0.003866738872602582f;
+    p = fmaf(p, s, -0.02002674713730812f);
+    p = fmaf(p, s, 0.04891432076692581f);
+    p = fmaf(p, s, -0.08009681850671768f);
+    p = fmaf(p, s, 0.1086575910449028f);
+    p = fmaf(p, s, -0.14257045090198517f);
+    p = fmaf(p, s, 0.19998681545257568f);
+    p = fmaf(p, s, -0.33333322405815125f);
+    p = p * s;
+    p = fmaf(p, z, z);
+    return r > 1.0f ? 1.5707963267948966f - p : p;
+}
+
+// Redescending loss, algebraically regrouped (exactly the literal blend of build.py:388-395):
+//   rho  = e^2/2 - sa ta^2/2 - kappa sb tb^2 + kappa sc tc^2,   t* = e - {a,b,c}, kappa = a/(2(c-b))
+//   rho' = e - sa ta - 2 kappa (sb tb - sc tc) - S1 + sa(sa ta^2)/2 ... (product rule on the gates)
+// Returns rho, psi_raw = rho'(e)/e (unclamped, used for the gradient: d rho/d r = psi_raw w^2 r) and
+// the curvature floor 1 - sigma_a.  e must be in [tiny, 40].
+__device__ __forceinline__ void redescending_fast(const LossF& L, const float e, float& rho, float& psi_raw,
+                                                  float& floor_) {
+    const float E = __expf(-e);
+    const float sa = fast_rcp(fmaf(E, L.ea, 1.0f));
+    const float sb = fast_rcp(fmaf(E, L.eb, 1.0f));
+    const float sc = fast_rcp(fmaf(E, L.ec, 1.0f));
+    const float ta = e - L.a, tb = e - L.b, tc = e - L.c;
+    const float qa = sa * ta, qb = sb * tb, qc = sc * tc;
+    const float ra = qa * ta, rb = qb * tb, rc = qc * tc;
+    const float S1 = fmaf(L.kappa, rb - rc, 0.5f * ra);
+    rho = fmaf(0.5f * e, e, -S1);
+    float d = e - qa;
+    d = fmaf(L.m2kappa, qb - qc, d);
+    d -= S1;
+    float w1 = sb * rb;
+    w1 = fmaf(-sc, rc, w1);
+    d = fmaf(L.kappa, w1, d);
+    d = fmaf(0.5f * sa, ra, d);
+    psi_raw = d * fast_rcp(e);
+    floor_ = 1.0f - sa;
 }
 
 }  // namespace acino

@@ -95,6 +95,8 @@ static void set_loss(LossF& L, double a, double b, double c) {
     auto step = [](double s, double x) { return 1.0 / (1.0 + std::exp(-(x - s))); };
     const double sa = step(a, 0), sb = step(b, 0), sc = step(c, 0);
     const double u = c / (c - b);
+    L.kappa = (float)(a / (2 * (c - b)));
+    L.m2kappa = (float)(-a / (c - b));
     L.rho0 = (float)((sa - sb) * (-a * a / 2) + (sb - sc) * (a * b - a * a / 2 + (a * (c - b) / 2) * (1 - u * u)) +
                      sc * (a * b - a * a / 2 + a * (c - b) / 2));
 }
@@ -161,7 +163,7 @@ int acino_set_cameras(acino_handle* h, int n_cams, const double* K, const double
         CamF& cf = h->scene.cam[c];
         for (int i = 0; i < 9; ++i) { cd.R[i] = R[c * 9 + i]; cf.R[i] = (float)cd.R[i]; }
         for (int i = 0; i < 3; ++i) { cd.t[i] = t[c * 3 + i]; cf.t[i] = (float)cd.t[i]; }
-        for (int i = 0; i < 4; ++i) { cd.D[i] = D[c * 4 + i]; cf.D[i] = (float)cd.D[i]; }
+        for (int i = 0; i < 4; ++i) { cd.D[i] = D[c * 4 + i]; cf.D[i] = (float)cd.D[i]; cf.D3[i] = (float)((2 * i + 3) * cd.D[i]); }
         cd.fx = K[c * 9 + 0]; cd.fy = K[c * 9 + 4]; cd.cx = K[c * 9 + 2]; cd.cy = K[c * 9 + 5];
         cf.fx = (float)cd.fx; cf.fy = (float)cd.fy; cf.cx = (float)cd.cx; cf.cy = (float)cd.cy;
     }

@@ -31,7 +31,7 @@
 namespace acino {
 
 constexpr int TAU_STRIDE = 8;           // (omega, v) padded to 8 floats: one LDS.128 + one LDS.64
-constexpr int TAUF = NANG * TAU_STRIDE + 4;  // per-frame stride 180 = 20 (mod 32): conflict-free across frames
+constexpr int TAUF = (NANG + 1) * TAU_STRIDE + 4;  // 22 twists + one all-zero slot; stride 188 = 28 (mod 32): conflict-free across frames
 constexpr int N_PAIR = NANG * (NANG + 1) / 2;  // 253 unordered angle pairs (incl. the diagonal)
 
 // joint of each angle slot (angle slot s <-> active slot 3+s):
@@ -49,8 +49,10 @@ constexpr bool joint_is_anc(int a, int k) {  // a ancestor-or-self of k
 }
 
 // One entry per unordered pair of angle slots.  Related pairs (one joint is an ancestor-or-self of
-// the other): H = tau_al . y_be with `be` the deeper angle; bits 0-4 al, 5-9 be, 10-18 packed index.
-// Unrelated pairs (disjoint subtrees) are structural zeros: bit 31 set.  Zeros are sorted last.
+// the other): H = tau_al . y_be with `be` the deeper angle.  Entry = float offsets into the frame's
+// tau / y arrays and the packed H index: bits 0-7 al*8, 8-15 be*8, 16-24 index.  Unrelated pairs
+// (disjoint subtrees) are structural zeros: they point at the all-zero twist slot 22, so the same
+// branch-free dot product writes 0.  Zeros are sorted last.
 struct PairTable {
     unsigned e[N_PAIR];
     int joint[NANG];
@@ -67,8 +69,9 @@ constexpr PairTable make_pair_table() {
                 const int lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
                 const unsigned idx = (unsigned)(lo * NA - (lo * (lo - 1)) / 2 + (hi - lo));
                 if (pass == 0 && a_anc_b && (ja != jb || al <= be))
-                    t.e[n++] = (unsigned)al | ((unsigned)be << 5) | (idx << 10);
-                if (pass == 1 && !a_anc_b && !b_anc_a && al < be) t.e[n++] = 0x80000000u | (idx << 10);
+                    t.e[n++] = (unsigned)(al * TAU_STRIDE) | ((unsigned)(be * TAU_STRIDE) << 8) | (idx << 16);
+                if (pass == 1 && !a_anc_b && !b_anc_a && al < be)
+                    t.e[n++] = (unsigned)(NANG * TAU_STRIDE) | ((unsigned)(be * TAU_STRIDE) << 8) | (idx << 16);
             }
     for (int a = 0; a < NANG; ++a) t.joint[a] = k_angle_joint[a];
     return t;
@@ -84,8 +87,13 @@ struct __align__(16) Smem {
     unsigned tab[N_PAIR + 3];          // pair table (copy of c_tab.e)
     float Ij[FT][NJ][NSP];             // subtree spatial inertia + wrench per joint
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
+    unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
     union {
         float Il[FT * NL][NSP];        // per-marker spatial inertia + wrench   (P2 -> P3)
+        struct {                       // bulk-copied input tiles (kernel start -> end of the camera loop)
+            float2 meas[FT * ACINO_MAX_CAMS / 2 * NL];   // [FT][C][NL] (u,v), C <= 8 fits the union
+            float w[FT * ACINO_MAX_CAMS / 2 * NL];       // [FT][C][NL]
+        } in;
         struct {                       // staged outputs in their global layout  (P4 -> P5)
             float H[FT][NU];
             float g[FT][NA];
@@ -268,9 +276,37 @@ __device__ __forceinline__ void cheetah_fk(const float2* __restrict__ sc, const 
 #undef TH
 }
 
+// ---- bulk async copy (TMA, 1-D) + mbarrier helpers ------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 template <int FT, bool WANT_H>
 __global__ void __launch_bounds__(FT * NL, (FT == 8) ? 5 : 2)
-fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
+fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
                 const float* __restrict__ xg, const float* __restrict__ meas,
                 const float* __restrict__ wts, float* __restrict__ cost_out,
                 float* __restrict__ g_out, float* __restrict__ H_out) {
@@ -281,14 +317,33 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
     const int f0 = blockIdx.x * FT;
     const int nf = min(FT, n_frames - f0);
     const int C = scene.n_cams;
+    // the input tiles of a full CTA are contiguous, 16-byte aligned blocks of global memory: stage them
+    // with three 1-D bulk async copies (TMA) that overlap the forward kinematics
+    const bool staged = use_bulk && nf == FT && C <= ACINO_MAX_CAMS / 2;
 
-    // ---- P0: state -> smem (coalesced), zero-fill frames past the end; pair table -> smem
-    for (int i = tid; i < FT * NA; i += NT) {
-        const int f = i / NA;
-        (&S.x[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
+    // ---- P0: kick off the input copies; pair table + zero twist slot -> smem
+    if (staged) {
+        if (tid == 0) {
+            mbar_init(&S.mbar[0], 1);
+            mbar_init(&S.mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const unsigned bx = FT * NA * 4, bm = FT * C * NL * 8, bw = FT * C * NL * 4;
+            mbar_expect_tx(&S.mbar[0], bx);
+            bulk_g2s(&S.x[0][0], xg + (size_t)f0 * NA, bx, &S.mbar[0]);
+            mbar_expect_tx(&S.mbar[1], bm + bw);
+            bulk_g2s(&S.in.meas[0], meas + (size_t)f0 * C * NL * 2, bm, &S.mbar[1]);
+            bulk_g2s(&S.in.w[0], wts + (size_t)f0 * C * NL, bw, &S.mbar[1]);
+        }
+    } else {
+        for (int i = tid; i < FT * NA; i += NT) {
+            const int f = i / NA;
+            (&S.x[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
+        }
     }
     for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
+    if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
     __syncthreads();
+    if (staged) mbar_wait(&S.mbar[0], 0);
 
     // ---- P1a: sin/cos of the 22 angles, one thread per (angle, frame)
     for (int t = tid; t < FT * NANG; t += NT) {
@@ -316,9 +371,15 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
         float a00 = 0.f, a01 = 0.f, a02 = 0.f, a11 = 0.f, a12 = 0.f, a22 = 0.f;
         float b0 = 0.f, b1 = 0.f, b2 = 0.f, cst = 0.f;
         const size_t base = ((size_t)(f0 + f) * C) * NL + l;
+        if (staged) mbar_wait(&S.mbar[1], 0);
         for (int c = 0; c < C; ++c) {
             float um = 0.f, vm = 0.f, w = 0.f;
-            if (live) {
+            if (staged) {
+                const float2 m = S.in.meas[(f * C + c) * NL + l];
+                w = S.in.w[(f * C + c) * NL + l];
+                um = m.x;
+                vm = m.y;
+            } else if (live) {
                 const float2 m = __ldg(reinterpret_cast<const float2*>(meas) + base + (size_t)c * NL);
                 w = __ldg(wts + base + (size_t)c * NL);
                 um = m.x;
@@ -328,43 +389,57 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
             const float xc = fmaf(cam.R[0], wx, fmaf(cam.R[1], wy, fmaf(cam.R[2], wz, cam.t[0])));
             const float yc = fmaf(cam.R[3], wx, fmaf(cam.R[4], wy, fmaf(cam.R[5], wz, cam.t[1])));
             const float zc = fmaf(cam.R[6], wx, fmaf(cam.R[7], wy, fmaf(cam.R[8], wz, cam.t[2])));
-            ProjOut<float> pr;
-            fisheye_cam<float, true>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
-            // residuals in a centred frame: (fx a s) + (cx - u_meas); zero-weight rows are
-            // exactly the constant rho(0) whatever the measurement holds
+            // Kannala-Brandt projection (pt3d_to_2d, all_optimizations.py:193-209) and its Jacobian
+            const float iz = fast_rcp(zc);
+            const float a = xc * iz, b = yc * iz;
+            const float r2 = fmaf(b, b, fmaf(a, a, 1e-12f));
+            const float ir = fast_rsqrt(r2);
+            const float r = r2 * ir;
+            const float th = atan_pos(r, ir);
+            const float th2 = th * th;
+            const float td = th * fmaf(th2, fmaf(th2, fmaf(th2, fmaf(th2, cam.D[3], cam.D[2]), cam.D[1]), cam.D[0]), 1.0f);
+            const float dtd = fmaf(th2, fmaf(th2, fmaf(th2, fmaf(th2, cam.D3[3], cam.D3[2]), cam.D3[1]), cam.D3[0]), 1.0f);
+            const float sd = td * ir;                                              // s = theta_d / r
+            const float q = fmaf(dtd, fast_rcp(1.0f + r2), -sd) * (ir * ir);     // (ds/dr)/r
+            const float aq = a * q, bq = b * q;
+            const float m00 = fmaf(a, aq, sd), m01 = b * aq, m11 = fmaf(b, bq, sd);
+            // residuals in a centred frame: (fx a s) + (cx - u_meas); zero-weight rows are exactly the
+            // constant rho(0) whatever the measurement holds
             const bool on = w != 0.f;
-            const float ru = on ? pr.u + (cam.cx - um) : 0.f;
-            const float rv = on ? pr.v + (cam.cy - vm) : 0.f;
-            float rho_u, d_u, psi_u, rho_v, d_v, psi_v;
-            redescending(scene.loss, fminf(fabsf(w * ru), 1e4f), rho_u, d_u, psi_u);
-            redescending(scene.loss, fminf(fabsf(w * rv), 1e4f), rho_v, d_v, psi_v);
+            const float ru = on ? fmaf(cam.fx, a * sd, cam.cx - um) : 0.f;
+            const float rv = on ? fmaf(cam.fy, b * sd, cam.cy - vm) : 0.f;
+            // world-frame Jacobian rows: J = diag(fx,fy)/z [m] [I | -(a,b)] R = c . G,  G_i = R_i - (a|b) R_2
+            const float g00 = fmaf(-a, cam.R[6], cam.R[0]), g01 = fmaf(-a, cam.R[7], cam.R[1]), g02 = fmaf(-a, cam.R[8], cam.R[2]);
+            const float g10 = fmaf(-b, cam.R[6], cam.R[3]), g11 = fmaf(-b, cam.R[7], cam.R[4]), g12 = fmaf(-b, cam.R[8], cam.R[5]);
+            const float fxi = cam.fx * iz, fyi = cam.fy * iz;
+            const float cu0 = fxi * m00, cu1 = fxi * m01, cv0 = fyi * m01, cv1 = fyi * m11;
+            const float Ju0 = fmaf(cu0, g00, cu1 * g10), Ju1 = fmaf(cu0, g01, cu1 * g11), Ju2 = fmaf(cu0, g02, cu1 * g12);
+            const float Jv0 = fmaf(cv0, g00, cv1 * g10), Jv1 = fmaf(cv0, g01, cv1 * g11), Jv2 = fmaf(cv0, g02, cv1 * g12);
+            // redescending loss of e = |w r| per coordinate
+            float rho_u, pr_u, fl_u, rho_v, pr_v, fl_v;
+            redescending_fast(scene.loss, fminf(fmaxf(fabsf(w * ru), 1e-20f), 40.0f), rho_u, pr_u, fl_u);
+            redescending_fast(scene.loss, fminf(fmaxf(fabsf(w * rv), 1e-20f), 40.0f), rho_v, pr_v, fl_v);
             cst += rho_u + rho_v;
-            // world-frame rows of the 2x3 Jacobian: J = Jc R
-            float Ju[3], Jv[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                Ju[k] = fmaf(pr.ju[0], cam.R[k], fmaf(pr.ju[1], cam.R[3 + k], pr.ju[2] * cam.R[6 + k]));
-                Jv[k] = fmaf(pr.jv[0], cam.R[k], fmaf(pr.jv[1], cam.R[3 + k], pr.jv[2] * cam.R[6 + k]));
-            }
-            // d rho / d r = sign(r) rho'(|w r|) w   (rho' itself can be negative next to the cusp at 0)
-            const float gu = (ru < 0.f ? -d_u : d_u) * w, gv = (rv < 0.f ? -d_v : d_v) * w;
+            // d rho / d r = sign(r) w rho'(e) = (rho'(e)/e) w^2 r ; curvature weight max(rho'/e, 1 - sigma_a) w^2
             const float w2 = w * w;
-            const float eu = psi_u * w2, ev = psi_v * w2;
-            b0 = fmaf(gu, Ju[0], fmaf(gv, Jv[0], b0));
-            b1 = fmaf(gu, Ju[1], fmaf(gv, Jv[1], b1));
-            b2 = fmaf(gu, Ju[2], fmaf(gv, Jv[2], b2));
+            const float gu = pr_u * (w2 * ru), gv = pr_v * (w2 * rv);
+            b0 = fmaf(gu, Ju0, fmaf(gv, Jv0, b0));
+            b1 = fmaf(gu, Ju1, fmaf(gv, Jv1, b1));
+            b2 = fmaf(gu, Ju2, fmaf(gv, Jv2, b2));
             if (WANT_H) {
-                const float tu0 = eu * Ju[0], tu1 = eu * Ju[1], tu2 = eu * Ju[2];
-                const float tv0 = ev * Jv[0], tv1 = ev * Jv[1], tv2 = ev * Jv[2];
-                a00 = fmaf(tu0, Ju[0], fmaf(tv0, Jv[0], a00));
-                a01 = fmaf(tu0, Ju[1], fmaf(tv0, Jv[1], a01));
-                a02 = fmaf(tu0, Ju[2], fmaf(tv0, Jv[2], a02));
-                a11 = fmaf(tu1, Ju[1], fmaf(tv1, Jv[1], a11));
-                a12 = fmaf(tu1, Ju[2], fmaf(tv1, Jv[2], a12));
-                a22 = fmaf(tu2, Ju[2], fmaf(tv2, Jv[2], a22));
+                const float eu = fmaxf(pr_u, fl_u) * w2, ev = fmaxf(pr_v, fl_v) * w2;
+                const float tu0 = eu * Ju0, tu1 = eu * Ju1, tu2 = eu * Ju2;
+                const float tv0 = ev * Jv0, tv1 = ev * Jv1, tv2 = ev * Jv2;
+                a00 = fmaf(tu0, Ju0, fmaf(tv0, Jv0, a00));
+                a01 = fmaf(tu0, Ju1, fmaf(tv0, Jv1, a01));
+                a02 = fmaf(tu0, Ju2, fmaf(tv0, Jv2, a02));
+                a11 = fmaf(tu1, Ju1, fmaf(tv1, Jv1, a11));
+                a12 = fmaf(tu1, Ju2, fmaf(tv1, Jv2, a12));
+                a22 = fmaf(tu2, Ju2, fmaf(tv2, Jv2, a22));
             }
         }
         S.costp[f][l] = cst;
+        if (staged) __syncthreads();   // the input tiles alias Il: every thread is done reading them
         // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]
         float* o = S.Il[tid];
         if (WANT_H) {
@@ -458,23 +533,24 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames,
     }
     __syncthreads();
 
-    // ---- P4b: one task per (angle pair, frame): H[al][be] = tau_al . y_be, or a structural zero
+    // ---- P4b: one entry per (angle pair, frame): H[al][be] = tau_al . y_be.  NT / FT = 20 exactly, so a
+    //      thread keeps its frame (tid % FT) and walks the table with stride 20: p = tid / FT + 20 k
     if (WANT_H) {
-        for (int task = tid; task < FT * N_PAIR; task += NT) {
-            const int p = task / FT;
-            const int f = task - p * FT;
-            const unsigned e = S.tab[p];
-            const int idx = (e >> 10) & 0x1FF;
-            float h = 0.f;
-            if (!(e >> 31)) {
-                const int al = e & 31, be = (e >> 5) & 31;
-                const float4 a0 = *reinterpret_cast<const float4*>(&S.tau[f][al * TAU_STRIDE]);
-                const float2 a1 = *reinterpret_cast<const float2*>(&S.tau[f][al * TAU_STRIDE + 4]);
-                const float4 y0 = *reinterpret_cast<const float4*>(&S.o.y[f][be * TAU_STRIDE]);
-                const float2 y1 = *reinterpret_cast<const float2*>(&S.o.y[f][be * TAU_STRIDE + 4]);
-                h = a0.x * y0.x + a0.y * y0.y + a0.z * y0.z + a0.w * y0.w + a1.x * y1.x + a1.y * y1.y;
+        const int f = tid % FT, p0 = tid / FT;
+        const float* tau_f = &S.tau[f][0];
+        const float* y_f = &S.o.y[f][0];
+        float* H_f = &S.o.H[f][0];
+#pragma unroll
+        for (int k = 0; k < (N_PAIR + NL - 1) / NL; ++k) {
+            const int p = p0 + NL * k;
+            if (p < N_PAIR) {
+                const unsigned e = S.tab[p];
+                const float4 a0 = *reinterpret_cast<const float4*>(tau_f + (e & 0xFFu));
+                const float2 a1 = *reinterpret_cast<const float2*>(tau_f + (e & 0xFFu) + 4);
+                const float4 y0 = *reinterpret_cast<const float4*>(y_f + ((e >> 8) & 0xFFu));
+                const float2 y1 = *reinterpret_cast<const float2*>(y_f + ((e >> 8) & 0xFFu) + 4);
+                H_f[e >> 16] = a0.x * y0.x + a0.y * y0.y + a0.z * y0.z + a0.w * y0.w + a1.x * y1.x + a1.y * y1.y;
             }
-            S.o.H[f][idx] = h;
         }
     }
     __syncthreads();
@@ -562,6 +638,9 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 template <int FT>
 static cudaError_t launch_fte_eval_ft(const SceneF& scene, int n_frames, const float* x, const float* meas,
                                       const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+    // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
+    // base pointers that decide
+    const int use_bulk = ((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0;
     const int grid = (n_frames + FT - 1) / FT;
     const size_t smem = sizeof(Smem<FT>);
     static bool attr_set = false;
@@ -573,9 +652,9 @@ static cudaError_t launch_fte_eval_ft(const SceneF& scene, int n_frames, const f
         attr_set = true;
     }
     if (H)
-        fte_eval_kernel<FT, true><<<grid, FT * NL, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, true><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     else
-        fte_eval_kernel<FT, false><<<grid, FT * NL, smem, stream>>>(scene, n_frames, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, false><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     return cudaGetLastError();
 }
 
