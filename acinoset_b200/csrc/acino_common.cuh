@@ -44,8 +44,18 @@ struct LossF {
     float m2kappa;        // -2 kappa
 };
 
+// Two cameras (2k, 2k+1) interleaved as float2 pairs: operands of the packed fp32 (FFMA2) path
+struct CamPairF {
+    float2 R[9];
+    float2 t[3];
+    float2 fx, fy, cx, cy;
+    float2 D[4];
+    float2 D3[4];
+};
+
 struct SceneF {
     CamF cam[ACINO_MAX_CAMS];
+    CamPairF pair[ACINO_MAX_CAMS / 2];
     LossF loss;
     int n_cams;
 };
@@ -195,6 +205,87 @@ __device__ __forceinline__ void redescending_fast(const LossF& L, const float e,
     d = fmaf(0.5f * sa, ra, d);
     psi_raw = d * fast_rcp(e);
     floor_ = 1.0f - sa;
+}
+
+// ------------------------------------------------------------------------------------------
+// Packed fp32 pairs: Blackwell (sm_100) issues fma/add/mul on two fp32 values per instruction
+// (PTX fma.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2).  Same FMA-pipe throughput as two scalar FFMAs but
+// half the issue slots - and this kernel is issue-bound.  A broadcast pair (s, s) is encoded by ptxas
+// as a scalar operand, so per-thread scalars and constants cost nothing extra.
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 pk(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ f2 bc(float s) { return pk(s, s); }
+__device__ __forceinline__ float lo(f2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+__device__ __forceinline__ float hi(f2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ f2 rcp2(f2 a) { return pk(fast_rcp(lo(a)), fast_rcp(hi(a))); }
+__device__ __forceinline__ f2 rsqrt2(f2 a) { return pk(fast_rsqrt(lo(a)), fast_rsqrt(hi(a))); }
+
+// atan of a pair r >= 0 given ir = 1/r (see atan_pos)
+__device__ __forceinline__ f2 atan_pos2(f2 r, f2 ir) {
+    const f2 z = pk(fminf(lo(r), lo(ir)), fminf(hi(r), hi(ir)));
+    const f2 s = mul2(z, z);
+    f2 p = bc(0.003866738872602582f);
+    p = fma2(p, s, bc(-0.02002674713730812f));
+    p = fma2(p, s, bc(0.04891432076692581f));
+    p = fma2(p, s, bc(-0.08009681850671768f));
+    p = fma2(p, s, bc(0.1086575910449028f));
+    p = fma2(p, s, bc(-0.14257045090198517f));
+    p = fma2(p, s, bc(0.19998681545257568f));
+    p = fma2(p, s, bc(-0.33333322405815125f));
+    p = mul2(p, s);
+    p = fma2(p, z, z);
+    const float pl = lo(p), ph = hi(p);
+    return pk(lo(r) > 1.0f ? 1.5707963267948966f - pl : pl, hi(r) > 1.0f ? 1.5707963267948966f - ph : ph);
+}
+
+// redescending_fast on a pair of e values in [tiny, 40]
+__device__ __forceinline__ void redescending_fast2(const LossF& L, const f2 e, f2& rho, f2& psi_raw, f2& floor_) {
+    const f2 ne = mul2(e, bc(-1.4426950408889634f));
+    const f2 E = pk(exp2f(lo(ne)), exp2f(hi(ne)));
+    const f2 one = bc(1.0f);
+    const f2 sa = rcp2(fma2(E, bc(L.ea), one));
+    const f2 sb = rcp2(fma2(E, bc(L.eb), one));
+    const f2 sc = rcp2(fma2(E, bc(L.ec), one));
+    const f2 ta = sub2(e, bc(L.a)), tb = sub2(e, bc(L.b)), tc = sub2(e, bc(L.c));
+    const f2 qa = mul2(sa, ta), qb = mul2(sb, tb), qc = mul2(sc, tc);
+    const f2 ra = mul2(qa, ta), rb = mul2(qb, tb), rc = mul2(qc, tc);
+    const f2 S1 = fma2(bc(L.kappa), sub2(rb, rc), mul2(ra, bc(0.5f)));
+    rho = sub2(mul2(mul2(e, bc(0.5f)), e), S1);
+    f2 d = sub2(e, qa);
+    d = fma2(bc(L.m2kappa), sub2(qb, qc), d);
+    d = sub2(d, S1);
+    const f2 w1 = sub2(mul2(sb, rb), mul2(sc, rc));
+    d = fma2(bc(L.kappa), w1, d);
+    d = fma2(mul2(sa, bc(0.5f)), ra, d);
+    psi_raw = mul2(d, rcp2(e));
+    floor_ = sub2(one, sa);
 }
 
 }  // namespace acino

@@ -167,6 +167,18 @@ int acino_set_cameras(acino_handle* h, int n_cams, const double* K, const double
         cd.fx = K[c * 9 + 0]; cd.fy = K[c * 9 + 4]; cd.cx = K[c * 9 + 2]; cd.cy = K[c * 9 + 5];
         cf.fx = (float)cd.fx; cf.fy = (float)cd.fy; cf.cx = (float)cd.cx; cf.cy = (float)cd.cy;
     }
+    // interleaved camera pairs for the packed-fp32 path; an odd last camera is paired with itself
+    // (its second lane always runs with weight 0)
+    for (int k = 0; k < (n_cams + 1) / 2; ++k) {
+        const CamF& a = h->scene.cam[2 * k];
+        const CamF& b = h->scene.cam[(2 * k + 1 < n_cams) ? 2 * k + 1 : 2 * k];
+        CamPairF& p = h->scene.pair[k];
+        for (int i = 0; i < 9; ++i) p.R[i] = make_float2(a.R[i], b.R[i]);
+        for (int i = 0; i < 3; ++i) p.t[i] = make_float2(a.t[i], b.t[i]);
+        for (int i = 0; i < 4; ++i) { p.D[i] = make_float2(a.D[i], b.D[i]); p.D3[i] = make_float2(a.D3[i], b.D3[i]); }
+        p.fx = make_float2(a.fx, b.fx); p.fy = make_float2(a.fy, b.fy);
+        p.cx = make_float2(a.cx, b.cx); p.cy = make_float2(a.cy, b.cy);
+    }
     h->scene.n_cams = n_cams;
     h->have_cams = true;
     return ACINO_OK;

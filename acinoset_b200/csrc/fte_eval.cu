@@ -85,7 +85,7 @@ struct __align__(16) Smem {
     float2 sc[FT][NANG];               // (sin, cos) of every angle
     float costp[FT][NL];               // per-(frame, marker) cost partials
     unsigned tab[N_PAIR + 3];          // pair table (copy of c_tab.e)
-    float Ij[FT][NJ][NSP];             // subtree spatial inertia + wrench per joint
+    __align__(16) float Ij[FT][NJ][NSP + 1];   // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads)
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
     union {
@@ -304,8 +304,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-template <int FT, bool WANT_H>
-__global__ void __launch_bounds__(FT * NL, (FT == 8) ? 5 : 2)
+#ifdef ACINO_PHASE_TIMING
+__device__ long long g_phase_cycles[16];
+__device__ int g_phase_count;
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_phase_cycles[i], (unsigned long long)(_t - _tprev)); _tprev = _t; } } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
+template <int FT, bool WANT_H, int MINB, int NPAIR>
+__global__ void __launch_bounds__(FT * NL, MINB)
 fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
                 const float* __restrict__ xg, const float* __restrict__ meas,
                 const float* __restrict__ wts, float* __restrict__ cost_out,
@@ -320,6 +328,9 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
     // the input tiles of a full CTA are contiguous, 16-byte aligned blocks of global memory: stage them
     // with three 1-D bulk async copies (TMA) that overlap the forward kinematics
     const bool staged = use_bulk && nf == FT && C <= ACINO_MAX_CAMS / 2;
+#ifdef ACINO_PHASE_TIMING
+    long long _tprev = clock64();
+#endif
 
     // ---- P0: kick off the input copies; pair table + zero twist slot -> smem
     if (staged) {
@@ -344,6 +355,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
     if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
     __syncthreads();
     if (staged) mbar_wait(&S.mbar[0], 0);
+    PHASE_MARK(0);
 
     // ---- P1a: sin/cos of the 22 angles, one thread per (angle, frame)
     for (int t = tid; t < FT * NANG; t += NT) {
@@ -353,6 +365,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         S.sc[f][a] = make_float2(sn, cs);
     }
     __syncthreads();
+    PHASE_MARK(1);
 
     // ---- P1b: rotation chain, one thread per frame
     if (tid < FT) {
@@ -360,6 +373,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         cheetah_fk(S.sc[tid], w);
     }
     __syncthreads();
+    PHASE_MARK(2);
 
     // ---- P2: projection + loss, one thread per (frame, marker), loop over cameras
     {
@@ -368,78 +382,107 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         const bool live = f < nf;
         const float px = S.p[f][l][0], py = S.p[f][l][1], pz = S.p[f][l][2];
         const float wx = S.x[f][0] + px, wy = S.x[f][1] + py, wz = S.x[f][2] + pz;
-        float a00 = 0.f, a01 = 0.f, a02 = 0.f, a11 = 0.f, a12 = 0.f, a22 = 0.f;
-        float b0 = 0.f, b1 = 0.f, b2 = 0.f, cst = 0.f;
         const size_t base = ((size_t)(f0 + f) * C) * NL + l;
         if (staged) mbar_wait(&S.mbar[1], 0);
-        for (int c = 0; c < C; ++c) {
-            float um = 0.f, vm = 0.f, w = 0.f;
+        // Two cameras (2k, 2k+1) per iteration in the two halves of packed fp32 registers (FFMA2 path);
+        // accumulators are pairs too and are folded after the loop.
+        const f2 WX = bc(wx), WY = bc(wy), WZ = bc(wz);
+        const f2 zero2 = bc(0.f), one2 = bc(1.f);
+        f2 A00 = zero2, A01 = zero2, A02 = zero2, A11 = zero2, A12 = zero2, A22 = zero2;
+        f2 B0 = zero2, B1 = zero2, B2 = zero2, CST = zero2;
+#pragma unroll
+        for (int c = 0; c < (NPAIR ? 2 * NPAIR : C); c += 2) {
+            const bool has2 = NPAIR ? true : (c + 1 < C);
+            float2 m0 = make_float2(0.f, 0.f), m1 = make_float2(0.f, 0.f);
+            float w0 = 0.f, w1 = 0.f;
             if (staged) {
-                const float2 m = S.in.meas[(f * C + c) * NL + l];
-                w = S.in.w[(f * C + c) * NL + l];
-                um = m.x;
-                vm = m.y;
+                m0 = S.in.meas[(f * C + c) * NL + l];
+                w0 = S.in.w[(f * C + c) * NL + l];
+                if (has2) {
+                    m1 = S.in.meas[(f * C + c + 1) * NL + l];
+                    w1 = S.in.w[(f * C + c + 1) * NL + l];
+                }
             } else if (live) {
-                const float2 m = __ldg(reinterpret_cast<const float2*>(meas) + base + (size_t)c * NL);
-                w = __ldg(wts + base + (size_t)c * NL);
-                um = m.x;
-                vm = m.y;
+                m0 = __ldg(reinterpret_cast<const float2*>(meas) + base + (size_t)c * NL);
+                w0 = __ldg(wts + base + (size_t)c * NL);
+                if (has2) {
+                    m1 = __ldg(reinterpret_cast<const float2*>(meas) + base + (size_t)(c + 1) * NL);
+                    w1 = __ldg(wts + base + (size_t)(c + 1) * NL);
+                }
             }
-            const CamF& cam = scene.cam[c];
-            const float xc = fmaf(cam.R[0], wx, fmaf(cam.R[1], wy, fmaf(cam.R[2], wz, cam.t[0])));
-            const float yc = fmaf(cam.R[3], wx, fmaf(cam.R[4], wy, fmaf(cam.R[5], wz, cam.t[1])));
-            const float zc = fmaf(cam.R[6], wx, fmaf(cam.R[7], wy, fmaf(cam.R[8], wz, cam.t[2])));
+            const CamPairF& cp = scene.pair[c >> 1];
+            const f2 R0 = pk(cp.R[0]), R1 = pk(cp.R[1]), R2 = pk(cp.R[2]), R3 = pk(cp.R[3]), R4 = pk(cp.R[4]),
+                     R5 = pk(cp.R[5]), R6 = pk(cp.R[6]), R7 = pk(cp.R[7]), R8 = pk(cp.R[8]);
+            const f2 XC = fma2(R0, WX, fma2(R1, WY, fma2(R2, WZ, pk(cp.t[0]))));
+            const f2 YC = fma2(R3, WX, fma2(R4, WY, fma2(R5, WZ, pk(cp.t[1]))));
+            const f2 ZC = fma2(R6, WX, fma2(R7, WY, fma2(R8, WZ, pk(cp.t[2]))));
             // Kannala-Brandt projection (pt3d_to_2d, all_optimizations.py:193-209) and its Jacobian
-            const float iz = fast_rcp(zc);
-            const float a = xc * iz, b = yc * iz;
-            const float r2 = fmaf(b, b, fmaf(a, a, 1e-12f));
-            const float ir = fast_rsqrt(r2);
-            const float r = r2 * ir;
-            const float th = atan_pos(r, ir);
-            const float th2 = th * th;
-            const float td = th * fmaf(th2, fmaf(th2, fmaf(th2, fmaf(th2, cam.D[3], cam.D[2]), cam.D[1]), cam.D[0]), 1.0f);
-            const float dtd = fmaf(th2, fmaf(th2, fmaf(th2, fmaf(th2, cam.D3[3], cam.D3[2]), cam.D3[1]), cam.D3[0]), 1.0f);
-            const float sd = td * ir;                                              // s = theta_d / r
-            const float q = fmaf(dtd, fast_rcp(1.0f + r2), -sd) * (ir * ir);     // (ds/dr)/r
-            const float aq = a * q, bq = b * q;
-            const float m00 = fmaf(a, aq, sd), m01 = b * aq, m11 = fmaf(b, bq, sd);
+            const f2 IZ = rcp2(ZC);
+            const f2 Aa = mul2(XC, IZ), Bb = mul2(YC, IZ);
+            const f2 RR2 = fma2(Bb, Bb, fma2(Aa, Aa, bc(1e-12f)));
+            const f2 IR = rsqrt2(RR2);
+            const f2 Rr = mul2(RR2, IR);
+            const f2 TH = atan_pos2(Rr, IR);
+            const f2 TH2 = mul2(TH, TH);
+            const f2 TD = mul2(TH, fma2(TH2, fma2(TH2, fma2(TH2, fma2(TH2, pk(cp.D[3]), pk(cp.D[2])), pk(cp.D[1])), pk(cp.D[0])), one2));
+            const f2 DTD = fma2(TH2, fma2(TH2, fma2(TH2, fma2(TH2, pk(cp.D3[3]), pk(cp.D3[2])), pk(cp.D3[1])), pk(cp.D3[0])), one2);
+            const f2 SD = mul2(TD, IR);                                                   // s = theta_d / r
+            const f2 Q = mul2(sub2(mul2(DTD, rcp2(add2(RR2, one2))), SD), mul2(IR, IR));  // (ds/dr)/r
+            const f2 AQ = mul2(Aa, Q), BQ = mul2(Bb, Q);
+            const f2 M00 = fma2(Aa, AQ, SD), M01 = mul2(Bb, AQ), M11 = fma2(Bb, BQ, SD);
+            const f2 FX = pk(cp.fx), FY = pk(cp.fy);
             // residuals in a centred frame: (fx a s) + (cx - u_meas); zero-weight rows are exactly the
             // constant rho(0) whatever the measurement holds
-            const bool on = w != 0.f;
-            const float ru = on ? fmaf(cam.fx, a * sd, cam.cx - um) : 0.f;
-            const float rv = on ? fmaf(cam.fy, b * sd, cam.cy - vm) : 0.f;
+            f2 RU = fma2(FX, mul2(Aa, SD), sub2(pk(cp.cx), pk(m0.x, m1.x)));
+            f2 RV = fma2(FY, mul2(Bb, SD), sub2(pk(cp.cy), pk(m0.y, m1.y)));
+            const bool on0 = w0 != 0.f, on1 = w1 != 0.f;
+            RU = pk(on0 ? lo(RU) : 0.f, on1 ? hi(RU) : 0.f);
+            RV = pk(on0 ? lo(RV) : 0.f, on1 ? hi(RV) : 0.f);
             // world-frame Jacobian rows: J = diag(fx,fy)/z [m] [I | -(a,b)] R = c . G,  G_i = R_i - (a|b) R_2
-            const float g00 = fmaf(-a, cam.R[6], cam.R[0]), g01 = fmaf(-a, cam.R[7], cam.R[1]), g02 = fmaf(-a, cam.R[8], cam.R[2]);
-            const float g10 = fmaf(-b, cam.R[6], cam.R[3]), g11 = fmaf(-b, cam.R[7], cam.R[4]), g12 = fmaf(-b, cam.R[8], cam.R[5]);
-            const float fxi = cam.fx * iz, fyi = cam.fy * iz;
-            const float cu0 = fxi * m00, cu1 = fxi * m01, cv0 = fyi * m01, cv1 = fyi * m11;
-            const float Ju0 = fmaf(cu0, g00, cu1 * g10), Ju1 = fmaf(cu0, g01, cu1 * g11), Ju2 = fmaf(cu0, g02, cu1 * g12);
-            const float Jv0 = fmaf(cv0, g00, cv1 * g10), Jv1 = fmaf(cv0, g01, cv1 * g11), Jv2 = fmaf(cv0, g02, cv1 * g12);
+            const f2 NA = sub2(zero2, Aa), NB = sub2(zero2, Bb);
+            const f2 G00 = fma2(NA, R6, R0), G01 = fma2(NA, R7, R1), G02 = fma2(NA, R8, R2);
+            const f2 G10 = fma2(NB, R6, R3), G11 = fma2(NB, R7, R4), G12 = fma2(NB, R8, R5);
+            const f2 FXI = mul2(FX, IZ), FYI = mul2(FY, IZ);
+            const f2 CU0 = mul2(FXI, M00), CU1 = mul2(FXI, M01), CV0 = mul2(FYI, M01), CV1 = mul2(FYI, M11);
+            const f2 JU0 = fma2(CU0, G00, mul2(CU1, G10)), JU1 = fma2(CU0, G01, mul2(CU1, G11)), JU2 = fma2(CU0, G02, mul2(CU1, G12));
+            const f2 JV0 = fma2(CV0, G00, mul2(CV1, G10)), JV1 = fma2(CV0, G01, mul2(CV1, G11)), JV2 = fma2(CV0, G02, mul2(CV1, G12));
             // redescending loss of e = |w r| per coordinate
-            float rho_u, pr_u, fl_u, rho_v, pr_v, fl_v;
-            redescending_fast(scene.loss, fminf(fmaxf(fabsf(w * ru), 1e-20f), 40.0f), rho_u, pr_u, fl_u);
-            redescending_fast(scene.loss, fminf(fmaxf(fabsf(w * rv), 1e-20f), 40.0f), rho_v, pr_v, fl_v);
-            cst += rho_u + rho_v;
+            const f2 Wp = pk(w0, w1);
+            const f2 WRU = mul2(Wp, RU), WRV = mul2(Wp, RV);
+            const f2 EU = pk(fminf(fmaxf(fabsf(lo(WRU)), 1e-20f), 40.0f), fminf(fmaxf(fabsf(hi(WRU)), 1e-20f), 40.0f));
+            const f2 EV = pk(fminf(fmaxf(fabsf(lo(WRV)), 1e-20f), 40.0f), fminf(fmaxf(fabsf(hi(WRV)), 1e-20f), 40.0f));
+            f2 rho_u, pr_u, fl_u, rho_v, pr_v, fl_v;
+            redescending_fast2(scene.loss, EU, rho_u, pr_u, fl_u);
+            redescending_fast2(scene.loss, EV, rho_v, pr_v, fl_v);
+            f2 RHO = add2(rho_u, rho_v);
+            if (!has2) RHO = pk(lo(RHO), 0.f);        // odd camera count: the padding lane adds nothing
+            CST = add2(CST, RHO);
             // d rho / d r = sign(r) w rho'(e) = (rho'(e)/e) w^2 r ; curvature weight max(rho'/e, 1 - sigma_a) w^2
-            const float w2 = w * w;
-            const float gu = pr_u * (w2 * ru), gv = pr_v * (w2 * rv);
-            b0 = fmaf(gu, Ju0, fmaf(gv, Jv0, b0));
-            b1 = fmaf(gu, Ju1, fmaf(gv, Jv1, b1));
-            b2 = fmaf(gu, Ju2, fmaf(gv, Jv2, b2));
+            const f2 W2 = mul2(Wp, Wp);
+            const f2 GU = mul2(pr_u, mul2(W2, RU)), GV = mul2(pr_v, mul2(W2, RV));
+            B0 = fma2(GU, JU0, fma2(GV, JV0, B0));
+            B1 = fma2(GU, JU1, fma2(GV, JV1, B1));
+            B2 = fma2(GU, JU2, fma2(GV, JV2, B2));
             if (WANT_H) {
-                const float eu = fmaxf(pr_u, fl_u) * w2, ev = fmaxf(pr_v, fl_v) * w2;
-                const float tu0 = eu * Ju0, tu1 = eu * Ju1, tu2 = eu * Ju2;
-                const float tv0 = ev * Jv0, tv1 = ev * Jv1, tv2 = ev * Jv2;
-                a00 = fmaf(tu0, Ju0, fmaf(tv0, Jv0, a00));
-                a01 = fmaf(tu0, Ju1, fmaf(tv0, Jv1, a01));
-                a02 = fmaf(tu0, Ju2, fmaf(tv0, Jv2, a02));
-                a11 = fmaf(tu1, Ju1, fmaf(tv1, Jv1, a11));
-                a12 = fmaf(tu1, Ju2, fmaf(tv1, Jv2, a12));
-                a22 = fmaf(tu2, Ju2, fmaf(tv2, Jv2, a22));
+                const f2 HU = mul2(pk(fmaxf(lo(pr_u), lo(fl_u)), fmaxf(hi(pr_u), hi(fl_u))), W2);
+                const f2 HV = mul2(pk(fmaxf(lo(pr_v), lo(fl_v)), fmaxf(hi(pr_v), hi(fl_v))), W2);
+                const f2 TU0 = mul2(HU, JU0), TU1 = mul2(HU, JU1), TU2 = mul2(HU, JU2);
+                const f2 TV0 = mul2(HV, JV0), TV1 = mul2(HV, JV1), TV2 = mul2(HV, JV2);
+                A00 = fma2(TU0, JU0, fma2(TV0, JV0, A00));
+                A01 = fma2(TU0, JU1, fma2(TV0, JV1, A01));
+                A02 = fma2(TU0, JU2, fma2(TV0, JV2, A02));
+                A11 = fma2(TU1, JU1, fma2(TV1, JV1, A11));
+                A12 = fma2(TU1, JU2, fma2(TV1, JV2, A12));
+                A22 = fma2(TU2, JU2, fma2(TV2, JV2, A22));
             }
         }
+        const float a00 = lo(A00) + hi(A00), a01 = lo(A01) + hi(A01), a02 = lo(A02) + hi(A02);
+        const float a11 = lo(A11) + hi(A11), a12 = lo(A12) + hi(A12), a22 = lo(A22) + hi(A22);
+        const float b0 = lo(B0) + hi(B0), b1 = lo(B1) + hi(B1), b2 = lo(B2) + hi(B2);
+        const float cst = lo(CST) + hi(CST);
         S.costp[f][l] = cst;
         if (staged) __syncthreads();   // the input tiles alias Il: every thread is done reading them
+        PHASE_MARK(3);
         // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]
         float* o = S.Il[tid];
         if (WANT_H) {
@@ -465,6 +508,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         o[24] = b0; o[25] = b1; o[26] = b2;
     }
     __syncthreads();
+    PHASE_MARK(4);
 
     // ---- P3: subtree sums up the kinematic tree, one thread per (component, frame)
     for (int task = tid; task < FT * NSP; task += NT) {
@@ -484,12 +528,14 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         const float s1 = v[3] + s2;
         const float s0 = ((v[0] + v[1]) + v[2]) + s1;
         float* d = &S.Ij[f][0][k];
-        d[0 * NSP] = s0;  d[1 * NSP] = s1;  d[2 * NSP] = s2;   d[3 * NSP] = s3;
-        d[4 * NSP] = s4;  d[5 * NSP] = s5;  d[6 * NSP] = s6;   d[7 * NSP] = s7;
-        d[8 * NSP] = s8;  d[9 * NSP] = s9;  d[10 * NSP] = s10; d[11 * NSP] = s11;
-        d[12 * NSP] = s12; d[13 * NSP] = s13;
+        constexpr int IS = NSP + 1;
+        d[0 * IS] = s0;  d[1 * IS] = s1;  d[2 * IS] = s2;   d[3 * IS] = s3;
+        d[4 * IS] = s4;  d[5 * IS] = s5;  d[6 * IS] = s6;   d[7 * IS] = s7;
+        d[8 * IS] = s8;  d[9 * IS] = s9;  d[10 * IS] = s10; d[11 * IS] = s11;
+        d[12 * IS] = s12; d[13 * IS] = s13;
     }
     __syncthreads();   // Il is dead from here on; the staged outputs alias it
+    PHASE_MARK(5);
 
     // ---- P4a: y_beta = I_subtree(beta) tau_beta, g, translation rows.  task (beta, frame);
     //      beta == 22 is the translation block
@@ -511,7 +557,10 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             }
             continue;
         }
-        const float* I = S.Ij[f][c_tab.joint[be]];
+        const float4* I4 = reinterpret_cast<const float4*>(S.Ij[f][c_tab.joint[be]]);
+        const float4 i0 = I4[0], i1 = I4[1], i2 = I4[2], i3 = I4[3], i4 = I4[4], i5 = I4[5], i6 = I4[6];
+        const float I[28] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y,
+                             i3.z, i3.w, i4.x, i4.y, i4.z, i4.w, i5.x, i5.y, i5.z, i5.w, i6.x, i6.y, i6.z, i6.w};
         const float4 t0 = *reinterpret_cast<const float4*>(&S.tau[f][be * TAU_STRIDE]);
         const float2 t1 = *reinterpret_cast<const float2*>(&S.tau[f][be * TAU_STRIDE + 4]);
         const float o0 = t0.x, o1 = t0.y, o2 = t0.z, v0 = t0.w, v1 = t1.x, v2 = t1.y;
@@ -532,28 +581,35 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         H[2 * NA + sb - 3] = yb2;
     }
     __syncthreads();
+    PHASE_MARK(6);
 
     // ---- P4b: one entry per (angle pair, frame): H[al][be] = tau_al . y_be.  NT / FT = 20 exactly, so a
-    //      thread keeps its frame (tid % FT) and walks the table with stride 20: p = tid / FT + 20 k
+    //      thread keeps its frame (tid % FT) and walks the table with stride 20: p = tid / FT + 20 k.
+    //      All loads and dot products first, all stores last: no store -> load ordering between entries.
     if (WANT_H) {
+        constexpr int NE = (N_PAIR + NL - 1) / NL;   // 13
         const int f = tid % FT, p0 = tid / FT;
         const float* tau_f = &S.tau[f][0];
         const float* y_f = &S.o.y[f][0];
         float* H_f = &S.o.H[f][0];
+        unsigned e[NE];
+        float hv[NE];
 #pragma unroll
-        for (int k = 0; k < (N_PAIR + NL - 1) / NL; ++k) {
-            const int p = p0 + NL * k;
-            if (p < N_PAIR) {
-                const unsigned e = S.tab[p];
-                const float4 a0 = *reinterpret_cast<const float4*>(tau_f + (e & 0xFFu));
-                const float2 a1 = *reinterpret_cast<const float2*>(tau_f + (e & 0xFFu) + 4);
-                const float4 y0 = *reinterpret_cast<const float4*>(y_f + ((e >> 8) & 0xFFu));
-                const float2 y1 = *reinterpret_cast<const float2*>(y_f + ((e >> 8) & 0xFFu) + 4);
-                H_f[e >> 16] = a0.x * y0.x + a0.y * y0.y + a0.z * y0.z + a0.w * y0.w + a1.x * y1.x + a1.y * y1.y;
-            }
+        for (int k = 0; k < NE; ++k) e[k] = S.tab[min(p0 + NL * k, N_PAIR - 1)];
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + (e[k] & 0xFFu));
+            const float2 a1 = *reinterpret_cast<const float2*>(tau_f + (e[k] & 0xFFu) + 4);
+            const float4 y0 = *reinterpret_cast<const float4*>(y_f + ((e[k] >> 8) & 0xFFu));
+            const float2 y1 = *reinterpret_cast<const float2*>(y_f + ((e[k] >> 8) & 0xFFu) + 4);
+            hv[k] = a0.x * y0.x + a0.y * y0.y + a0.z * y0.z + a0.w * y0.w + a1.x * y1.x + a1.y * y1.y;
         }
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+            if (p0 + NL * k < N_PAIR) H_f[e[k] >> 16] = hv[k];
     }
     __syncthreads();
+    PHASE_MARK(7);
 
     // ---- P5: write-out.  The staged blocks have the global layout: straight vector copies
     if (cost_out)
@@ -578,7 +634,13 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             for (int i = tid; i < nf * NU; i += NT) dst[i] = src[i];
         }
     }
+    PHASE_MARK(8);
 }
+
+#ifdef ACINO_PHASE_TIMING
+extern "C" void acino_debug_phase_cycles(long long* out16) { cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(long long) * 16); }
+extern "C" void acino_debug_phase_reset() { long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // fk_project: pose_to_3d + project_points_fisheye for every camera (reprojection only).
@@ -635,9 +697,11 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 }
 
 // ------------------------------------------------------------------------------------------
-template <int FT>
-static cudaError_t launch_fte_eval_ft(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                                      const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+static int g_variant = -1;   // ACINO_FTE_VARIANT: experiment selector (frames/CTA, min CTAs/SM, unrolled camera pairs)
+
+template <int FT, int MINB, int NPAIR>
+static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
     const int use_bulk = ((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0;
@@ -645,33 +709,31 @@ static cudaError_t launch_fte_eval_ft(const SceneF& scene, int n_frames, const f
     const size_t smem = sizeof(Smem<FT>);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<FT, true, MINB, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fte_eval_kernel<FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fte_eval_kernel<FT, false, MINB, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (H)
-        fte_eval_kernel<FT, true><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, true, MINB, NPAIR><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     else
-        fte_eval_kernel<FT, false><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, false, MINB, NPAIR><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     return cudaGetLastError();
 }
-
-static int g_ft = 8;   // frames per CTA (8 or 16); ACINO_FTE_FT overrides for experiments
 
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
                             const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    static bool env_read = false;
-    if (!env_read) {
-        const char* e = getenv("ACINO_FTE_FT");
-        if (e && atoi(e) == 16) g_ft = 16;
-        if (e && atoi(e) == 8) g_ft = 8;
-        env_read = true;
+    if (g_variant < 0) {
+        const char* e = getenv("ACINO_FTE_VARIANT");
+        g_variant = e ? atoi(e) : 0;
     }
-    if (g_ft == 16) return launch_fte_eval_ft<16>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    return launch_fte_eval_ft<8>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    // variant 4: 16 frames per CTA (kept for A/B runs, scripts/bench_variants.sh); the default is 8 frames,
+    // 5 CTAs per SM, runtime camera-pair loop (unrolling the pair loop or trading CTAs for registers
+    // measured no faster - profiles/r01_fte_eval.md)
+    if (g_variant == 4) return launch_fte_eval_v<16, 2, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    return launch_fte_eval_v<8, 5, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,

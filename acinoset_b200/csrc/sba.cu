@@ -14,8 +14,6 @@
 
 namespace acino {
 
-constexpr int SBA_MAXC = ACINO_MAX_CAMS;
-
 struct SbaCam {           // per camera, refreshed from the parameter vector each evaluation
     double R[9];
     double dR[27];        // dR[i][j][k] = d R_ij / d rvec_k  at [ (i*3+j)*3 + k ]
