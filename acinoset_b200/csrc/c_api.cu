@@ -66,6 +66,11 @@ struct acino_handle {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;
+    // host-API pipeline: H2D / compute / D2H on three streams, chunked, chained with events
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    static constexpr int kMaxChunks = 64;
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+    bool pipe_ready = false;
 };
 
 static thread_local std::string g_err;
@@ -149,6 +154,14 @@ int acino_destroy(acino_handle* h) {
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->pipe_ready) {
+        cudaStreamDestroy(h->s_h2d);
+        cudaStreamDestroy(h->s_d2h);
+        for (int i = 0; i < acino_handle::kMaxChunks; ++i) {
+            cudaEventDestroy(h->ev_in[i]);
+            cudaEventDestroy(h->ev_done[i]);
+        }
+    }
     delete h;
     return ACINO_OK;
 }
@@ -206,6 +219,21 @@ int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const floa
     return ACINO_OK;
 }
 
+static int ensure_pipe(acino_handle* h) {
+    if (h->pipe_ready) return ACINO_OK;
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < acino_handle::kMaxChunks; ++i) {
+        CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    h->pipe_ready = true;
+    return ACINO_OK;
+}
+
+// Host-buffer entry point.  The batch is cut into chunks; chunk i+1 is copied in (stream s_h2d) while
+// chunk i is evaluated (stream `stream`) and chunk i-1 is copied out (stream s_d2h) - PCIe is full
+// duplex, so with pinned host buffers the call costs max(H2D, D2H) instead of H2D + kernel + D2H.
 int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* meas, const float* w,
                    float* cost, float* g, float* H) {
     if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fte_eval: NULL handle");
@@ -213,12 +241,14 @@ int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* m
     if (n_frames < 0 || (n_frames > 0 && (!x || !meas || !w))) return fail(h, ACINO_ERR_ARG, "acino_fte_eval: bad arguments");
     if (n_frames == 0) return ACINO_OK;
     CK(cudaSetDevice(h->device));
+    int rc = ensure_pipe(h);
+    if (rc) return rc;
     const size_t N = (size_t)n_frames, C = (size_t)h->scene.n_cams;
     const size_t nx = N * NA, nm = N * C * NL * 2, nw = N * C * NL, nc = N, ng = N * NA, nh = N * NU;
-    // sub-buffers start on 64-float (256 B) boundaries: the kernel loads meas as float2
+    // sub-buffers start on 64-float (256 B) boundaries: the kernel stages tiles with 16-byte bulk copies
     const size_t ax = pad64(nx), am = pad64(nm), aw = pad64(nw), ac = pad64(nc), ag = pad64(ng);
     const size_t total = (ax + am + aw + ac + ag + nh) * sizeof(float);
-    int rc = ensure_ws(h, total);
+    rc = ensure_ws(h, total);
     if (rc) return rc;
     float* dx = (float*)h->ws;
     float* dm = dx + ax;
@@ -226,16 +256,28 @@ int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* m
     float* dc = dw + aw;
     float* dg = dc + ac;
     float* dH = dg + ag;
-    cudaStream_t s = h->stream;
-    CK(cudaMemcpyAsync(dx, x, nx * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(dm, meas, nm * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(dw, w, nw * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(launch_fte_eval(h->scene, n_frames, dx, dm, dw, cost ? dc : nullptr, g ? dg : nullptr, H ? dH : nullptr, s));
-    h->launches += 1;
-    if (cost) CK(cudaMemcpyAsync(cost, dc, nc * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (g) CK(cudaMemcpyAsync(g, dg, ng * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (H) CK(cudaMemcpyAsync(H, dH, nh * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // chunk size: a multiple of 64 frames (keeps every chunk's tiles 16-byte aligned), <= kMaxChunks chunks
+    size_t chunk = 16384;
+    while ((N + chunk - 1) / chunk > (size_t)acino_handle::kMaxChunks) chunk *= 2;
+    const int n_chunks = (int)((N + chunk - 1) / chunk);
+    for (int i = 0; i < n_chunks; ++i) {
+        const size_t f0 = (size_t)i * chunk, nf = (f0 + chunk <= N) ? chunk : N - f0;
+        CK(cudaMemcpyAsync(dx + f0 * NA, x + f0 * NA, nf * NA * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaMemcpyAsync(dm + f0 * C * NL * 2, meas + f0 * C * NL * 2, nf * C * NL * 2 * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaMemcpyAsync(dw + f0 * C * NL, w + f0 * C * NL, nf * C * NL * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaEventRecord(h->ev_in[i], h->s_h2d));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_in[i], 0));
+        CK(launch_fte_eval(h->scene, (int)nf, dx + f0 * NA, dm + f0 * C * NL * 2, dw + f0 * C * NL, cost ? dc + f0 : nullptr,
+                           g ? dg + f0 * NA : nullptr, H ? dH + f0 * NU : nullptr, h->stream));
+        h->launches += 1;
+        CK(cudaEventRecord(h->ev_done[i], h->stream));
+        CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[i], 0));
+        if (cost) CK(cudaMemcpyAsync(cost + f0, dc + f0, nf * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (g) CK(cudaMemcpyAsync(g + f0 * NA, dg + f0 * NA, nf * NA * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (H) CK(cudaMemcpyAsync(H + f0 * NU, dH + f0 * NU, nf * NU * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    CK(cudaStreamSynchronize(h->s_d2h));
+    CK(cudaStreamSynchronize(h->stream));
     return ACINO_OK;
 }
 
