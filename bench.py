@@ -123,13 +123,22 @@ def make_inputs_cpu(n_frames, seed):
     return p["x0"].astype(np.float32), p["meas"].astype(np.float32), p["w"].astype(np.float32), p["cams"]
 
 
+def host_threads():
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1: ask the OS instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline_time(x, meas, w, cams, target_s=12.0, threads=0):
     """Time the oracle C port (oracle/c/fte_oracle.c) on a bounded sample; returns dict."""
     from oracle import c_port
 
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     K, D, R, t, _ = cams
-    cores = c_port.max_threads() if threads <= 0 else threads
+    threads = host_threads() if threads <= 0 else threads
+    cores = threads
     n0 = min(2000, x.shape[0])
     t0 = time.perf_counter()
     c_port.fte_eval(x[:n0], meas[:n0], w[:n0], K, D, R, t, n_threads=threads)
@@ -160,17 +169,17 @@ def run_reference(args):
     from oracle import c_port
 
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    cores = c_port.max_threads()
+    cores = host_threads()
     sample_seqs = 16
     n = sample_seqs * FRAMES_PER_SEQ
     x, meas, w, cams = make_inputs_cpu(n, seed=1000)
     K, D, R, t, _ = cams
     xd, md, wd = x.astype(np.float64), meas.astype(np.float64), w.astype(np.float64)
     for _ in range(args.warmup):
-        c_port.fte_eval(xd, md, wd, K, D, R, t)
+        c_port.fte_eval(xd, md, wd, K, D, R, t, n_threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c_port.fte_eval(xd, md, wd, K, D, R, t)
+        c_port.fte_eval(xd, md, wd, K, D, R, t, n_threads=cores)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     out = {
