@@ -66,19 +66,18 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
     load_block(D + (size_t)e * SB2, sR, false);
     for (int i = tid; i < SB * LD; i += BCR_THREADS) sW[i] = 0.0;
     __syncthreads();
-    // right-looking Cholesky, one barrier per column: a_ij -= a_ik a_jk / a_kk  (i >= j > k)
-    for (int k = 0; k < SB - 1; ++k) {
-        const double d = sR[k * LD + k];
-        const double inv = 1.0 / d;
-        const int m = SB - 1 - k;                 // trailing size
-        for (int t = tid; t < m * m; t += BCR_THREADS) {
-            const int r = t / m, cc = t - r * m;
-            if (cc <= r) {
-                const int i = k + 1 + r, j = k + 1 + cc;
-                sR[i * LD + j] = fma(-sR[i * LD + k] * inv, sR[j * LD + k], sR[i * LD + j]);
+    // right-looking Cholesky, one barrier per column: a_ij -= a_ik a_jk / a_kk  (i >= j > k).
+    // 16 x 16 thread grid strided over the trailing matrix (no index division in the loop)
+    {
+        const int ty = tid >> 4, tx = tid & 15;
+        for (int k = 0; k < SB - 1; ++k) {
+            const double inv = 1.0 / sR[k * LD + k];
+            for (int i = k + 1 + ty; i < SB; i += 16) {
+                const double lik = -sR[i * LD + k] * inv;
+                for (int j = k + 1 + tx; j <= i; j += 16) sR[i * LD + j] = fma(lik, sR[j * LD + k], sR[i * LD + j]);
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     // scale columns: R_ik = a_ik / sqrt(a_kk); flag non-positive pivots
     for (int t = tid; t < SB * SB; t += BCR_THREADS) {
@@ -96,21 +95,26 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
         if (i > k) sR[i * LD + k] = sR[i * LD + k] / sz[k];
     }
     __syncthreads();
-    if (tid < SB) sR[tid * LD + tid] = sz[tid];
+    if (tid < SB) {
+        sR[tid * LD + tid] = sz[tid];
+        sz2[tid] = 1.0 / sz[tid];
+    }
     __syncthreads();
     // W = R^-1: thread j solves R w = e_j by forward substitution (column j of W)
     if (tid < SB) {
         const int j = tid;
-        sW[j * LD + j] = 1.0 / sR[j * LD + j];
+        sW[j * LD + j] = sz2[j];
         for (int i = j + 1; i < SB; ++i) {
-            double s0 = 0.0, s1 = 0.0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int k = j;
-            for (; k + 1 < i; k += 2) {
+            for (; k + 3 < i; k += 4) {
                 s0 = fma(sR[i * LD + k], sW[k * LD + j], s0);
                 s1 = fma(sR[i * LD + k + 1], sW[(k + 1) * LD + j], s1);
+                s2 = fma(sR[i * LD + k + 2], sW[(k + 2) * LD + j], s2);
+                s3 = fma(sR[i * LD + k + 3], sW[(k + 3) * LD + j], s3);
             }
-            if (k < i) s0 = fma(sR[i * LD + k], sW[k * LD + j], s0);
-            sW[i * LD + j] = -(s0 + s1) / sR[i * LD + i];
+            for (; k < i; ++k) s0 = fma(sR[i * LD + k], sW[k * LD + j], s0);
+            sW[i * LD + j] = -((s0 + s1) + (s2 + s3)) * sz2[i];
         }
     }
     __syncthreads();
