@@ -60,6 +60,8 @@ def _load():
     lib.acino_triangulate_pairwise.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     lib.acino_triangulate_pairwise.restype = ci
     i64 = ctypes.c_int64
+    lib.acino_generic_fk.argtypes = [vp, ci, ci, ci] + [vp] * 7
+    lib.acino_generic_fk.restype = ci
     lib.acino_lm_prepare_dev.argtypes = [vp, ci, i64, i64] + [vp] * 9
     lib.acino_lm_prepare_dev.restype = ci
     lib.acino_lm_assemble_dev.argtypes = [vp, ci, i64, i64, ci, vp, vp, vp, vp, cd, vp, vp, vp, vp]
@@ -100,7 +102,7 @@ EXPORTED = [
     "acino_create", "acino_destroy", "acino_last_error", "acino_version", "acino_launch_count",
     "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
     "acino_fk_project_dev", "acino_fk_project", "acino_project_points", "acino_undistort_points",
-    "acino_triangulate_points", "acino_triangulate_pairwise",
+    "acino_triangulate_points", "acino_triangulate_pairwise", "acino_generic_fk",
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
     "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_eval_dev",

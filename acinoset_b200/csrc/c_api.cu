@@ -17,6 +17,9 @@ cudaError_t launch_triangulate_points_f64(const CamD& c1, const CamD& c2, int n,
                                           double* out, cudaStream_t s);
 cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_frames, int L, const double* uv,
                                             const unsigned char* valid, double* pos, int* count, cudaStream_t s);
+cudaError_t launch_generic_fk(int n_frames, int n_parts, int n_links, const int* dof_mask, const int* link_parent,
+                              const int* link_child, const int* link_flags, const double* link_tv, const double* x,
+                              double* pos, cudaStream_t s);
 cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, const double* x_ext, const float* g,
                               const double* sw, const double* lo, const double* hi, double* gtot, unsigned char* fixed,
                               double* cost_s, cudaStream_t s);
@@ -411,6 +414,44 @@ int acino_triangulate_pairwise(acino_handle* h, int n_frames, int n_markers, con
     h->launches += 1;
     CK(cudaMemcpyAsync(pos, dP, N * L * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (count) CK(cudaMemcpyAsync(count, dC, ncnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_generic_fk(acino_handle* h, int n_frames, int n_parts, int n_links, const int32_t* dof_mask,
+                     const int32_t* link_parent, const int32_t* link_child, const int32_t* link_flags, const double* link_tv,
+                     const double* x, double* pos) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_generic_fk: NULL handle");
+    if (n_frames < 0 || n_parts < 1 || n_parts > 32 || n_links < 0 || !dof_mask || (n_links > 0 && (!link_parent || !link_child || !link_flags || !link_tv)) ||
+        (n_frames > 0 && (!x || !pos)))
+        return fail(h, ACINO_ERR_ARG, "acino_generic_fk: bad arguments (n_parts must be 1..32)");
+    for (int l = 0; l < n_links; ++l)
+        if (link_parent[l] < 0 || link_parent[l] >= n_parts || link_child[l] < 0 || link_child[l] >= n_parts)
+            return fail(h, ACINO_ERR_ARG, "acino_generic_fk: link index out of range");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t ns = 3 + 3 * (size_t)n_parts, N = (size_t)n_frames;
+    const size_t bx = N * ns * 8, bp = N * n_parts * 3 * 8, bi = (size_t)(n_parts + 3 * n_links) * 4, bt = (size_t)n_links * 3 * 8;
+    const size_t ox = 0, op = (bx + 255) & ~(size_t)255, ot = op + ((bp + 255) & ~(size_t)255), oi = ot + ((bt + 255) & ~(size_t)255);
+    int rc = ensure_ws(h, oi + bi + 256);
+    if (rc) return rc;
+    char* base = (char*)h->ws;
+    double* dX = (double*)(base + ox);
+    double* dP = (double*)(base + op);
+    double* dT = (double*)(base + ot);
+    int* dI = (int*)(base + oi);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dX, x, bx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dI, dof_mask, (size_t)n_parts * 4, cudaMemcpyHostToDevice, s));
+    if (n_links) {
+        CK(cudaMemcpyAsync(dI + n_parts, link_parent, (size_t)n_links * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dI + n_parts + n_links, link_child, (size_t)n_links * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dI + n_parts + 2 * n_links, link_flags, (size_t)n_links * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dT, link_tv, bt, cudaMemcpyHostToDevice, s));
+    }
+    CK(launch_generic_fk(n_frames, n_parts, n_links, dI, dI + n_parts, dI + n_parts + n_links, dI + n_parts + 2 * n_links, dT, dX, dP, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(pos, dP, bp, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return ACINO_OK;
 }

@@ -251,3 +251,81 @@ cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_
 }
 
 }  // namespace acino
+
+// ---- generic skeleton-pickle forward kinematics (reference src/build.py:32-95), fp64 ----------------
+// Table driven: the host simulates the builder once (acinoset_b200/skeleton.py) and hands over, per
+// link in order, (parent part, child part, whether the parent's LOCAL rotation is used transposed or
+// not - the reference toggles `rot[child+"_i"]` every time a part appears as a child, build.py:78-79)
+// and the rest-pose offset.  pose[child] = pose[parent] + M_parent * offset; roots sit at (x, y, z).
+namespace acino {
+
+constexpr int GFK_MAX_PARTS = 32;
+
+__global__ void generic_fk_kernel(const int n_frames, const int n_parts, const int n_links, const int n_state,
+                                  const int* __restrict__ dof_mask, const int* __restrict__ link_parent,
+                                  const int* __restrict__ link_child, const int* __restrict__ link_flags,
+                                  const double* __restrict__ link_tv, const double* __restrict__ x,
+                                  double* __restrict__ pos) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_frames) return;
+    const double* xs = x + (size_t)n * n_state;
+    double pose[GFK_MAX_PARTS][3];
+    for (int p = 0; p < n_parts; ++p) {
+        pose[p][0] = xs[0];
+        pose[p][1] = xs[1];
+        pose[p][2] = xs[2];
+    }
+    for (int l = 0; l < n_links; ++l) {
+        const int a = link_parent[l], b = link_child[l], fl = link_flags[l];
+        // local passive rotation of part a: L = Rz(psi) Rx(phi) Ry(theta) (each factor only if its dof is set)
+        double L[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        const int m = dof_mask[a];
+        if (m & 2) {   // Ry(theta) (build.py:54-55)
+            const double c = cos(xs[3 + n_parts + a]), s = sin(xs[3 + n_parts + a]);
+            const double R[3][3] = {{c, 0, -s}, {0, 1, 0}, {s, 0, c}};
+            double T[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) T[i][j] = R[i][0] * L[0][j] + R[i][1] * L[1][j] + R[i][2] * L[2][j];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) L[i][j] = T[i][j];
+        }
+        if (m & 1) {   // Rx(phi) (build.py:56-57)
+            const double c = cos(xs[3 + a]), s = sin(xs[3 + a]);
+            const double R[3][3] = {{1, 0, 0}, {0, c, s}, {0, -s, c}};
+            double T[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) T[i][j] = R[i][0] * L[0][j] + R[i][1] * L[1][j] + R[i][2] * L[2][j];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) L[i][j] = T[i][j];
+        }
+        if (m & 4) {   // Rz(psi) (build.py:58-59)
+            const double c = cos(xs[3 + 2 * n_parts + a]), s = sin(xs[3 + 2 * n_parts + a]);
+            const double R[3][3] = {{c, s, 0}, {-s, c, 0}, {0, 0, 1}};
+            double T[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) T[i][j] = R[i][0] * L[0][j] + R[i][1] * L[1][j] + R[i][2] * L[2][j];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) L[i][j] = T[i][j];
+        }
+        const double* tv = link_tv + 3 * l;
+        for (int i = 0; i < 3; ++i) {
+            // flag 1: use L^T (the initial "_i" matrix), flag 0: use L (it has been transposed back)
+            const double d = (fl & 1) ? (L[0][i] * tv[0] + L[1][i] * tv[1] + L[2][i] * tv[2])
+                                      : (L[i][0] * tv[0] + L[i][1] * tv[1] + L[i][2] * tv[2]);
+            pose[b][i] = pose[a][i] + d;
+        }
+    }
+    for (int p = 0; p < n_parts; ++p)
+        for (int i = 0; i < 3; ++i) pos[((size_t)n * n_parts + p) * 3 + i] = pose[p][i];
+}
+
+cudaError_t launch_generic_fk(int n_frames, int n_parts, int n_links, const int* dof_mask, const int* link_parent,
+                              const int* link_child, const int* link_flags, const double* link_tv, const double* x,
+                              double* pos, cudaStream_t s) {
+    if (n_frames <= 0) return cudaSuccess;
+    generic_fk_kernel<<<nblk(n_frames, 64), 64, 0, s>>>(n_frames, n_parts, n_links, 3 + 3 * n_parts, dof_mask, link_parent,
+                                                        link_child, link_flags, link_tv, x, pos);
+    return cudaGetLastError();
+}
+
+}  // namespace acino

@@ -108,6 +108,16 @@ int acino_triangulate_points(acino_handle* h, int n, const double* uv1, const do
 int acino_triangulate_pairwise(acino_handle* h, int n_frames, int n_markers, const double* uv,
                                const uint8_t* valid, double* pos, int32_t* count);
 
+/* Generic skeleton-pickle forward kinematics: the pose_to_3d that build_model lambdifies
+ * (src/build.py:32-95), quirks included.  The host (acinoset_b200/skeleton.py) flattens the skeleton:
+ * dof_mask [n_parts] (bit0 phi/x, bit1 theta/y, bit2 psi/z), and per link in order parent / child part
+ * index, flag (1 = the parent's local rotation is used transposed, 0 = as is) and rest-pose offset
+ * tv [n_links][3].  x [N][3 + 3 n_parts] = [x,y,z,*phi,*theta,*psi] -> pos [N][n_parts][3] (fp64,
+ * host pointers).  n_parts <= 32. */
+int acino_generic_fk(acino_handle* h, int n_frames, int n_parts, int n_links, const int32_t* dof_mask,
+                     const int32_t* link_parent, const int32_t* link_child, const int32_t* link_flags,
+                     const double* link_tv, const double* x, double* pos);
+
 /* ---- FTE solve building blocks (device pointers, stream-ordered) ------------------------------
  * Together they replace `opt.solve(m)` (all_optimizations.py:503-524): a projected
  * Levenberg-Marquardt loop on  F(x) = sum rho(w r) + sum_{n>=3,p} q_p (third difference / Ts^2)^2

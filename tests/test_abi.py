@@ -122,3 +122,37 @@ def test_rotation_conversions_match_cv2_golden():
     for rv, Rm, rb in zip(g["rvec"], g["rmat"], g["rvec_back"]):
         assert np.abs(rotations.rodrigues_to_mat(rv) - Rm).max() < 1e-14
         assert np.abs(rotations.rodrigues_to_vec(Rm) - rb).max() < 1e-12
+
+
+def test_generic_skeleton_flattening_matches_oracle_walk():
+    """Host logic of the generic builder (no GPU): the flattened link table reproduces the oracle's
+    step-by-step replay of build.py:32-95 on random states."""
+    import json
+
+    from conftest import golden
+    from acinoset_b200 import skeleton
+    from oracle import skeleton as osk
+
+    g = golden("generic_fk.npz")
+    for tag in ("K1", "K2"):
+        skel = json.loads(str(g[tag + "_skeleton_json"]))
+        flat = skeleton.flatten_skeleton(skel)
+        assert flat["out_names"] == list(g[tag + "_pose_order"])
+        P = len(flat["parts"])
+        rng = np.random.default_rng(3)
+        x = rng.normal(0, 0.7, 3 + 3 * P)
+        ref, names = osk.generic_fk_builder(skel)(x)
+        # replay the flat table on the host with the oracle's rotation helpers
+        pose = {i: x[:3].copy() for i in range(P)}
+        for a, b, fl, tv in zip(flat["link_parent"], flat["link_child"], flat["link_flags"], flat["link_tv"]):
+            L = np.eye(3)
+            m = flat["dof_mask"][a]
+            if m & 2:
+                L = osk.rot_y(x[3 + P + a]) @ L
+            if m & 1:
+                L = osk.rot_x(x[3 + a]) @ L
+            if m & 4:
+                L = osk.rot_z(x[3 + 2 * P + a]) @ L
+            pose[b] = pose[a] + (L.T if fl else L) @ tv
+        out = np.stack([pose[i] for i in flat["out_order"]])
+        assert np.abs(out - ref).max() < 1e-13
