@@ -125,15 +125,61 @@ def params_to_points_extrinsics(params, n_cameras, n_points):
     return obj_pts, r_arr, t_arr
 
 
+
+# ---- multi-GPU plan (pure NumPy / torch: runs on CPU tensors with gloo in the tests) ----------------
+def shard_points(point_3d_indices, n_points, world):
+    """Shard the 3-D points (board views) over ranks in contiguous index ranges; every point's
+    observations follow it, so the point blocks stay private to a rank and only the 6C camera
+    parameters are shared.  Returns a list of
+    (point0, n_points_local, obs_ids) with obs_ids the global observation ids of the shard."""
+    pidx = np.asarray(point_3d_indices, dtype=np.int64)
+    out = []
+    for r in range(world):
+        p0 = (r * n_points) // world
+        p1 = ((r + 1) * n_points) // world
+        ids = np.nonzero((pidx >= p0) & (pidx < p1))[0]
+        out.append((p0, p1 - p0, ids))
+    return out
+
+
+def allreduce_camera_system(Sr, world, group=None):
+    """The ONE data-path collective of a sharded SBA iteration: sum of the per-rank reduced camera
+    systems, packed [S (6C x 6C) | rhs (6C)] in one buffer (5.4 KB at C = 6).  Every rank receives
+    the same bits, so the redundant dense solves that follow agree exactly."""
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(Sr, op=dist.ReduceOp.SUM, group=group)
+    return Sr
+
+
+def allreduce_scalars(v, world, group=None):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v
+
+
+def scatter_sum(local, ids, n_total, world, group=None):
+    """Place a rank's rows at their global ids and sum over ranks (the final gather of the sharded
+    points / residuals; done once per solve, outside the iteration)."""
+    import torch
+
+    full = torch.zeros((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full[ids] = local
+    return allreduce_scalars(full, world, group)
+
 # ---- device problem ----------------------------------------------------------------------------------
 class SBAProblem:
     """Observations + cameras resident on one GPU; evaluates residuals / Jacobian blocks and runs LM."""
 
     def __init__(self, points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, device=0,
-                 with_extrinsics=True, f_scale=1.0):
+                 with_extrinsics=True, f_scale=1.0, rank=0, world=1, group=None):
         import torch
 
         self.torch = torch
+        self.rank, self.world, self.group = int(rank), int(world), group
         self.h = _fte.get_handle(device)
         self.dev = torch.device("cuda", device)
         self.C = len(k_arr)
@@ -167,8 +213,11 @@ class SBAProblem:
                         wgt=buf(n, 2), cost=buf(n), cams=self.cams[i]) for i in range(2)]
         self.pred = buf(n)
         self.dp = buf(self.n_pts, 3)
-        self.S = buf(6 * self.C, 6 * self.C)
-        self.dc = buf(6 * self.C)
+        n6 = 6 * self.C
+        self.Sr = buf(n6 * n6 + n6)                 # [S | rhs]: one buffer = one all_reduce when sharded
+        self.S = self.Sr[:n6 * n6].view(n6, n6)
+        self.dc = self.Sr[n6 * n6:]
+        self.sc4 = buf(4)
         self.partial = buf(int(_lib.lib.acino_sba_schur_partial_size(self.n_pts, self.C)))
         self.out5 = buf(5)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -193,7 +242,9 @@ class SBAProblem:
                         s["Jp"] if want_j else None, s["wgt"] if want_j else None, s["cost"])
 
     def _sum(self, a1, a2=None):
+        """Fixed-order local sums (+ one small all_reduce when the points are sharded)."""
         self.h.call_dev("acino_lm_reduce_dev", self.n_obs, None, a1, a2, None, None, self.out5)
+        allreduce_scalars(self.out5[1:3], self.world, self.group)
         o = self.out5.cpu().numpy()
         return float(o[1]), float(o[2])
 
@@ -240,6 +291,7 @@ class SBAProblem:
                 if self.with_ext:
                     self.h.call_dev("acino_sba_schur_dev", self.n_pts, self.C, self.pt_ptr, self.obs, self.cam_idx, s["res"],
                                     s["Jc"], s["Jp"], s["wgt"], float(lam), self.partial, self.S, self.dc)
+                    allreduce_camera_system(self.Sr, self.world, self.group)
                     self.h.call_dev("acino_sba_dense_solve_dev", n6, self.S, self.dc, self.info)
                 self.h.call_dev("acino_sba_backsub_dev", self.n_pts, self.C, self.pt_ptr, self.obs, self.cam_idx, s["res"],
                                 s["Jc"] if self.with_ext else None, s["Jp"], s["wgt"], float(lam),
@@ -259,8 +311,11 @@ class SBAProblem:
                 if Ft < F and rho > 1e-4:
                     accepted = True
                     dF = F - Ft
-                    xs = float(t_.sqrt((self.dp ** 2).sum() + ((self.dc ** 2).sum() if self.with_ext else 0.0)).item())
-                    xn = float(t_.sqrt((t["pts"] ** 2).sum() + ((t["params"] ** 2).sum() if self.with_ext else 0.0)).item())
+                    self.sc4[0] = (self.dp ** 2).sum()
+                    self.sc4[1] = (t["pts"] ** 2).sum()
+                    allreduce_scalars(self.sc4[:2], self.world, self.group)      # point parts are sharded
+                    xs = float(t_.sqrt(self.sc4[0] + ((self.dc ** 2).sum() if self.with_ext else 0.0)).item())
+                    xn = float(t_.sqrt(self.sc4[1] + ((t["params"] ** 2).sum() if self.with_ext else 0.0)).item())
                     F = Ft
                     s, t = t, s
                     lam = max(lam / 3, 1e-15) if rho > 0.75 else (lam * 2 if rho < 0.25 else lam)
@@ -284,6 +339,50 @@ class SBAProblem:
 
 
 # ---- reference-named entry points ------------------------------------------------------------------
+def _dist_ctx():
+    """(rank, world, device): a torchrun launch with an initialised process group shards the points
+    over the ranks; a plain call is the single-GPU solve."""
+    import os
+
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", 0))
+    except ImportError:
+        pass
+    return 0, 1, 0
+
+
+def _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, x_cam0, fixed_rt, f_scale,
+                   max_nfev, ftol, verbose):
+    """Common driver: shard the points over the ranks of the process group (if any), solve, and
+    return the full-size result on every rank."""
+    import torch
+
+    rank, world, device = _dist_ctx()
+    n_points = len(points_3d)
+    pidx = np.asarray(point_3d_indices, dtype=np.int64)
+    cidx = np.asarray(camera_indices, dtype=np.int64)
+    p2 = np.asarray(points_2d, dtype=np.float32).reshape(-1, 2)
+    p0, npl, ids = shard_points(pidx, n_points, world)[rank]
+    prob = SBAProblem(p2[ids], pidx[ids] - p0, cidx[ids], k_arr, d_arr, npl, device=device,
+                      with_extrinsics=fixed_rt is None, f_scale=f_scale, rank=rank, world=world)
+    if fixed_rt is not None:
+        prob.set_fixed_cameras(*fixed_rt)
+    out = prob.solve(x_cam0, np.asarray(points_3d, dtype=np.float64)[p0:p0 + npl], max_nfev=max_nfev, ftol=ftol,
+                     verbose=verbose if rank == 0 else 0)
+    if world > 1:
+        dev = prob.dev
+        ids_t = torch.as_tensor(ids).to(dev)
+        pts = scatter_sum(torch.as_tensor(out["pts"]).to(dev), torch.arange(p0, p0 + npl, device=dev), n_points, world)
+        fun = scatter_sum(torch.as_tensor(out["fun"].reshape(-1, 2)).to(dev), ids_t, len(pidx), world)
+        f0 = scatter_sum(torch.as_tensor(out["f0"].reshape(-1, 2)).to(dev), ids_t, len(pidx), world)
+        out = dict(out, pts=pts.cpu().numpy(), fun=fun.cpu().numpy().ravel(), f0=f0.cpu().numpy().ravel())
+    out["world"] = world
+    return out
+
+
 def cost_func_points_only(params, n_points, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr, points_2d,
                           project_func=None):
     prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, with_extrinsics=False)
@@ -325,12 +424,9 @@ def jac_points_extrinsics(params, n_cameras, n_points, point_3d_indices, camera_
 def bundle_adjust_points_only(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr,
                               project_func=None, f_scale=50, verbose=0):
     """calib.py:327-341: cauchy f_scale=50, ftol=1e-15, max_nfev=500 -> (obj_pts, residuals)."""
-    n_points = len(points_3d)
-    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, with_extrinsics=False,
-                      f_scale=f_scale)
-    prob.set_fixed_cameras(r_arr, t_arr)
     t0 = time.time()
-    out = prob.solve(None, np.asarray(points_3d, dtype=np.float64), max_nfev=500, ftol=1e-15, verbose=verbose)
+    out = _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, None, (r_arr, t_arr),
+                         f_scale, 500, 1e-15, verbose)
     print("Optimization took {0:.0f} seconds".format(time.time() - t0))
     residuals = dict(before=out["f0"], after=out["fun"])
     return out["pts"], residuals
@@ -351,10 +447,9 @@ def bundle_adjust_points_and_extrinsics(points_2d, points_3d, point_3d_indices, 
     n_cameras = len(k_arr)
     r_vecs = np.array([rodrigues_to_vec(r) for r in r_arr], dtype=np.float64).flatten()
     t_vecs = np.asarray(t_arr, dtype=np.float64).flatten()
-    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points)
     t0 = time.time()
-    out = prob.solve(np.concatenate([r_vecs, t_vecs]), np.asarray(points_3d, dtype=np.float64), max_nfev=1000, ftol=1e-10,
-                     verbose=verbose)
+    out = _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr,
+                         np.concatenate([r_vecs, t_vecs]), None, 1.0, 1000, 1e-10, verbose)
     print("Optimization took {0:.0f} seconds".format(time.time() - t0))
     obj_pts, r_new, t_new = params_to_points_extrinsics(np.concatenate([out["params"], out["pts"].ravel()]), n_cameras,
                                                         n_points)

@@ -1,5 +1,5 @@
-"""Needs >= 2 GPUs: the frame-sharded FTE solve (one all_gather of interface blocks per LM attempt)
-equals the single-GPU solve."""
+"""Needs >= 2 GPUs: the frame-sharded FTE solve (one all_gather of interface blocks per LM attempt) and the
+view-sharded SBA solve (one all_reduce of the reduced camera system per LM attempt) equal the single-GPU solves."""
 import os
 import subprocess
 import sys
@@ -19,5 +19,18 @@ def test_sharded_solve_equals_single_gpu(world):
     port = 29600 + (os.getpid() % 1000)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "_mgpu_worker.py"), "600"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_sba_equals_single_gpu(world):
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 30600 + (os.getpid() % 1000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "_mgpu_worker_sba.py"), "300"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

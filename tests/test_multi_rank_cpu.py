@@ -33,15 +33,36 @@ def test_default_bounds_match_reference_table():
     assert np.array_equal(lm.Q_SIGMA_ACTIVE, skeleton.Q_SIGMA[skeleton.ACTIVE_IDX])
 
 
-@pytest.mark.timeout(300)
-def test_interface_gather_world2_gloo():
-    port = 29500 + (os.getpid() % 2000)
+def _run_world2(worker, port):
     procs = []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    OMP_NUM_THREADS="2")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_rank_worker.py")], env=env,
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", worker)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=280)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+@pytest.mark.timeout(300)
+def test_interface_gather_world2_gloo():
+    _run_world2("_rank_worker.py", 29500 + (os.getpid() % 2000))
+
+
+@pytest.mark.timeout(300)
+def test_sba_sharded_camera_system_world2_gloo():
+    """Sharded SBA: per-rank Schur complement + ONE all_reduce of [S | rhs] == the global step."""
+    _run_world2("_rank_worker_sba.py", 31600 + (os.getpid() % 2000))
+
+
+def test_shard_points_plan():
+    from acinoset_b200 import sba
+
+    pidx = np.repeat(np.arange(10), 3)
+    for w in (1, 2, 3, 8):
+        plan = sba.shard_points(pidx, 10, w)
+        assert len(plan) == w and sum(n for _, n, _ in plan) == 10
+        assert np.array_equal(np.sort(np.concatenate([i for _, _, i in plan])), np.arange(30))
+        for p0, n, ids in plan:
+            assert np.all((pidx[ids] >= p0) & (pidx[ids] < p0 + n))
