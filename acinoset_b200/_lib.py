@@ -51,6 +51,10 @@ def _load():
     lib.acino_fk_project_dev.restype = ci
     lib.acino_fk_project.argtypes = [vp, ci, vp, vp, vp]
     lib.acino_fk_project.restype = ci
+    lib.acino_fte_jac_dev.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.acino_fte_jac_dev.restype = ci
+    lib.acino_fte_jac.argtypes = [vp, ci, vp, vp, vp]
+    lib.acino_fte_jac.restype = ci
     lib.acino_project_points.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
     lib.acino_project_points.restype = ci
     lib.acino_undistort_points.argtypes = [vp, ci, vp, vp, vp, vp]
@@ -101,7 +105,7 @@ lib = _load()
 EXPORTED = [
     "acino_create", "acino_destroy", "acino_last_error", "acino_version", "acino_launch_count",
     "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
-    "acino_fk_project_dev", "acino_fk_project", "acino_project_points", "acino_undistort_points",
+    "acino_fk_project_dev", "acino_fk_project", "acino_fte_jac_dev", "acino_fte_jac", "acino_project_points", "acino_undistort_points",
     "acino_triangulate_points", "acino_triangulate_pairwise", "acino_generic_fk",
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
@@ -193,6 +197,16 @@ class Handle:
         self._check(lib.acino_fk_project(self._h, N, _np_ptr(x), _np_ptr(pos), _np_ptr(uv)), "acino_fk_project")
         return pos, uv
 
+    def fte_jac(self, x, want_uv=True, want_J=True):
+        """h(x) and d h / d x for every camera: x (N,25) -> uv (N,C,20,2), J (N,C,20,2,25)."""
+        x = _host(x, np.float32)
+        N = x.shape[0]
+        x = _host(x, np.float32, (N, N_ACTIVE))
+        uv = np.empty((N, self.n_cams, N_MARKERS, 2), np.float32) if want_uv else None
+        J = np.empty((N, self.n_cams, N_MARKERS, 2, N_ACTIVE), np.float32) if want_J else None
+        self._check(lib.acino_fte_jac(self._h, N, _np_ptr(x), _np_ptr(uv), _np_ptr(J)), "acino_fte_jac")
+        return uv, J
+
     # ---- camera geometry (fp64, host buffers)
     @staticmethod
     def _cam(K, D, R=None, t=None):
@@ -270,6 +284,17 @@ class Handle:
         self._check(lib.acino_fk_project_dev(self._h, N, _dp(x), _dp(pos), _dp(uv), ctypes.c_void_p(s)),
                     "acino_fk_project_dev")
 
+    def fte_jac_dev(self, x, uv=None, J=None, stream=None):
+        import torch
+
+        N = x.shape[0]
+        _check_dev(x, (N, N_ACTIVE), self.device)
+        if uv is not None:
+            _check_dev(uv, (N, self.n_cams, N_MARKERS, 2), self.device)
+        if J is not None:
+            _check_dev(J, (N, self.n_cams, N_MARKERS, 2, N_ACTIVE), self.device)
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(lib.acino_fte_jac_dev(self._h, N, _dp(x), _dp(uv), _dp(J), ctypes.c_void_p(s)), "acino_fte_jac_dev")
 
     # ---- raw device-pointer calls used by acinoset_b200.lm (arguments are torch tensors / scalars)
     def call_dev(self, name, *args, stream=None):

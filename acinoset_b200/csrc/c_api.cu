@@ -11,6 +11,7 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
                             const float* w, float* cost, float* g, float* H, cudaStream_t stream);
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream);
+cudaError_t launch_fte_jac(const SceneF& scene, int n_frames, const float* x, float* uv, float* J, cudaStream_t stream);
 cudaError_t launch_project_points_f64(const CamD& cam, int n, const double* X, double* uv, cudaStream_t s);
 cudaError_t launch_undistort_points_f64(const CamD& cam, int n, const double* uv, double* out, cudaStream_t s);
 cudaError_t launch_triangulate_points_f64(const CamD& c1, const CamD& c2, int n, const double* uv1, const double* uv2,
@@ -314,6 +315,40 @@ int acino_fk_project(acino_handle* h, int n_frames, const float* x, float* pos, 
     h->launches += 1;
     if (pos) CK(cudaMemcpyAsync(pos, dp, np * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (uv) CK(cudaMemcpyAsync(uv, du, nu * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_fte_jac_dev(acino_handle* h, int n_frames, const float* x, float* uv, float* J, void* cuda_stream) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fte_jac_dev: NULL handle");
+    if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_fte_jac_dev: cameras not set");
+    if (n_frames < 0 || (n_frames > 0 && !x)) return fail(h, ACINO_ERR_ARG, "acino_fte_jac_dev: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    CK(launch_fte_jac(h->scene, n_frames, x, uv, J, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_fte_jac(acino_handle* h, int n_frames, const float* x, float* uv, float* J) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_fte_jac: NULL handle");
+    if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_fte_jac: cameras not set");
+    if (n_frames < 0 || (n_frames > 0 && !x)) return fail(h, ACINO_ERR_ARG, "acino_fte_jac: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t N = (size_t)n_frames, C = (size_t)h->scene.n_cams;
+    const size_t nx = N * NA, nu = N * C * NL * 2, nj = nu * NA;
+    int rc = ensure_ws(h, (pad64(nx) + pad64(nu) + nj) * sizeof(float));
+    if (rc) return rc;
+    float* dx = (float*)h->ws;
+    float* du = dx + pad64(nx);
+    float* dj = du + pad64(nu);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dx, x, nx * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(launch_fte_jac(h->scene, n_frames, dx, uv ? du : nullptr, J ? dj : nullptr, s));
+    h->launches += 1;
+    if (uv) CK(cudaMemcpyAsync(uv, du, nu * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (J) CK(cudaMemcpyAsync(J, dj, nj * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return ACINO_OK;
 }

@@ -81,6 +81,15 @@ int acino_fk_project_dev(acino_handle* h, int n_frames, const float* x, float* p
                          void* cuda_stream);
 int acino_fk_project(acino_handle* h, int n_frames, const float* x, float* pos, float* uv);
 
+/* Dense measurement Jacobian (the EKF's linearisation): h_function (all_optimizations.py:615-621) and
+ * the analytic replacement of numerical_jacobian (:634-649, used at :800-806) for every camera at once.
+ *   uv [N][C][20][2]      predicted pixels h(x)                       (may be NULL)
+ *   J  [N][C][20][2][25]  d uv / d x in the active-slot order above   (may be NULL)
+ * acinoset_b200/ekf.py permutes the columns into the EKF's joint-grouped state order (:734-746). */
+int acino_fte_jac_dev(acino_handle* h, int n_frames, const float* x, float* uv, float* J,
+                      void* cuda_stream);
+int acino_fte_jac(acino_handle* h, int n_frames, const float* x, float* uv, float* J);
+
 /* ---- camera geometry (fp64, host pointers) -------------------------------------------------
  * Single-camera arguments: K [3][3], D [4], R [3][3] (world->camera), t [3]. */
 
@@ -147,8 +156,8 @@ int acino_lm_reduce_dev(acino_handle* h, int n, const float* a0, const double* a
 
 /* Block cyclic reduction of a block-tridiagonal SPD chain (schedule: acinoset_b200/bcr.py).
  * elim / surv are [n][3] int32 rows (block, left, right) / (block, eliminated-left, eliminated-right),
- * -1 = none.  factor overwrites D_e with W = chol(D_e)^-1 and rhs_e with z; info != 0 flags a
- * non-positive pivot (block index + 1). */
+ * -1 = none.  factor overwrites D_e with its factor R = L Delta^1/2 (strict lower triangle L, diagonal
+ * Delta^-1/2) and rhs_e with z = R^-1 b; info != 0 flags a non-positive pivot (block index + 1). */
 int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, double* D, const double* Lc,
                          double* P, double* Q, double* rhs, int32_t* info, void* cuda_stream);
 int acino_bcr_update_dev(acino_handle* h, int n_surv, const int32_t* surv, double* D, double* Lc,
