@@ -18,128 +18,194 @@ namespace acino {
 
 constexpr int SB = 75;          // super-block size: 3 frames x 25 parameters
 constexpr int LD = 76;          // shared-memory leading dimension (doubles)
-constexpr int BCR_THREADS = 256;
 constexpr size_t SB2 = (size_t)SB * SB;
 
-// C(75x75 tile set) = op(A) * B with A, B in shared memory (ld = LD); each thread owns a 5x5 tile:
-// ty = tid / 16 -> rows 5 ty .. 5 ty + 4, tx = tid % 16 -> cols 5 tx .. 5 tx + 4 (80 x 80 cover).
-template <bool TRANS_A>
-__device__ __forceinline__ void gemm75(const double* __restrict__ sA, const double* __restrict__ sB, double acc[5][5]) {
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    const int i0 = 5 * ty, j0 = 5 * tx;
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) acc[r][c] = 0.0;
-    if (i0 >= SB || j0 >= SB) return;
-    for (int k = 0; k < SB; ++k) {
-        double a[5], b[5];
-#pragma unroll
-        for (int r = 0; r < 5; ++r) a[r] = TRANS_A ? sA[k * LD + i0 + r] : sA[(i0 + r) * LD + k];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) b[c] = sB[k * LD + j0 + c];
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
-    }
-}
-
-// global (row-major 75x75) -> shared (ld 76); optionally transposed
-__device__ __forceinline__ void load_block(const double* __restrict__ g, double* __restrict__ s, bool transpose) {
-    for (int i = threadIdx.x; i < SB * SB; i += BCR_THREADS) {
-        const int r = i / SB, c = i - r * SB;
-        if (transpose) s[c * LD + r] = g[i];
-        else s[r * LD + c] = g[i];
-    }
-}
-
-// ---- bcr_factor: fused elimination of one super-block -------------------------------------------
+// ---- bcr_factor: fused, blocked elimination of one super-block --------------------------------------
 // Gaussian elimination (no pivoting; the block is SPD) of the augmented panel
 //     [ D_e | Lc_e | Lc_c^T | b_e ]      75 x (75 + 75 + 75 + 1)
 // held COLUMN-major in shared memory (column stride FCS = 76 doubles: 16-byte accesses of a quarter-warp
-// = 4 columns x 2 row pairs are bank-conflict-free, the pivot column is a broadcast).
-// Two threads own column j (interleaved row pairs).  Step k: a_ij -= a_ik (a_kj / a_kk) for i > k (D columns: i >= j only, the
-// row-k entry a_kj is read from the lower triangle as a_jk).  After step k-1 row k of the right-hand
-// columns is (L^-1 [Lc_e | Lc_c^T | b])_k with D = L Delta L^T, so
-//     P = R^-1 Lc_e, Q = R^-1 Lc_c^T, z = R^-1 b   with R = L Delta^1/2   are row scalings by a_kk^-1/2.
-// One barrier per step; the owner of the next pivot column updates its diagonal entry first and
-// publishes 1/a_kk.  No explicit inverse, no separate GEMMs: 0.5 MFMA per block instead of 1.1.
+// = 4 columns x 2 row pairs are bank-conflict-free, pivot-column reads are broadcasts).  After eliminating
+// pivots 0..k-1, row k of the right-hand columns is (L^-1 [Lc_e | Lc_c^T | b])_k with D = L Delta L^T, so
+//     P = R^-1 Lc_e, Q = R^-1 Lc_c^T, z = R^-1 b   with R = L Delta^1/2   are row scalings by a_kk^-1/2:
+// no explicit inverse and no separate GEMMs (0.5 MFMA per block instead of 1.1).
+// A rank-1 update per pivot streams the whole trailing panel through shared memory 75 times and is bound
+// by its 128 B/clk; so pivots are eliminated FB at a time (rank-FB update, the multipliers in registers):
+//   (a) one thread factors the FB x FB diagonal block in registers, publishes 1/a_qq and c_pq = a_pq / a_qq
+//       - for the NEXT block while (c) of the current one runs (look-ahead: the chain of dependent fp64
+//       divisions is off the critical path)
+//   (b) thread per row below the block: its FB panel entries (forward substitution with c);
+//       thread per right-hand column: its FB pivot-row entries (same recurrence)
+//   (c) two threads per trailing column (interleaved row pairs): a_ij += sum_p a_ip m_p, m_p = -a_pj / a_pp
+//       (D columns: lower triangle only, a_pj read as a_jp)
 // Stored for back-substitution in place of D_e: strict lower triangle = L (unit diagonal implied),
 // diagonal = a_kk^-1/2.
 constexpr int FCOLS = 3 * SB + 1;   // 226 panel columns
-constexpr int FCS = 76;             // column stride (doubles): 152 words = 24 (mod 32) -> 4 columns x 2 row-pairs tile the banks
-constexpr int FACTOR_THREADS = 512; // two threads per column (interleaved row pairs)
+constexpr int FCS = 76;             // column stride (doubles): 152 words = 24 (mod 32)
+constexpr int FB = 5;               // pivots per block step (divides 75)
+constexpr int FACTOR_THREADS = 512;
 constexpr size_t BCR_FACTOR_SMEM = (size_t)FCOLS * FCS * sizeof(double);
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+
+#ifdef ACINO_BCR_TIMING
+__device__ long long g_bcr_cycles[8];
+#define BCR_MARK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_bcr_cycles[slot], (unsigned long long)(_t - _tprev)); _tprev = _t; } } while (0)
+#else
+#define BCR_MARK(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(FACTOR_THREADS)
 bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__ D, const double* __restrict__ Lc,
                   double* __restrict__ P, double* __restrict__ Q, double* __restrict__ rhs, int* __restrict__ info) {
     extern __shared__ __align__(16) double sm[];     // [FCOLS][FCS]
-    __shared__ double sinv[SB], sdi[SB];
+    __shared__ double sinv[SB], sdi[SB], scpq[FB][FB];
     const int e = elim[3 * blockIdx.x], a = elim[3 * blockIdx.x + 1], c = elim[3 * blockIdx.x + 2];
     const int tid = threadIdx.x;
-    // ---- load the panel (column-major); row 75 of every column is zero padding
-    for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
-        const int r = i / SB, cc = i - r * SB;
-        sm[r * FCS + cc] = D[(size_t)e * SB2 + i];                                      // symmetric: (r,cc) == (cc,r)
-        if (a >= 0) sm[(SB + cc) * FCS + r] = Lc[(size_t)e * SB2 + i];                  // Lc_e (r, cc)
-        if (c >= 0) sm[(2 * SB + r) * FCS + cc] = Lc[(size_t)c * SB2 + i];              // Lc_c^T (cc, r) = Lc_c (r, cc)
-    }
-    if (tid < SB) sm[3 * SB * FCS + tid] = rhs[(size_t)e * SB + tid];
-    if (tid < FCOLS) sm[tid * FCS + SB] = 0.0;
-    __syncthreads();
-    if (tid == 0) {
-        const double d = sm[0];
-        if (!(d > 0.0)) atomicExch(info, e + 1);
-        sinv[0] = 1.0 / d;
+#ifdef ACINO_BCR_TIMING
+    long long _tprev = clock64();
+#endif
+    // ---- load the panel (column-major) with 8-byte async copies, all in flight at once
+    {
+        const double* gD = D + (size_t)e * SB2;
+        const double* gA = Lc + (size_t)e * SB2;
+        const double* gC = Lc + (size_t)(c >= 0 ? c : 0) * SB2;
+        for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
+            const int r = i / SB, cc = i - r * SB;
+            cp_async8(&sm[r * FCS + cc], gD + i);                              // symmetric: (r,cc) == (cc,r)
+            if (a >= 0) cp_async8(&sm[(SB + cc) * FCS + r], gA + i);           // Lc_e (r, cc)
+            if (c >= 0) cp_async8(&sm[(2 * SB + r) * FCS + cc], gC + i);       // Lc_c^T (cc, r) = Lc_c (r, cc)
+        }
+        if (tid < SB) sm[3 * SB * FCS + tid] = rhs[(size_t)e * SB + tid];
+        if (tid < FCOLS) sm[tid * FCS + SB] = 0.0;                             // row 75: zero padding
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     const int col = tid >> 1, half = tid & 1;
     const bool is_d = col < SB;
-    const bool active_col = col < FCOLS && (is_d || col >= 3 * SB || (col < 2 * SB ? a >= 0 : c >= 0));
+    const bool rhs_on = (tid >= SB && tid < FCOLS) && (tid >= 3 * SB || (tid < 2 * SB ? a >= 0 : c >= 0));   // phase (b)
+    const bool active_col = col < FCOLS && (is_d || col >= 3 * SB || (col < 2 * SB ? a >= 0 : c >= 0));       // phase (c)
     double* cj = sm + col * FCS;
-    for (int k = 0; k < SB - 1; ++k) {
-        __syncthreads();
-        if (!active_col || col <= k) continue;
-        const double* ck = sm + k * FCS;
-        const double m = -((is_d ? ck[col] : cj[k]) * sinv[k]);
-        int i = is_d ? col : k + 1;              // first row this column updates
-        if (col == k + 1 && half == 0) {         // owner of the next pivot: finish a_(k+1)(k+1), publish its inverse
-            const double d = fma(ck[i], m, cj[i]);
-            cj[i] = d;
-            if (!(d > 0.0)) atomicExch(info, e + 1);
-            sinv[k + 1] = 1.0 / d;
+    __syncthreads();
+    // (a) of a diagonal block in registers, by ONE thread (FACTOR_THREADS - 1: its column slot is beyond the panel,
+    // so it is otherwise idle).  For k1 > 0 it first applies the pending rank-FB update of block k1 - FB to the
+    // FB x FB entries itself ("look-ahead"): the factorisation of the next diagonal block - a chain of 5 dependent
+    // fp64 divisions - then overlaps the trailing update (c) of the current block instead of serialising with it.
+    auto diag_block = [&](const int k1) {
+        double A[FB][FB];
+#pragma unroll
+        for (int r = 0; r < FB; ++r)
+#pragma unroll
+            for (int p = 0; p <= r; ++p) A[r][p] = sm[(k1 + p) * FCS + k1 + r];
+        if (k1 > 0) {
+            const int k0 = k1 - FB;
+            double l[FB][FB];          // l[q][r] = a_(k1+r)(k0+q): panel column q, row k1 + r
+#pragma unroll
+            for (int q = 0; q < FB; ++q)
+#pragma unroll
+                for (int r = 0; r < FB; ++r) l[q][r] = sm[(k0 + q) * FCS + k1 + r];
+#pragma unroll
+            for (int p = 0; p < FB; ++p) {
+#pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const double mq = -(l[q][p] * sinv[k0 + q]);
+#pragma unroll
+                    for (int r = p; r < FB; ++r) A[r][p] = fma(l[q][r], mq, A[r][p]);
+                }
+            }
         }
-        if (col == k + 1) ++i;
+#pragma unroll
+        for (int q = 0; q < FB; ++q) {
+            const double d = A[q][q];
+            if (!(d > 0.0)) atomicExch(info, e + 1);
+            const double inv = 1.0 / d;
+            sinv[k1 + q] = inv;
+#pragma unroll
+            for (int r = q + 1; r < FB; ++r) {
+                const double cq = A[r][q] * inv;          // a_rq / a_qq
+                scpq[r][q] = cq;
+#pragma unroll
+                for (int p = q + 1; p <= r; ++p) A[r][p] = fma(-cq, A[p][q], A[r][p]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < FB; ++r)
+#pragma unroll
+            for (int p = 0; p <= r; ++p) sm[(k1 + p) * FCS + k1 + r] = A[r][p];
+    };
+    BCR_MARK(0);
+    if (tid == FACTOR_THREADS - 1) diag_block(0);
+    for (int k0 = 0; k0 < SB; k0 += FB) {
+        __syncthreads();
+        BCR_MARK(k0 == 0 ? 1 : 3);
+        // ---- (b) panel rows below the block (threads 0..74) and pivot rows of the right-hand columns (threads 75..225)
+        if (tid < SB ? tid >= k0 + FB : rhs_on) {
+            // element p of this thread's vector: row `tid` of panel column k0+p, or row k0+p of column `tid`
+            double* base = tid < SB ? sm + k0 * FCS + tid : sm + tid * FCS + k0;
+            const int stride = tid < SB ? FCS : 1;
+            double v[FB];
+#pragma unroll
+            for (int p = 0; p < FB; ++p) v[p] = base[p * stride];
+#pragma unroll
+            for (int p = 1; p < FB; ++p) {
+#pragma unroll
+                for (int q = 0; q < p; ++q) v[p] = fma(-scpq[p][q], v[q], v[p]);
+                base[p * stride] = v[p];
+            }
+        }
+        __syncthreads();
+        BCR_MARK(2);
+        // ---- (c) rank-FB update of the trailing columns; meanwhile (a) of the next diagonal block
+        const int k1 = k0 + FB;
+        if (tid == FACTOR_THREADS - 1 && k1 < SB) diag_block(k1);
+        if (!active_col || col < k1) continue;
+        double m[FB];
+#pragma unroll
+        for (int p = 0; p < FB; ++p) m[p] = -((is_d ? sm[(k0 + p) * FCS + col] : cj[k0 + p]) * sinv[k0 + p]);
+        const double* pk = sm + k0 * FCS;
+        // first row this column updates; the next diagonal block belongs to the look-ahead thread
+        int i = is_d ? (col < k1 + FB ? k1 + FB : col) : k1;
         if (i & 1) {                             // odd first row: a single-row update, then aligned pairs
-            if (half == 0) cj[i] = fma(ck[i], m, cj[i]);
+            if (half == 0 && i < SB) {
+                double v = cj[i];
+#pragma unroll
+                for (int p = 0; p < FB; ++p) v = fma(pk[p * FCS + i], m[p], v);
+                cj[i] = v;
+            }
             ++i;
         }
         // aligned row pairs (i, i+1), interleaved over the column's two threads; the last pair touches padding
         i += 2 * half;
-        for (; i + 12 < SB + 1; i += 16) {       // four pairs per trip: all loads, then the FMAs, then the stores
-            const double2 p0 = *reinterpret_cast<const double2*>(ck + i), p1 = *reinterpret_cast<const double2*>(ck + i + 4);
-            const double2 p2 = *reinterpret_cast<const double2*>(ck + i + 8), p3 = *reinterpret_cast<const double2*>(ck + i + 12);
+        for (; i + 4 < SB + 1; i += 8) {         // two pairs per trip
             double2 q0 = *reinterpret_cast<double2*>(cj + i), q1 = *reinterpret_cast<double2*>(cj + i + 4);
-            double2 q2 = *reinterpret_cast<double2*>(cj + i + 8), q3 = *reinterpret_cast<double2*>(cj + i + 12);
-            q0.x = fma(p0.x, m, q0.x); q0.y = fma(p0.y, m, q0.y);
-            q1.x = fma(p1.x, m, q1.x); q1.y = fma(p1.y, m, q1.y);
-            q2.x = fma(p2.x, m, q2.x); q2.y = fma(p2.y, m, q2.y);
-            q3.x = fma(p3.x, m, q3.x); q3.y = fma(p3.y, m, q3.y);
+            double2 l0[FB], l1[FB];
+#pragma unroll
+            for (int p = 0; p < FB; ++p) {
+                l0[p] = *reinterpret_cast<const double2*>(pk + p * FCS + i);
+                l1[p] = *reinterpret_cast<const double2*>(pk + p * FCS + i + 4);
+            }
+#pragma unroll
+            for (int p = 0; p < FB; ++p) {
+                q0.x = fma(l0[p].x, m[p], q0.x); q0.y = fma(l0[p].y, m[p], q0.y);
+                q1.x = fma(l1[p].x, m[p], q1.x); q1.y = fma(l1[p].y, m[p], q1.y);
+            }
             *reinterpret_cast<double2*>(cj + i) = q0;
             *reinterpret_cast<double2*>(cj + i + 4) = q1;
-            *reinterpret_cast<double2*>(cj + i + 8) = q2;
-            *reinterpret_cast<double2*>(cj + i + 12) = q3;
         }
-        for (; i < SB; i += 4) {
-            const double2 p0 = *reinterpret_cast<const double2*>(ck + i);
+        if (i < SB) {
             double2 q0 = *reinterpret_cast<double2*>(cj + i);
-            q0.x = fma(p0.x, m, q0.x);
-            q0.y = fma(p0.y, m, q0.y);
+#pragma unroll
+            for (int p = 0; p < FB; ++p) {
+                const double2 l0 = *reinterpret_cast<const double2*>(pk + p * FCS + i);
+                q0.x = fma(l0.x, m[p], q0.x);
+                q0.y = fma(l0.y, m[p], q0.y);
+            }
             *reinterpret_cast<double2*>(cj + i) = q0;
         }
     }
     __syncthreads();
+    BCR_MARK(3);
     if (tid < SB) sdi[tid] = sqrt(fmax(sinv[tid], 0.0));
     __syncthreads();
     // ---- write-out: factor in place of D_e, P, Q, z
@@ -150,74 +216,158 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
         if (c >= 0) Q[(size_t)e * SB2 + i] = sm[(2 * SB + cc) * FCS + r] * sdi[r];
     }
     if (tid < SB) rhs[(size_t)e * SB + tid] = sm[3 * SB * FCS + tid] * sdi[tid];
+    BCR_MARK(4);
 }
 
-__global__ void __launch_bounds__(BCR_THREADS)
+#ifdef ACINO_BCR_TIMING
+extern "C" void acino_debug_bcr_cycles(long long* out8) { cudaMemcpyFromSymbol(out8, g_bcr_cycles, sizeof(long long) * 8); }
+extern "C" void acino_debug_bcr_reset() { long long z[8] = {0}; cudaMemcpyToSymbol(g_bcr_cycles, z, sizeof(z)); }
+#endif
+
+// ---- bcr_update: Schur update of one surviving super-block ------------------------------------------
+//   Lc_j = -Q_el^T P_el                        (75 x 75 GEMM, warps 0-7: 15 x 15 grid of 5x5 register tiles)
+//   D_j -= Q_el^T Q_el + P_er^T P_er           (two SYRKs: only the 120 upper tiles of each; warps 8-11 take
+//                                               Q_el^T Q_el, warps 12-15 P_er^T P_er, summed through shared
+//                                               memory, written with their mirror images)
+//   b_j -= Q_el^T z_el + P_er^T z_er
+// The three operand blocks are staged with 8-byte async copies issued together.
+constexpr int UPDATE_THREADS = 512;
+constexpr size_t BCR_UPDATE_SMEM = (size_t)(3 * SB * LD + 2 * SB) * sizeof(double);
+
+struct TriTiles {
+    unsigned char ty[120], tx[120];
+};
+constexpr TriTiles make_tri_tiles() {
+    TriTiles t{};
+    int n = 0;
+    for (int y = 0; y < 15; ++y)
+        for (int x = y; x < 15; ++x) {
+            t.ty[n] = (unsigned char)y;
+            t.tx[n] = (unsigned char)x;
+            ++n;
+        }
+    return t;
+}
+__constant__ TriTiles c_tri_tiles = make_tri_tiles();
+
+// acc(5x5) = A[:, i0:i0+5]^T B[:, j0:j0+5], A and B 75 x 75 row-major in shared memory (ld = LD)
+__device__ __forceinline__ void tile_atb(const double* __restrict__ sA, const double* __restrict__ sB, const int i0,
+                                         const int j0, double acc[5][5]) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[r][c] = 0.0;
+#pragma unroll 3
+    for (int k = 0; k < SB; ++k) {
+        double a[5], b[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) a[r] = sA[k * LD + i0 + r];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) b[c] = sB[k * LD + j0 + c];
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+    }
+}
+
+__global__ void __launch_bounds__(UPDATE_THREADS)
 bcr_update_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict__ D, double* __restrict__ Lc,
                   const double* __restrict__ P, const double* __restrict__ Q, double* __restrict__ rhs) {
     extern __shared__ __align__(16) double sm[];
-    double* sA = sm;
-    double* sB = sm + SB * LD;
-    __shared__ double sz[SB];
+    double* sQ = sm;                       // Q_el
+    double* sP = sm + SB * LD;             // P_el; after the GEMM: staging of the P_er^T P_er tiles
+    double* sP2 = sm + 2 * SB * LD;        // P_er
+    double* szl = sm + 3 * SB * LD;        // z_el
+    double* szr = szl + SB;                // z_er
     const int j = surv[3 * blockIdx.x], el = surv[3 * blockIdx.x + 1], er = surv[3 * blockIdx.x + 2];
     const int tid = threadIdx.x;
-    const int ty = tid >> 4, tx = tid & 15;
-    double accD[5][5], acc[5][5];
+    for (int i = tid; i < SB * SB; i += UPDATE_THREADS) {
+        const int r = i / SB, c = i - r * SB;
+        if (el >= 0) {
+            cp_async8(&sQ[r * LD + c], Q + (size_t)el * SB2 + i);
+            cp_async8(&sP[r * LD + c], P + (size_t)el * SB2 + i);
+        }
+        if (er >= 0) cp_async8(&sP2[r * LD + c], P + (size_t)er * SB2 + i);
+    }
+    if (tid < SB) {
+        szl[tid] = el >= 0 ? rhs[(size_t)el * SB + tid] : 0.0;
+        szr[tid] = er >= 0 ? rhs[(size_t)er * SB + tid] : 0.0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    double acc[5][5];
+    if (tid < 256) {
+        // ---- Lc_j = -Q_el^T P_el
+        const int ty = tid >> 4, tx = tid & 15;
+        if (el >= 0 && ty < 15 && tx < 15) {
+            tile_atb(sQ, sP, 5 * ty, 5 * tx, acc);
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+            for (int r = 0; r < 5; ++r)
 #pragma unroll
-        for (int c = 0; c < 5; ++c) accD[r][c] = 0.0;
-    double rj = 0.0;
-    if (el >= 0) {
-        load_block(Q + (size_t)el * SB2, sA, false);
-        load_block(P + (size_t)el * SB2, sB, false);
-        if (tid < SB) sz[tid] = rhs[(size_t)el * SB + tid];
-        __syncthreads();
-        // Lc_j = -Q^T P
-        gemm75<true>(sA, sB, acc);
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const int i = 5 * ty + r, jj = 5 * tx + c;
-                if (i < SB && jj < SB) Lc[(size_t)j * SB2 + i * SB + jj] = -acc[r][c];
-            }
-        // D_j -= Q^T Q ; b_j -= Q^T z
-        gemm75<true>(sA, sA, acc);
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) accD[r][c] += acc[r][c];
+                for (int c = 0; c < 5; ++c) Lc[(size_t)j * SB2 + (5 * ty + r) * SB + 5 * tx + c] = -acc[r][c];
+        }
+        // ---- b_j -= Q_el^T z_el + P_er^T z_er
         if (tid < SB) {
             double s = 0.0;
-            for (int k = 0; k < SB; ++k) s = fma(sA[k * LD + tid], sz[k], s);
-            rj += s;
+            if (el >= 0)
+                for (int k = 0; k < SB; ++k) s = fma(sQ[k * LD + tid], szl[k], s);
+            if (er >= 0)
+                for (int k = 0; k < SB; ++k) s = fma(sP2[k * LD + tid], szr[k], s);
+            rhs[(size_t)j * SB + tid] -= s;
         }
-        __syncthreads();
+        asm volatile("bar.sync 2, 512;" ::: "memory");      // P_el is free from here on
+        asm volatile("bar.sync 3, 512;" ::: "memory");      // staged tiles are complete
+    } else {
+        // ---- D_j -= Q_el^T Q_el + P_er^T P_er, upper tiles; group A (Q) = threads 256..383, group B (P) = 384..511
+        const int t = (tid - 256) & 127;
+        const bool grpB = tid >= 384;
+        const bool have = t < 120 && (grpB ? er >= 0 : el >= 0);
+        int ty = 0, tx = 0;
+        if (t < 120) {
+            ty = c_tri_tiles.ty[t];
+            tx = c_tri_tiles.tx[t];
+        }
+        if (have) {
+            const double* M = grpB ? sP2 : sQ;
+            tile_atb(M, M, 5 * ty, 5 * tx, acc);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) acc[r][c] = 0.0;
+        }
+        asm volatile("bar.sync 2, 512;" ::: "memory");      // the GEMM no longer reads P_el
+        if (grpB && t < 120) {
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) sP[(5 * ty + r) * LD + 5 * tx + c] = acc[r][c];
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        if (!grpB && t < 120) {
+            // read-modify-write of this thread's own 25 entries: all loads first (a store to D followed by a load
+            // from D would otherwise be serialised - one global round trip per entry); the mirror image gets the
+            // same value (D stays exactly symmetric)
+            double* Dj = D + (size_t)j * SB2;
+            double nv[5][5];
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) nv[r][c] = Dj[(5 * ty + r) * SB + 5 * tx + c];
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) nv[r][c] -= acc[r][c] + sP[(5 * ty + r) * LD + 5 * tx + c];
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    Dj[(5 * ty + r) * SB + 5 * tx + c] = nv[r][c];
+                    if (ty != tx) Dj[(5 * tx + c) * SB + 5 * ty + r] = nv[r][c];
+                }
+        }
     }
-    if (er >= 0) {
-        load_block(P + (size_t)er * SB2, sA, false);
-        if (tid < SB) sz[tid] = rhs[(size_t)er * SB + tid];
-        __syncthreads();
-        gemm75<true>(sA, sA, acc);
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) accD[r][c] += acc[r][c];
-        if (tid < SB) {
-            double s = 0.0;
-            for (int k = 0; k < SB; ++k) s = fma(sA[k * LD + tid], sz[k], s);
-            rj += s;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const int i = 5 * ty + r, jj = 5 * tx + c;
-            if (i < SB && jj < SB) D[(size_t)j * SB2 + i * SB + jj] -= accD[r][c];
-        }
-    if (tid < SB) rhs[(size_t)j * SB + tid] -= rj;
 }
 
 // x_e = R^-T (z - P x_a - Q x_c), R = L Delta^1/2 stored by bcr_factor in D_e.  256 threads.
@@ -287,7 +437,6 @@ bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*
     }
 }
 
-constexpr size_t BCR_SMEM = 2 * SB * LD * sizeof(double);
 
 cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const double* Lc, double* P, double* Q,
                               double* rhs, int* info, cudaStream_t s) {
@@ -296,7 +445,7 @@ cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const doub
     if (!set) {
         cudaError_t e = cudaFuncSetAttribute(bcr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR_SMEM);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_SMEM);
+        e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE_SMEM);
         if (e != cudaSuccess) return e;
         set = true;
     }
@@ -307,7 +456,7 @@ cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const doub
 cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
                               double* rhs, cudaStream_t s) {
     if (n_surv <= 0) return cudaSuccess;
-    bcr_update_kernel<<<n_surv, BCR_THREADS, BCR_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
+    bcr_update_kernel<<<n_surv, UPDATE_THREADS, BCR_UPDATE_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
     return cudaGetLastError();
 }
 
