@@ -385,9 +385,9 @@ bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*
     const int tid = threadIdx.x;
     if (tid < SB) sxx[tid] = a >= 0 ? x[(size_t)a * SB + tid] : 0.0;
     else if (tid < 2 * SB) sxx[tid] = c >= 0 ? x[(size_t)c * SB + tid - SB] : 0.0;
-    for (int i = tid; i < SB * SB; i += 256) {
+    for (int i = tid; i < SB * SB; i += 256) {      // L: async, lands while the mat-vec below runs
         const int r = i / SB;
-        sL[r * LD + (i - r * SB)] = D[(size_t)e * SB2 + i];
+        cp_async8(&sL[r * LD + (i - r * SB)], D + (size_t)e * SB2 + i);
     }
     __syncthreads();
     if (tid < 3 * SB) {
@@ -406,6 +406,7 @@ bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*
         }
         spart[part][r] = s0 + s1;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (tid < 32) {
         const int lane = tid;

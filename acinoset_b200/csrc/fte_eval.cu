@@ -36,10 +36,10 @@ constexpr int N_PAIR = NANG * (NANG + 1) / 2;  // 253 unordered angle pairs (inc
 // One entry per unordered pair of angle slots.  Related pairs (one joint is an ancestor-or-self of
 // the other): H = tau_al . y_be with `be` the deeper angle.  Entry = float offsets into the frame's
 // tau / y arrays and the packed H index: bits 0-7 al*8, 8-15 be*8, 16-24 index.  Unrelated pairs
-// (disjoint subtrees) are structural zeros: they point at the all-zero twist slot 22, so the same
-// branch-free dot product writes 0.  Zeros are sorted last.
+// (disjoint subtrees) are structural zeros, sorted last: entries N_REL.. only carry the H index and are
+// written as 0 without any arithmetic.
 struct PairTable {
-    unsigned e[N_PAIR];
+    unsigned e[N_PAIR + 3];     // padded to 256 entries = 1024 bytes: one bulk copy
     int joint[NANG];
 };
 constexpr PairTable make_pair_table() {
@@ -61,7 +61,19 @@ constexpr PairTable make_pair_table() {
     for (int a = 0; a < NANG; ++a) t.joint[a] = k_angle_joint[a];
     return t;
 }
+constexpr int count_related_pairs() {
+    int n = 0;
+    for (int be = 0; be < NANG; ++be)
+        for (int al = 0; al < NANG; ++al) {
+            const int ja = k_angle_joint[al], jb = k_angle_joint[be];
+            if (joint_is_anc(ja, jb) && (ja != jb || al <= be)) ++n;
+        }
+    return n;
+}
+constexpr int N_REL = count_related_pairs();   // 185 related pairs; the other 68 are structural zeros
+static_assert(N_REL == 185, "kinematic tree changed: check the pair table");
 __constant__ PairTable c_tab = make_pair_table();
+__device__ __align__(16) const PairTable d_tab = make_pair_table();     // global-memory copy: source of the bulk (TMA) copy
 
 template <int FT>
 struct __align__(16) Smem {
@@ -74,7 +86,7 @@ struct __align__(16) Smem {
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
     union {
-        float Il[FT * NL][NSP];        // per-marker spatial inertia + wrench   (P2 -> P3)
+        __align__(16) float Il[FT * NL][NSP + 1];   // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 / LDS.64  (P2 -> P3)
         struct {                       // bulk-copied input tiles (kernel start -> end of the camera loop)
             float2 meas[FT * ACINO_MAX_CAMS / 2 * NL];   // [FT][C][NL] (u,v), C <= 8 fits the union
             float w[FT * ACINO_MAX_CAMS / 2 * NL];       // [FT][C][NL]
@@ -116,6 +128,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
+// shared -> global bulk store (TMA, 1-D) of a staged output tile; the issuing thread waits until the
+// source has been read before the CTA may retire
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+
 #ifdef ACINO_PHASE_TIMING
 __device__ long long g_phase_cycles[16];
 __device__ int g_phase_count;
@@ -139,7 +158,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
     const int C = scene.n_cams;
     // the input tiles of a full CTA are contiguous, 16-byte aligned blocks of global memory: stage them
     // with three 1-D bulk async copies (TMA) that overlap the forward kinematics
-    const bool staged = use_bulk && nf == FT && C <= ACINO_MAX_CAMS / 2;
+    const bool staged = (use_bulk & 1) && nf == FT && C <= ACINO_MAX_CAMS / 2;
 #ifdef ACINO_PHASE_TIMING
     long long _tprev = clock64();
 #endif
@@ -151,8 +170,9 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             mbar_init(&S.mbar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const unsigned bx = FT * NA * 4, bm = FT * C * NL * 8, bw = FT * C * NL * 4;
-            mbar_expect_tx(&S.mbar[0], bx);
+            mbar_expect_tx(&S.mbar[0], bx + (N_PAIR + 3) * 4);
             bulk_g2s(&S.x[0][0], xg + (size_t)f0 * NA, bx, &S.mbar[0]);
+            bulk_g2s(&S.tab[0], &d_tab.e[0], (N_PAIR + 3) * 4, &S.mbar[0]);
             mbar_expect_tx(&S.mbar[1], bm + bw);
             bulk_g2s(&S.in.meas[0], meas + (size_t)f0 * C * NL * 2, bm, &S.mbar[1]);
             bulk_g2s(&S.in.w[0], wts + (size_t)f0 * C * NL, bw, &S.mbar[1]);
@@ -163,7 +183,8 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             (&S.x[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
         }
     }
-    for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
+    if (!staged)
+        for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
     if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
     __syncthreads();
     if (staged) mbar_wait(&S.mbar[0], 0);
@@ -296,7 +317,9 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         if (staged) __syncthreads();   // the input tiles alias Il: every thread is done reading them
         PHASE_MARK(3);
         // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]
-        float* o = S.Il[tid];
+        float o[NSP + 1];
+#pragma unroll
+        for (int i = 0; i < NSP + 1; ++i) o[i] = 0.f;
         if (WANT_H) {
             // PA = [p]x A  (rows)
             const float q00 = py * a02 - pz * a01, q01 = py * a12 - pz * a11, q02 = py * a22 - pz * a12;
@@ -318,33 +341,39 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         o[22] = pz * b0 - px * b2;
         o[23] = px * b1 - py * b0;
         o[24] = b0; o[25] = b1; o[26] = b2;
+        float4* dst = reinterpret_cast<float4*>(S.Il[tid]);
+#pragma unroll
+        for (int i = (WANT_H ? 0 : 5); i < (NSP + 1) / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
     __syncthreads();
     PHASE_MARK(4);
 
-    // ---- P3: subtree sums up the kinematic tree, one thread per (component, frame)
-    for (int task = tid; task < FT * NSP; task += NT) {
-        const int k = task / FT;
-        const int f = task - k * FT;
-        if (!WANT_H && k < 21) continue;
-        float v[NL];
+    // ---- P3: subtree sums up the kinematic tree, one thread per (component pair, frame), packed adds
+    {
+        constexpr int NKP = (NSP + 1) / 2;       // 14 component pairs
+        const int task = tid;
+        const int f = task / NKP;
+        const int kp = task - f * NKP;
+        if (task < FT * NKP && (WANT_H || kp >= 10)) {
+            f2 v[NL];
 #pragma unroll
-        for (int l = 0; l < NL; ++l) v[l] = S.Il[f * NL + l][k];
-        const float s13 = v[19], s12 = v[18] + s13;
-        const float s11 = v[16], s10 = v[15] + s11;
-        const float s5 = v[7], s4 = v[6] + s5;
-        const float s3 = ((v[5] + v[14]) + v[17]) + ((s4 + s10) + s12);
-        const float s9 = v[13], s8 = v[12] + s9;
-        const float s7 = v[10], s6 = v[9] + s7;
-        const float s2 = ((v[4] + v[8]) + v[11]) + ((s3 + s6) + s8);
-        const float s1 = v[3] + s2;
-        const float s0 = ((v[0] + v[1]) + v[2]) + s1;
-        float* d = &S.Ij[f][0][k];
-        constexpr int IS = NSP + 1;
-        d[0 * IS] = s0;  d[1 * IS] = s1;  d[2 * IS] = s2;   d[3 * IS] = s3;
-        d[4 * IS] = s4;  d[5 * IS] = s5;  d[6 * IS] = s6;   d[7 * IS] = s7;
-        d[8 * IS] = s8;  d[9 * IS] = s9;  d[10 * IS] = s10; d[11 * IS] = s11;
-        d[12 * IS] = s12; d[13 * IS] = s13;
+            for (int l = 0; l < NL; ++l) v[l] = pk(*reinterpret_cast<const float2*>(&S.Il[f * NL + l][2 * kp]));
+            const f2 s13 = v[19], s12 = add2(v[18], s13);
+            const f2 s11 = v[16], s10 = add2(v[15], s11);
+            const f2 s5 = v[7], s4 = add2(v[6], s5);
+            const f2 s3 = add2(add2(add2(v[5], v[14]), v[17]), add2(add2(s4, s10), s12));
+            const f2 s9 = v[13], s8 = add2(v[12], s9);
+            const f2 s7 = v[10], s6 = add2(v[9], s7);
+            const f2 s2 = add2(add2(add2(v[4], v[8]), v[11]), add2(add2(s3, s6), s8));
+            const f2 s1 = add2(v[3], s2);
+            const f2 s0 = add2(add2(add2(v[0], v[1]), v[2]), s1);
+            float* d = &S.Ij[f][0][2 * kp];
+            constexpr int IS = NSP + 1;
+#define ST2(j, v) *reinterpret_cast<float2*>(d + (j) * IS) = make_float2(lo(v), hi(v))
+            ST2(0, s0); ST2(1, s1); ST2(2, s2); ST2(3, s3); ST2(4, s4); ST2(5, s5); ST2(6, s6);
+            ST2(7, s7); ST2(8, s8); ST2(9, s9); ST2(10, s10); ST2(11, s11); ST2(12, s12); ST2(13, s13);
+#undef ST2
+        }
     }
     __syncthreads();   // Il is dead from here on; the staged outputs alias it
     PHASE_MARK(5);
@@ -399,7 +428,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
     //      thread keeps its frame (tid % FT) and walks the table with stride 20: p = tid / FT + 20 k.
     //      All loads and dot products first, all stores last: no store -> load ordering between entries.
     if (WANT_H) {
-        constexpr int NE = (N_PAIR + NL - 1) / NL;   // 13
+        constexpr int NE = (N_REL + NL - 1) / NL;    // 10 related entries per thread
         const int f = tid % FT, p0 = tid / FT;
         const float* tau_f = &S.tau[f][0];
         const float* y_f = &S.o.y[f][0];
@@ -407,7 +436,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         unsigned e[NE];
         float hv[NE];
 #pragma unroll
-        for (int k = 0; k < NE; ++k) e[k] = S.tab[min(p0 + NL * k, N_PAIR - 1)];
+        for (int k = 0; k < NE; ++k) e[k] = S.tab[min(p0 + NL * k, N_REL - 1)];
 #pragma unroll
         for (int k = 0; k < NE; ++k) {
             const float4 a0 = *reinterpret_cast<const float4*>(tau_f + (e[k] & 0xFFu));
@@ -418,12 +447,31 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         }
 #pragma unroll
         for (int k = 0; k < NE; ++k)
-            if (p0 + NL * k < N_PAIR) H_f[e[k] >> 16] = hv[k];
+            if (p0 + NL * k < N_REL) H_f[e[k] >> 16] = hv[k];
+        // structural zeros: (N_PAIR - N_REL) x FT stores
+#pragma unroll
+        for (int k = 0; k < ((N_PAIR - N_REL) * FT + NT - 1) / NT; ++k) {
+            const int z = p0 + NL * k;
+            if (z < N_PAIR - N_REL) H_f[S.tab[N_REL + z] >> 16] = 0.f;
+        }
     }
     __syncthreads();
     PHASE_MARK(7);
 
-    // ---- P5: write-out.  The staged blocks have the global layout: straight vector copies
+    // ---- P5: write-out.  The staged blocks have the global layout.  Full tiles with 16-byte aligned outputs:
+    //      three bulk async stores (TMA) issued by one thread; otherwise straight vector copies
+    if ((use_bulk & 2) && nf == FT) {
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (cost_out) bulk_s2g(cost_out + f0, &S.o.cost[0], FT * 4);
+            if (g_out) bulk_s2g(g_out + (size_t)f0 * NA, &S.o.g[0][0], FT * NA * 4);
+            if (WANT_H && H_out) bulk_s2g(H_out + (size_t)f0 * NU, &S.o.H[0][0], FT * NU * 4);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        PHASE_MARK(8);
+        return;
+    }
     if (cost_out)
         for (int f = tid; f < nf; f += NT) cost_out[f0 + f] = S.o.cost[f];
     if (g_out) {
@@ -516,7 +564,9 @@ static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const fl
                                      const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
-    const int use_bulk = ((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0;
+    // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
+    const int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
+                         (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
     const int grid = (n_frames + FT - 1) / FT;
     const size_t smem = sizeof(Smem<FT>);
     static bool attr_set = false;
@@ -541,11 +591,17 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
         const char* e = getenv("ACINO_FTE_VARIANT");
         g_variant = e ? atoi(e) : 0;
     }
-    // variant 4: 16 frames per CTA (kept for A/B runs, scripts/bench_variants.sh); the default is 8 frames,
-    // 5 CTAs per SM, runtime camera-pair loop (unrolling the pair loop or trading CTAs for registers
-    // measured no faster - profiles/r01_fte_eval.md)
+    // Default: 8 frames per CTA, 4 CTAs per SM (96 registers, no spills), runtime camera-pair loop.
+    // A/B variants kept for scripts/bench_variants.sh (B200, 256 000 frames, profiles/r01_fte_eval.md):
+    //   0 default 6.45e8 frames/s | 1: 5 CTAs/SM, 72 regs 6.2e8 | 4: 16 frames/CTA 4.8e8 | 5/6: 4 frames/CTA 5.7e8 / 5.4e8
+    //   8: camera-pair loop unrolled 6.4e8 | 9: unrolled, 3 CTAs/SM, 128 regs 5.6e8
+    if (g_variant == 1) return launch_fte_eval_v<8, 5, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
     if (g_variant == 4) return launch_fte_eval_v<16, 2, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    return launch_fte_eval_v<8, 5, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 5) return launch_fte_eval_v<4, 9, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 6) return launch_fte_eval_v<4, 10, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    return launch_fte_eval_v<8, 4, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
