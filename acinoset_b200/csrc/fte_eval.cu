@@ -25,6 +25,7 @@
 // H = sum_l J_l^T A_l J_l collapses to tau_a^T I_{deeper subtree} tau_b: ~4 kFMA instead of
 // ~8 kFMA per frame for the chain rule and no 60x25 Jacobian is ever materialised.
 #include <cstdlib>
+#include <type_traits>
 
 #include "acino_common.cuh"
 #include "cheetah_fk.cuh"
@@ -75,22 +76,34 @@ static_assert(N_REL == 185, "kinematic tree changed: check the pair table");
 __constant__ PairTable c_tab = make_pair_table();
 __device__ __align__(16) const PairTable d_tab = make_pair_table();     // global-memory copy: source of the bulk (TMA) copy
 
-template <int FT>
+// bulk-copied input tiles.  One bulk copy per frame into padded frame slots: the 20 lanes of frame f+1 continue in
+// the banks where frame f stopped (stride = 8 (mod 32) words for the float2 tile, 20 (mod 32) for the weights), so a
+// warp that straddles two frames reads conflict-free
+template <int FT, int MAXC>
+struct InTiles {
+    float2 meas[FT * (MAXC * NL + 16)];   // [FT][C][NL] (u,v)
+    float w[FT * (MAXC * NL + 32)];       // [FT][C][NL]
+};
+struct NoTiles {};
+constexpr int MAXC_PERSIST = 6;           // cameras the separate (prefetchable) input buffer of the persistent kernel holds
+
+template <int FT, bool PERSIST>
 struct __align__(16) Smem {
-    float x[FT][NA];                   // state
+    float x[2][FT][NA];                // state (double buffered: the persistent kernel prefetches the next tile)
     float p[FT][NL][3];                // marker positions relative to the head point
     float2 sc[FT][NANG];               // (sin, cos) of every angle
     float costp[FT][NL];               // per-(frame, marker) cost partials
     unsigned tab[N_PAIR + 3];          // pair table (copy of c_tab.e)
-    __align__(16) float Ij[FT][NJ][NSP + 1];   // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads)
+    // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads); frame stride 396 words = 12 (mod 32):
+    // the 8 frames of a quarter-warp hit 8 distinct 4-bank groups (392 gave 2-way conflicts on every LDS.128 of P4a)
+    __align__(16) float Ij[FT][NJ * (NSP + 1) + 4];
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
+    // persistent kernel: input tiles in their own buffer, refilled for the NEXT tile while P2b..P5 of the current one run
+    __align__(16) typename std::conditional<PERSIST, InTiles<FT, MAXC_PERSIST>, NoTiles>::type in_s;
     union {
         __align__(16) float Il[FT * NL][NSP + 1];   // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 / LDS.64  (P2 -> P3)
-        struct {                       // bulk-copied input tiles (kernel start -> end of the camera loop)
-            float2 meas[FT * ACINO_MAX_CAMS / 2 * NL];   // [FT][C][NL] (u,v), C <= 8 fits the union
-            float w[FT * ACINO_MAX_CAMS / 2 * NL];       // [FT][C][NL]
-        } in;
+        InTiles<FT, ACINO_MAX_CAMS / 2> in_u;       // one-tile-per-CTA kernel: input tiles alias Il (kernel start -> end of the camera loop)
         struct {                       // staged outputs in their global layout  (P4 -> P5)
             float H[FT][NU];
             float g[FT][NA];
@@ -143,7 +156,7 @@ __device__ int g_phase_count;
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
-template <int FT, bool WANT_H, int MINB, int NPAIR>
+template <int FT, bool WANT_H, int MINB, int NPAIR, bool PERSIST>
 __global__ void __launch_bounds__(FT * NL, MINB)
 fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
                 const float* __restrict__ xg, const float* __restrict__ meas,
@@ -151,53 +164,94 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
                 float* __restrict__ g_out, float* __restrict__ H_out) {
     constexpr int NT = FT * NL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<FT>& S = *reinterpret_cast<Smem<FT>*>(smem_raw);
+    Smem<FT, PERSIST>& S = *reinterpret_cast<Smem<FT, PERSIST>*>(smem_raw);
     const int tid = threadIdx.x;
-    const int f0 = blockIdx.x * FT;
-    const int nf = min(FT, n_frames - f0);
     const int C = scene.n_cams;
-    // the input tiles of a full CTA are contiguous, 16-byte aligned blocks of global memory: stage them
-    // with three 1-D bulk async copies (TMA) that overlap the forward kinematics
-    const bool staged = (use_bulk & 1) && nf == FT && C <= ACINO_MAX_CAMS / 2;
+    const int n_tiles = (n_frames + FT - 1) / FT;
+    // the input tiles of a full tile are contiguous, 16-byte aligned blocks of global memory: stage them with 1-D
+    // bulk async copies (TMA) that overlap the forward kinematics (and, in the persistent kernel, the previous tile)
+    const bool bulk_in = (use_bulk & 1) && C <= (PERSIST ? MAXC_PERSIST : ACINO_MAX_CAMS / 2);
+    float2* in_meas;
+    float* in_w;
+    if constexpr (PERSIST) {
+        in_meas = S.in_s.meas;
+        in_w = S.in_s.w;
+    } else {
+        in_meas = S.in_u.meas;
+        in_w = S.in_u.w;
+    }
+    // padded frame strides of the staged tiles (see InTiles): float2 units / float units
+    const int ms2 = (C * NL * 2 + ((8 - C * NL * 2) & 31)) >> 1;
+    const int ws = C * NL + ((20 - C * NL) & 31);
+    const unsigned bx = FT * NA * 4, bm = C * NL * 8, bw = C * NL * 4;     // bytes: state tile; per-frame meas / weight rows
+    auto issue_x = [&](const int t, const int buf, const bool with_tab) {
+        mbar_expect_tx(&S.mbar[0], bx + (with_tab ? (N_PAIR + 3) * 4 : 0));
+        bulk_g2s(&S.x[buf][0][0], xg + (size_t)t * FT * NA, bx, &S.mbar[0]);
+        if (with_tab) bulk_g2s(&S.tab[0], &d_tab.e[0], (N_PAIR + 3) * 4, &S.mbar[0]);
+    };
+    auto issue_mw = [&](const int t) {
+        mbar_expect_tx(&S.mbar[1], FT * (bm + bw));
+        for (int ff = 0; ff < FT; ++ff) {
+            bulk_g2s(&in_meas[ff * ms2], meas + (size_t)(t * FT + ff) * C * NL * 2, bm, &S.mbar[1]);
+            bulk_g2s(&in_w[ff * ws], wts + (size_t)(t * FT + ff) * C * NL, bw, &S.mbar[1]);
+        }
+    };
 #ifdef ACINO_PHASE_TIMING
     long long _tprev = clock64();
 #endif
 
-    // ---- P0: kick off the input copies; pair table + zero twist slot -> smem
-    if (staged) {
-        if (tid == 0) {
-            mbar_init(&S.mbar[0], 1);
-            mbar_init(&S.mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const unsigned bx = FT * NA * 4, bm = FT * C * NL * 8, bw = FT * C * NL * 4;
-            mbar_expect_tx(&S.mbar[0], bx + (N_PAIR + 3) * 4);
-            bulk_g2s(&S.x[0][0], xg + (size_t)f0 * NA, bx, &S.mbar[0]);
-            bulk_g2s(&S.tab[0], &d_tab.e[0], (N_PAIR + 3) * 4, &S.mbar[0]);
-            mbar_expect_tx(&S.mbar[1], bm + bw);
-            bulk_g2s(&S.in.meas[0], meas + (size_t)f0 * C * NL * 2, bm, &S.mbar[1]);
-            bulk_g2s(&S.in.w[0], wts + (size_t)f0 * C * NL, bw, &S.mbar[1]);
+    // ---- prologue: barriers, zero twist slot, the first tile's copies
+    int tile = blockIdx.x;
+    if (bulk_in && tid == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < n_tiles && (tile + 1) * FT <= n_frames) {
+            issue_x(tile, 0, true);
+            issue_mw(tile);
         }
+    }
+    if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
+    bool tab_ready = false;
+    unsigned ph_x = 0, ph_m = 0;       // completed phases of mbar[0] / mbar[1]
+    bool out_pending = false;          // (thread 0) bulk stores of the previous tile may still be reading `o`
+    __syncthreads();
+
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int f0 = tile * FT;
+    const int nf = min(FT, n_frames - f0);
+    const bool staged = bulk_in && nf == FT;
+    const int xb = PERSIST ? (it & 1) : 0;
+    float (*Sx)[NA] = S.x[xb];
+    // ---- P0: the tile's state (and, first time, the pair table)
+    if (staged) {
+        mbar_wait(&S.mbar[0], ph_x & 1);
+        ++ph_x;
+        tab_ready = true;
     } else {
         for (int i = tid; i < FT * NA; i += NT) {
             const int f = i / NA;
-            (&S.x[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
+            (&Sx[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
         }
+        if (!tab_ready)
+            for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
+        tab_ready = true;
+        __syncthreads();
     }
-    if (!staged)
-        for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
-    if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
-    __syncthreads();
-    if (staged) mbar_wait(&S.mbar[0], 0);
     PHASE_MARK(0);
 
     // ---- P1a: sin/cos of the 22 angles, one thread per (angle, frame)
     for (int t = tid; t < FT * NANG; t += NT) {
         const int a = t / FT, f = t - a * FT;
         float sn, cs;
-        sincosf(S.x[f][3 + a], &sn, &cs);
+        sincosf(Sx[f][3 + a], &sn, &cs);
         S.sc[f][a] = make_float2(sn, cs);
     }
     __syncthreads();
+    if (PERSIST && bulk_in && tid == 0) {          // every thread is past its wait on mbar[0]: re-arm it for the next tile
+        const int tn = tile + gridDim.x;
+        if (tn < n_tiles && (tn + 1) * FT <= n_frames) issue_x(tn, xb ^ 1, false);
+    }
     PHASE_MARK(1);
 
     // ---- P1b: rotation chain, one thread per frame
@@ -214,9 +268,12 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         const int l = tid - f * NL;
         const bool live = f < nf;
         const float px = S.p[f][l][0], py = S.p[f][l][1], pz = S.p[f][l][2];
-        const float wx = S.x[f][0] + px, wy = S.x[f][1] + py, wz = S.x[f][2] + pz;
+        const float wx = Sx[f][0] + px, wy = Sx[f][1] + py, wz = Sx[f][2] + pz;
         const size_t base = ((size_t)(f0 + f) * C) * NL + l;
-        if (staged) mbar_wait(&S.mbar[1], 0);
+        if (staged) {
+            mbar_wait(&S.mbar[1], ph_m & 1);
+            ++ph_m;
+        }
         // Two cameras (2k, 2k+1) per iteration in the two halves of packed fp32 registers (FFMA2 path);
         // accumulators are pairs too and are folded after the loop.
         const f2 WX = bc(wx), WY = bc(wy), WZ = bc(wz);
@@ -229,11 +286,11 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             float2 m0 = make_float2(0.f, 0.f), m1 = make_float2(0.f, 0.f);
             float w0 = 0.f, w1 = 0.f;
             if (staged) {
-                m0 = S.in.meas[(f * C + c) * NL + l];
-                w0 = S.in.w[(f * C + c) * NL + l];
+                m0 = in_meas[f * ms2 + c * NL + l];
+                w0 = in_w[f * ws + c * NL + l];
                 if (has2) {
-                    m1 = S.in.meas[(f * C + c + 1) * NL + l];
-                    w1 = S.in.w[(f * C + c + 1) * NL + l];
+                    m1 = in_meas[f * ms2 + (c + 1) * NL + l];
+                    w1 = in_w[f * ws + (c + 1) * NL + l];
                 }
             } else if (live) {
                 m0 = __ldg(reinterpret_cast<const float2*>(meas) + base + (size_t)c * NL);
@@ -314,7 +371,18 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
         const float b0 = lo(B0) + hi(B0), b1 = lo(B1) + hi(B1), b2 = lo(B2) + hi(B2);
         const float cst = lo(CST) + hi(CST);
         S.costp[f][l] = cst;
-        if (staged) __syncthreads();   // the input tiles alias Il: every thread is done reading them
+        if (PERSIST) {
+            // Il aliases the staged outputs of the previous tile: its bulk stores must have read them; then the
+            // input buffer is free and is refilled for the next tile while P2b..P5 of this one run
+            if (tid == 0 && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            if (bulk_in && tid == 0) {
+                const int tn = tile + gridDim.x;
+                if (tn < n_tiles && (tn + 1) * FT <= n_frames) issue_mw(tn);
+            }
+        } else if (staged) {
+            __syncthreads();           // the input tiles alias Il: every thread is done reading them
+        }
         PHASE_MARK(3);
         // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]
         float o[NSP + 1];
@@ -367,7 +435,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             const f2 s2 = add2(add2(add2(v[4], v[8]), v[11]), add2(add2(s3, s6), s8));
             const f2 s1 = add2(v[3], s2);
             const f2 s0 = add2(add2(add2(v[0], v[1]), v[2]), s1);
-            float* d = &S.Ij[f][0][2 * kp];
+            float* d = &S.Ij[f][2 * kp];
             constexpr int IS = NSP + 1;
 #define ST2(j, v) *reinterpret_cast<float2*>(d + (j) * IS) = make_float2(lo(v), hi(v))
             ST2(0, s0); ST2(1, s1); ST2(2, s2); ST2(3, s3); ST2(4, s4); ST2(5, s5); ST2(6, s6);
@@ -390,7 +458,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
 #pragma unroll
             for (int l = 0; l < NL; ++l) c += S.costp[f][l];
             S.o.cost[f] = c;
-            const float* I0 = S.Ij[f][0];
+            const float* I0 = S.Ij[f];
             g[0] = I0[24]; g[1] = I0[25]; g[2] = I0[26];
             if (WANT_H) {
                 H[upper_index(0, 0)] = I0[15]; H[upper_index(0, 1)] = I0[16]; H[upper_index(0, 2)] = I0[17];
@@ -398,7 +466,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             }
             continue;
         }
-        const float4* I4 = reinterpret_cast<const float4*>(S.Ij[f][c_tab.joint[be]]);
+        const float4* I4 = reinterpret_cast<const float4*>(&S.Ij[f][c_tab.joint[be] * (NSP + 1)]);
         const float4 i0 = I4[0], i1 = I4[1], i2 = I4[2], i3 = I4[3], i4 = I4[4], i5 = I4[5], i6 = I4[6];
         const float I[28] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y,
                              i3.z, i3.w, i4.x, i4.y, i4.z, i4.w, i5.x, i5.y, i5.z, i5.w, i6.x, i6.y, i6.z, i6.w};
@@ -467,34 +535,35 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             if (g_out) bulk_s2g(g_out + (size_t)f0 * NA, &S.o.g[0][0], FT * NA * 4);
             if (WANT_H && H_out) bulk_s2g(H_out + (size_t)f0 * NU, &S.o.H[0][0], FT * NU * 4);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            out_pending = true;        // waited for before the next tile overwrites the stage (or at exit)
         }
-        PHASE_MARK(8);
-        return;
-    }
-    if (cost_out)
-        for (int f = tid; f < nf; f += NT) cost_out[f0 + f] = S.o.cost[f];
-    if (g_out) {
-        float* dst = g_out + (size_t)f0 * NA;
-        const float* src = &S.o.g[0][0];
-        if (nf == FT) {
-            for (int i = tid; i < FT * NA / 4; i += NT)
-                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-        } else {
-            for (int i = tid; i < nf * NA; i += NT) dst[i] = src[i];
+    } else {
+        if (cost_out)
+            for (int f = tid; f < nf; f += NT) cost_out[f0 + f] = S.o.cost[f];
+        if (g_out) {
+            float* dst = g_out + (size_t)f0 * NA;
+            const float* src = &S.o.g[0][0];
+            if (nf == FT) {
+                for (int i = tid; i < FT * NA / 4; i += NT)
+                    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+            } else {
+                for (int i = tid; i < nf * NA; i += NT) dst[i] = src[i];
+            }
         }
-    }
-    if (WANT_H && H_out) {
-        float* dst = H_out + (size_t)f0 * NU;
-        const float* src = &S.o.H[0][0];
-        if (nf == FT) {
-            for (int i = tid; i < FT * NU / 4; i += NT)
-                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-        } else {
-            for (int i = tid; i < nf * NU; i += NT) dst[i] = src[i];
+        if (WANT_H && H_out) {
+            float* dst = H_out + (size_t)f0 * NU;
+            const float* src = &S.o.H[0][0];
+            if (nf == FT) {
+                for (int i = tid; i < FT * NU / 4; i += NT)
+                    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+            } else {
+                for (int i = tid; i < nf * NU; i += NT) dst[i] = src[i];
+            }
         }
     }
     PHASE_MARK(8);
+    }   // tiles
+    if (tid == 0 && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 #ifdef ACINO_PHASE_TIMING
@@ -559,7 +628,7 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 // ------------------------------------------------------------------------------------------
 static int g_variant = -1;   // ACINO_FTE_VARIANT: experiment selector (frames/CTA, min CTAs/SM, unrolled camera pairs)
 
-template <int FT, int MINB, int NPAIR>
+template <int FT, int MINB, int NPAIR, bool PERSIST>
 static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const float* x, const float* meas,
                                      const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
@@ -567,20 +636,30 @@ static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const fl
     // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
     const int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
                          (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
-    const int grid = (n_frames + FT - 1) / FT;
-    const size_t smem = sizeof(Smem<FT>);
+    const int n_tiles = (n_frames + FT - 1) / FT;
+    int grid = n_tiles;
+    if (PERSIST) {       // one wave of resident CTAs, each walking tiles blockIdx.x, blockIdx.x + grid, ...
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        }
+        grid = n_tiles < n_sm * MINB ? n_tiles : n_sm * MINB;
+    }
+    const size_t smem = sizeof(Smem<FT, PERSIST>);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<FT, true, MINB, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fte_eval_kernel<FT, false, MINB, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (H)
-        fte_eval_kernel<FT, true, MINB, NPAIR><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     else
-        fte_eval_kernel<FT, false, MINB, NPAIR><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
+        fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     return cudaGetLastError();
 }
 
@@ -595,13 +674,14 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
     // A/B variants kept for scripts/bench_variants.sh (B200, 256 000 frames, profiles/r01_fte_eval.md):
     //   0 default 6.45e8 frames/s | 1: 5 CTAs/SM, 72 regs 6.2e8 | 4: 16 frames/CTA 4.8e8 | 5/6: 4 frames/CTA 5.7e8 / 5.4e8
     //   8: camera-pair loop unrolled 6.4e8 | 9: unrolled, 3 CTAs/SM, 128 regs 5.6e8
-    if (g_variant == 1) return launch_fte_eval_v<8, 5, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 4) return launch_fte_eval_v<16, 2, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 5) return launch_fte_eval_v<4, 9, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 6) return launch_fte_eval_v<4, 10, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    return launch_fte_eval_v<8, 4, 0>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 1) return launch_fte_eval_v<8, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 4) return launch_fte_eval_v<16, 2, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 5) return launch_fte_eval_v<4, 9, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 6) return launch_fte_eval_v<4, 10, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 10) return launch_fte_eval_v<8, 4, 0, true>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,

@@ -176,8 +176,62 @@ def fte(DATA_DIR, start_frame, end_frame, dlc_thresh, fps=None, device=0, verbos
     t0 = time()
     out = fte_solve(df, k_arr, d_arr, r_arr, t_arr, start_frame, end_frame, dlc_thresh, fps, device=device, verbose=verbose)
     print("\nOptimization took {0:.2f} seconds\n".format(time() - t0))
+    save_fte(out, out_dir, scene_fpath, start_frame, dlc_thresh, device=device)
+    return out
+
+
+# ---- output writers -----------------------------------------------------------
+def save_3d_cheetah_as_2d(positions_3d_arr, out_dir, scene_fpath, bodyparts, project_func=None, start_frame=0,
+                          save_as_csv=True, out_fname="fte", device=0):
+    """Reprojection of an optimised trajectory into every camera of the scene, written as one
+    DeepLabCut-style table per camera - the call at all_optimizations.py:560
+    (``app.save_3d_cheetah_as_2d(positions, OUT_DIR, scene_fpath, markers, project_points_fisheye,
+    start_frame)``; the callee lives in the reference's missing ``lib`` package, so the file format is the
+    DLC layout its own loader reads back, utils.py:105-120: columns (scorer, bodyparts, x|y|likelihood),
+    index = frame number).  All N x L points of a camera are projected by ONE kernel launch.
+    Returns the list of per-camera DataFrames; files ``cam{i+1}_{out_fname}.h5`` (and ``.csv``)."""
+    import os
+
+    import pandas as pd
+
+    from . import calib, utils
+
+    k_arr, d_arr, r_arr, t_arr, _ = utils.load_scene(scene_fpath)
+    P = np.asarray(positions_3d_arr, dtype=np.float64)
+    N, L = P.shape[0], P.shape[1]
+    assert L == len(bodyparts)
+    project = calib.project_points_fisheye if project_func is None else project_func
+    cols = pd.MultiIndex.from_product([["acinoset_b200"], list(bodyparts), ["x", "y", "likelihood"]],
+                                      names=["scorer", "bodyparts", "coords"])
+    index = np.arange(start_frame, start_frame + N)
+    os.makedirs(out_dir, exist_ok=True)
+    dfs = []
+    for i in range(len(k_arr)):
+        uv = np.asarray(project(P.reshape(-1, 3), k_arr[i], d_arr[i], r_arr[i], t_arr[i])).reshape(N, L, 2)
+        data = np.concatenate([uv, np.ones((N, L, 1))], axis=2).reshape(N, L * 3)
+        df = pd.DataFrame(data, columns=cols, index=index)
+        fpath = os.path.join(out_dir, f"cam{i + 1}_{out_fname}")
+        try:
+            df.to_hdf(fpath + ".h5", key="df_with_missing", format="table", mode="w")
+        except ImportError:          # pytables missing: the csv twin carries the same table
+            save_as_csv = True
+        if save_as_csv:
+            df.to_csv(fpath + ".csv")
+        dfs.append(df)
+    return dfs
+
+
+def save_fte(out, out_dir, scene_fpath, start_frame, dlc_thresh, markers=None, device=0):
+    """``app.save_fte`` at all_optimizations.py:559: the result pickle {positions, x, dx, ddx, start_frame}
+    (:540-556) plus the 2-D reprojection files."""
+    import os
+    import pickle
+
+    os.makedirs(out_dir, exist_ok=True)
     out_fpath = os.path.join(out_dir, "fte.pickle")
     with open(out_fpath, "wb") as f:
         pickle.dump({k: out[k] for k in ("positions", "x", "dx", "ddx", "start_frame")}, f)
     print(f"Saved {out_fpath}")
-    return out
+    save_3d_cheetah_as_2d(out["positions"], out_dir, scene_fpath, MARKERS if markers is None else markers, None,
+                          start_frame, device=device)
+    return out_fpath

@@ -59,3 +59,16 @@ def test_fte_reference_signature_writes_pickle(tmp_path, dummy_cams):
     assert set(saved) == {"positions", "x", "dx", "ddx", "start_frame"}
     assert saved["positions"].shape == (60, 20, 3) and saved["x"].shape == (60, 25) and saved["start_frame"] == 0
     assert np.array_equal(saved["x"], out["x"])
+    # 2-D reprojection files (all_optimizations.py:560): one DLC-style table per camera, read back by the loader
+    from oracle import fisheye
+
+    files = sorted((data / "fte").glob("cam*_fte.csv"))
+    assert len(files) == 6
+    df2 = utils.load_dlc_points_as_df([str(f) for f in files], verbose=False)
+    assert len(df2) == 60 * 6 * 20
+    dense, lik = utils.dlc_df_to_dense(df2, 6, fte.MARKERS, 0, 60)
+    for c in range(6):
+        uv = fisheye.project(saved["positions"], K[c], D[c], R[c], t[c])
+        ok = np.abs(uv) < 1e4                       # behind-camera points project "validly" far outside the image
+        assert np.abs(dense[:, c] - uv)[ok].max() < 1e-6 * np.abs(uv[ok]).max() + 1e-6
+    assert np.all(lik == 1.0)
