@@ -538,27 +538,18 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
             out_pending = true;        // waited for before the next tile overwrites the stage (or at exit)
         }
     } else {
+        // partial tile or outputs that are not 16-byte aligned: scalar copies
         if (cost_out)
             for (int f = tid; f < nf; f += NT) cost_out[f0 + f] = S.o.cost[f];
         if (g_out) {
             float* dst = g_out + (size_t)f0 * NA;
             const float* src = &S.o.g[0][0];
-            if (nf == FT) {
-                for (int i = tid; i < FT * NA / 4; i += NT)
-                    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-            } else {
-                for (int i = tid; i < nf * NA; i += NT) dst[i] = src[i];
-            }
+            for (int i = tid; i < nf * NA; i += NT) dst[i] = src[i];
         }
         if (WANT_H && H_out) {
             float* dst = H_out + (size_t)f0 * NU;
             const float* src = &S.o.H[0][0];
-            if (nf == FT) {
-                for (int i = tid; i < FT * NU / 4; i += NT)
-                    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-            } else {
-                for (int i = tid; i < nf * NU; i += NT) dst[i] = src[i];
-            }
+            for (int i = tid; i < nf * NU; i += NT) dst[i] = src[i];
         }
     }
     PHASE_MARK(8);

@@ -68,7 +68,8 @@ int acino_set_redescending(acino_handle* h, double a, double b, double c);
  *   cost [N]            sum_{c,l,d} rho(w * r)
  *   g    [N][25]        d cost / d x_n
  *   H    [N][325]       packed upper triangle of sum psi(w r) w^2 J^T J  (psi = max(rho'/e, 1-sigma_a))
- * Any of cost/g/H may be NULL (not written). */
+ * Any of cost/g/H may be NULL (not written).  meas must be 8-byte aligned (ACINO_ERR_ARG otherwise); with every
+ * pointer 16-byte aligned the tiles move by bulk async copies (TMA), otherwise by plain loads / stores - same bits. */
 int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const float* meas,
                        const float* w, float* cost, float* g, float* H, void* cuda_stream);
 int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* meas,
