@@ -1,6 +1,7 @@
 // C ABI of libacino_b200.so (see include/acino_b200.h).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -31,7 +32,8 @@ cudaError_t launch_lm_step(int n_frames, long long frame0, long long ng, const d
                            const double* gtot, const float* H, const double* sw, const double* lo, const double* hi,
                            double* xt_ext, float* xt32, double* pred, double* step, cudaStream_t s);
 cudaError_t launch_lm_reduce(int n, const float* a0, const double* a1, const double* a2, const double* a3,
-                             const double* m, double* out, cudaStream_t s);
+                             const double* m, double* out, double* ws, cudaStream_t s);
+size_t lm_reduce_ws_bytes();
 cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const double* Lc, double* P, double* Q,
                               double* rhs, int* info, cudaStream_t s);
 cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
@@ -69,6 +71,7 @@ struct acino_handle {
     // host-API staging (device)
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    double* red_ws = nullptr;          // partials + ticket counter of lm_reduce (zero-initialised once)
     cudaStream_t stream = nullptr;
     // host-API pipeline: H2D / compute / D2H on three streams, chunked, chained with events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -157,6 +160,7 @@ int acino_destroy(acino_handle* h) {
     if (!h) return ACINO_OK;
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
+    if (h->red_ws) cudaFree(h->red_ws);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->pipe_ready) {
         cudaStreamDestroy(h->s_h2d);
@@ -261,7 +265,13 @@ int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* m
     float* dg = dc + ac;
     float* dH = dg + ag;
     // chunk size: a multiple of 64 frames (keeps every chunk's tiles 16-byte aligned), <= kMaxChunks chunks
-    size_t chunk = 16384;
+    static size_t chunk0 = 0;
+    if (!chunk0) {
+        const char* e = getenv("ACINO_E2E_CHUNK");      // A/B knob (frames per chunk, multiple of 64)
+        chunk0 = e ? (size_t)atol(e) : 16384;
+        if (chunk0 < 64 || chunk0 % 64) chunk0 = 16384;
+    }
+    size_t chunk = chunk0;
     while ((N + chunk - 1) / chunk > (size_t)acino_handle::kMaxChunks) chunk *= 2;
     const int n_chunks = (int)((N + chunk - 1) / chunk);
     for (int i = 0; i < n_chunks; ++i) {
@@ -533,7 +543,13 @@ int acino_lm_reduce_dev(acino_handle* h, int n, const float* a0, const double* a
                         const double* m, double* out, void* cuda_stream) {
     DEV_ENTER("acino_lm_reduce_dev");
     if (n < 0 || !out) return fail(h, ACINO_ERR_ARG, "acino_lm_reduce_dev: bad arguments");
-    CK(launch_lm_reduce(n, a0, a1, a2, a3, m, out, s));
+    if (!h->red_ws) {
+        CK(cudaMalloc((void**)&h->red_ws, lm_reduce_ws_bytes()));
+        CK(cudaMemset(h->red_ws, 0, lm_reduce_ws_bytes()));
+        CK(cudaDeviceSynchronize());
+    }
+    // the handle is not thread-safe and calls are stream-ordered by contract: one reduction at a time uses red_ws
+    CK(launch_lm_reduce(n, a0, a1, a2, a3, m, out, h->red_ws, s));
     h->launches += 1;
     return ACINO_OK;
 }

@@ -195,13 +195,19 @@ __global__ void lm_step_kernel(const int n_frames, const long long frame0, const
 }
 
 // fixed-order fp64 reduction of up to 4 arrays (sum) + 1 array (max): single CTA, 1024 threads.
-// out[0..3] = sums (a0 is float), out[4] = max of m.
+// out[0..3] = sums (a0 is float), out[4] = max of m.  Two stages, both in a FIXED order so the result is
+// bit-reproducible: CTA b reduces elements b*1024 + t, (b + G)*1024 + t, ... into partial[b][5]; the last CTA to
+// finish (ticket counter) adds the G partials in order b = 0..G-1.  ws: [G][5] doubles followed by the counter.
+constexpr int RED_MAX_CTAS = 148;
 __global__ void __launch_bounds__(1024)
 lm_reduce_kernel(const int n, const float* __restrict__ a0, const double* __restrict__ a1, const double* __restrict__ a2,
-                 const double* __restrict__ a3, const double* __restrict__ m, double* __restrict__ out) {
+                 const double* __restrict__ a3, const double* __restrict__ m, double* __restrict__ out,
+                 double* __restrict__ ws) {
     __shared__ double s[5][1024];
+    __shared__ bool last;
+    const int G = gridDim.x;
     double v0 = 0, v1 = 0, v2 = 0, v3 = 0, vm = 0;
-    for (int i = threadIdx.x; i < n; i += 1024) {
+    for (size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x; i < (size_t)n; i += (size_t)G * 1024) {
         if (a0) v0 += (double)a0[i];
         if (a1) v1 += a1[i];
         if (a2) v2 += a2[i];
@@ -218,7 +224,27 @@ lm_reduce_kernel(const int n, const float* __restrict__ a0, const double* __rest
         }
         __syncthreads();
     }
-    if (threadIdx.x < 5) out[threadIdx.x] = s[threadIdx.x][0];
+    if (G == 1) {
+        if (threadIdx.x < 5) out[threadIdx.x] = s[threadIdx.x][0];
+        return;
+    }
+    unsigned* counter = reinterpret_cast<unsigned*>(ws + RED_MAX_CTAS * 5);
+    if (threadIdx.x < 5) ws[blockIdx.x * 5 + threadIdx.x] = s[threadIdx.x][0];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(counter, 1u);
+        last = ticket == (unsigned)(G - 1);
+        if (last) *counter = 0;            // re-armed for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 5) {
+        __threadfence();
+        const volatile double* w = ws;
+        double acc = 0.0;
+        for (int b = 0; b < G; ++b) acc = threadIdx.x < 4 ? acc + w[b * 5 + threadIdx.x] : fmax(acc, w[b * 5 + 4]);
+        out[threadIdx.x] = acc;
+    }
 }
 
 cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, const double* x_ext, const float* g,
@@ -250,9 +276,14 @@ cudaError_t launch_lm_step(int n_frames, long long frame0, long long ng, const d
     return cudaGetLastError();
 }
 
+size_t lm_reduce_ws_bytes() { return (RED_MAX_CTAS * 5 + 1) * sizeof(double); }
+
 cudaError_t launch_lm_reduce(int n, const float* a0, const double* a1, const double* a2, const double* a3,
-                             const double* m, double* out, cudaStream_t s) {
-    lm_reduce_kernel<<<1, 1024, 0, s>>>(n, a0, a1, a2, a3, m, out);
+                             const double* m, double* out, double* ws, cudaStream_t s) {
+    int G = (n + 8191) / 8192;             // >= 8 elements per thread before a second CTA pays off
+    G = G < 1 ? 1 : (G > RED_MAX_CTAS ? RED_MAX_CTAS : G);
+    if (!ws) G = 1;
+    lm_reduce_kernel<<<G, 1024, 0, s>>>(n, a0, a1, a2, a3, m, out, ws);
     return cudaGetLastError();
 }
 

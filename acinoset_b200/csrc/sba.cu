@@ -81,48 +81,89 @@ __global__ void sba_cams_fixed_kernel(const int C, const double* __restrict__ R,
     cams[c] = cam;
 }
 
-// thread per observation: residual (2), Jc (2x6: d/d rvec, d/d t), Jp (2x3), Cauchy weights (2), cost
+// thread per observation: residual (2), Jc (2x6: d/d rvec, d/d t), Jp (2x3), Cauchy weights (2), cost.
+// A thread's outputs are 23 doubles in five arrays at strides of 16 / 96 / 48 bytes: written directly, every store
+// instruction of a warp touches 32 different sectors.  Full CTAs therefore stage their outputs in shared memory in
+// the global layout (each array's slice of 128 observations is contiguous) and one thread issues five bulk async
+// stores (TMA); the kernel's HBM traffic is then the algorithmic 176 B per observation.
+constexpr int SBA_EVAL_THREADS = 128;
+struct __align__(16) SbaEvalStage {
+    double Jc[SBA_EVAL_THREADS * 12];
+    double Jp[SBA_EVAL_THREADS * 6];
+    double res[SBA_EVAL_THREADS * 2];
+    double wgt[SBA_EVAL_THREADS * 2];
+    double cost[SBA_EVAL_THREADS];
+};
+
 template <bool WANT_J>
-__global__ void sba_eval_kernel(const int n_obs, const SbaCam* __restrict__ cams, const double* __restrict__ pts,
-                                const float* __restrict__ uv, const int* __restrict__ cam_idx,
-                                const int* __restrict__ pt_idx, const double f_scale, double* __restrict__ res,
-                                double* __restrict__ Jc, double* __restrict__ Jp, double* __restrict__ wgt,
-                                double* __restrict__ cost) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_obs) return;
-    const SbaCam& cam = cams[cam_idx[i]];
-    const double* X = pts + 3 * (size_t)pt_idx[i];
-    const double x = X[0], y = X[1], z = X[2];
-    const double xc = cam.R[0] * x + cam.R[1] * y + cam.R[2] * z + cam.t[0];
-    const double yc = cam.R[3] * x + cam.R[4] * y + cam.R[5] * z + cam.t[1];
-    const double zc = cam.R[6] * x + cam.R[7] * y + cam.R[8] * z + cam.t[2];
-    ProjOut<double> pr;
-    fisheye_cam<double, WANT_J>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
-    const double ru = pr.u + cam.cx - (double)uv[2 * i], rv = pr.v + cam.cy - (double)uv[2 * i + 1];
-    res[2 * i] = ru;
-    res[2 * i + 1] = rv;
-    const double ic = 1.0 / f_scale;
-    const double zu = ru * ic * ru * ic, zv = rv * ic * rv * ic;
-    if (cost) cost[i] = 0.5 * f_scale * f_scale * (log1p(zu) + log1p(zv));
-    if (WANT_J) {
-        wgt[2 * i] = 1.0 / (1.0 + zu);
-        wgt[2 * i + 1] = 1.0 / (1.0 + zv);
-        const double* J[2] = {pr.ju, pr.jv};
-        if (Jc) {
-            // d Xc / d rvec_k = (dR/dr_k) X
-            double M[3][3];
-            for (int a = 0; a < 3; ++a)
-                for (int k = 0; k < 3; ++k)
-                    M[a][k] = cam.dR[(a * 3 + 0) * 3 + k] * x + cam.dR[(a * 3 + 1) * 3 + k] * y + cam.dR[(a * 3 + 2) * 3 + k] * z;
-            for (int d = 0; d < 2; ++d) {
-                for (int k = 0; k < 3; ++k)
-                    Jc[(size_t)i * 12 + d * 6 + k] = J[d][0] * M[0][k] + J[d][1] * M[1][k] + J[d][2] * M[2][k];
-                for (int k = 0; k < 3; ++k) Jc[(size_t)i * 12 + d * 6 + 3 + k] = J[d][k];
+__global__ void __launch_bounds__(SBA_EVAL_THREADS)
+sba_eval_kernel(const int n_obs, const int bulk_ok, const SbaCam* __restrict__ cams, const double* __restrict__ pts,
+                const float* __restrict__ uv, const int* __restrict__ cam_idx,
+                const int* __restrict__ pt_idx, const double f_scale, double* __restrict__ res,
+                double* __restrict__ Jc, double* __restrict__ Jp, double* __restrict__ wgt,
+                double* __restrict__ cost) {
+    __shared__ SbaEvalStage S;
+    const int i0 = blockIdx.x * SBA_EVAL_THREADS;
+    const int tid = threadIdx.x;
+    const int i = i0 + tid;
+    const bool staged = bulk_ok && i0 + SBA_EVAL_THREADS <= n_obs;      // uniform per CTA
+    if (i < n_obs) {
+        const SbaCam& cam = cams[cam_idx[i]];
+        const double* X = pts + 3 * (size_t)pt_idx[i];
+        const double x = X[0], y = X[1], z = X[2];
+        const double xc = cam.R[0] * x + cam.R[1] * y + cam.R[2] * z + cam.t[0];
+        const double yc = cam.R[3] * x + cam.R[4] * y + cam.R[5] * z + cam.t[1];
+        const double zc = cam.R[6] * x + cam.R[7] * y + cam.R[8] * z + cam.t[2];
+        ProjOut<double> pr;
+        fisheye_cam<double, WANT_J>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
+        const double ru = pr.u + cam.cx - (double)uv[2 * i], rv = pr.v + cam.cy - (double)uv[2 * i + 1];
+        double* o_res = staged ? S.res + 2 * tid : res + 2 * (size_t)i;
+        o_res[0] = ru;
+        o_res[1] = rv;
+        const double ic = 1.0 / f_scale;
+        const double zu = ru * ic * ru * ic, zv = rv * ic * rv * ic;
+        if (cost) (staged ? S.cost + tid : cost + i)[0] = 0.5 * f_scale * f_scale * (log1p(zu) + log1p(zv));
+        if (WANT_J) {
+            double* o_w = staged ? S.wgt + 2 * tid : wgt + 2 * (size_t)i;
+            o_w[0] = 1.0 / (1.0 + zu);
+            o_w[1] = 1.0 / (1.0 + zv);
+            const double* J[2] = {pr.ju, pr.jv};
+            if (Jc) {
+                double* o_jc = staged ? S.Jc + 12 * tid : Jc + 12 * (size_t)i;
+                // d Xc / d rvec_k = (dR/dr_k) X
+                double M[3][3];
+                for (int a = 0; a < 3; ++a)
+                    for (int k = 0; k < 3; ++k)
+                        M[a][k] = cam.dR[(a * 3 + 0) * 3 + k] * x + cam.dR[(a * 3 + 1) * 3 + k] * y + cam.dR[(a * 3 + 2) * 3 + k] * z;
+                for (int d = 0; d < 2; ++d) {
+                    for (int k = 0; k < 3; ++k) o_jc[d * 6 + k] = J[d][0] * M[0][k] + J[d][1] * M[1][k] + J[d][2] * M[2][k];
+                    for (int k = 0; k < 3; ++k) o_jc[d * 6 + 3 + k] = J[d][k];
+                }
             }
+            double* o_jp = staged ? S.Jp + 6 * tid : Jp + 6 * (size_t)i;
+            for (int d = 0; d < 2; ++d)
+                for (int k = 0; k < 3; ++k) o_jp[d * 3 + k] = J[d][0] * cam.R[k] + J[d][1] * cam.R[3 + k] + J[d][2] * cam.R[6 + k];
         }
-        for (int d = 0; d < 2; ++d)
-            for (int k = 0; k < 3; ++k)
-                Jp[(size_t)i * 6 + d * 3 + k] = J[d][0] * cam.R[k] + J[d][1] * cam.R[3 + k] + J[d][2] * cam.R[6 + k];
+    }
+    if (staged) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            auto st = [](void* dst, const void* src, unsigned bytes) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                             "r"((unsigned)__cvta_generic_to_shared(src)), "r"(bytes)
+                             : "memory");
+            };
+            st(res + 2 * (size_t)i0, S.res, SBA_EVAL_THREADS * 16);
+            if (cost) st(cost + i0, S.cost, SBA_EVAL_THREADS * 8);
+            if (WANT_J) {
+                st(wgt + 2 * (size_t)i0, S.wgt, SBA_EVAL_THREADS * 16);
+                if (Jc) st(Jc + 12 * (size_t)i0, S.Jc, SBA_EVAL_THREADS * 96);
+                st(Jp + 6 * (size_t)i0, S.Jp, SBA_EVAL_THREADS * 48);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
     }
 }
 
@@ -394,18 +435,21 @@ cudaError_t launch_sba_eval(int n_obs, const void* cams, const double* pts, cons
                             const int* pt_idx, double f_scale, double* res, double* Jc, double* Jp, double* wgt,
                             double* cost, cudaStream_t s) {
     if (n_obs <= 0) return cudaSuccess;
+    const int bulk_ok = ((((uintptr_t)res | (uintptr_t)Jc | (uintptr_t)Jp | (uintptr_t)wgt | (uintptr_t)cost) & 15u) == 0) ? 1 : 0;
     if (Jp)
-        sba_eval_kernel<true><<<nb(n_obs, 128), 128, 0, s>>>(n_obs, (const SbaCam*)cams, pts, uv, cam_idx, pt_idx, f_scale,
-                                                             res, Jc, Jp, wgt, cost);
+        sba_eval_kernel<true><<<nb(n_obs, SBA_EVAL_THREADS), SBA_EVAL_THREADS, 0, s>>>(n_obs, bulk_ok, (const SbaCam*)cams, pts, uv, cam_idx,
+                                                                                     pt_idx, f_scale, res, Jc, Jp, wgt, cost);
     else
-        sba_eval_kernel<false><<<nb(n_obs, 128), 128, 0, s>>>(n_obs, (const SbaCam*)cams, pts, uv, cam_idx, pt_idx,
-                                                              f_scale, res, Jc, Jp, wgt, cost);
+        sba_eval_kernel<false><<<nb(n_obs, SBA_EVAL_THREADS), SBA_EVAL_THREADS, 0, s>>>(n_obs, bulk_ok, (const SbaCam*)cams, pts, uv, cam_idx,
+                                                                                      pt_idx, f_scale, res, Jc, Jp, wgt, cost);
     return cudaGetLastError();
 }
 
 int sba_schur_grid(int n_pts) {
+    // one resident wave: 5 CTAs per SM by shared memory (4 warps x 11 KB of private accumulators).  The kernel is a
+    // chain of dependent global loads per point (CSR row -> observation -> camera -> blocks): it needs warps, not flops
     int g = nb(n_pts, SCHUR_WARPS * 32);
-    return g < 1 ? 1 : (g > 148 ? 148 : g);
+    return g < 1 ? 1 : (g > 148 * 5 ? 148 * 5 : g);
 }
 
 cudaError_t launch_sba_schur(int n_pts, int C, const int* pt_ptr, const int* obs, const int* cam_idx, const double* res,
