@@ -168,11 +168,13 @@ def cpu_baseline_time(x, meas, w, cams, target_s=12.0, threads=0):
     c_port.fte_eval(x[:n0], meas[:n0], w[:n0], K, D, R, t, n_threads=threads)
     rate0 = n0 / (time.perf_counter() - t0)
     n = int(min(x.shape[0], max(n0, rate0 * target_s)))
+    reps = max(1, int(round(rate0 * target_s / n)))           # the whole batch several times over when the host is fast
     t0 = time.perf_counter()
-    c_port.fte_eval(x[:n], meas[:n], w[:n], K, D, R, t, n_threads=threads)
+    for _ in range(reps):
+        c_port.fte_eval(x[:n], meas[:n], w[:n], K, D, R, t, n_threads=threads)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} frames of the same batch, fp64 C restatement (oracle/c/fte_oracle.c), "
+    return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} pass(es) over {n} frames of the same batch, fp64 C restatement (oracle/c/fte_oracle.c), "
                       f"OpenMP over frames, {dt:.1f} s; reference Pyomo+IPOPT path not runnable in this image"}
 
 
