@@ -156,12 +156,12 @@ __device__ int g_phase_count;
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
-template <int FT, bool WANT_H, int MINB, int NPAIR, bool PERSIST>
-__global__ void __launch_bounds__(FT * NL, MINB)
-fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
-                const float* __restrict__ xg, const float* __restrict__ meas,
-                const float* __restrict__ wts, float* __restrict__ cost_out,
-                float* __restrict__ g_out, float* __restrict__ H_out) {
+template <int FT, bool WANT_H, int NPAIR, bool PERSIST>
+__device__ __forceinline__ void
+fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
+              const float* __restrict__ xg, const float* __restrict__ meas,
+              const float* __restrict__ wts, float* __restrict__ cost_out,
+              float* __restrict__ g_out, float* __restrict__ H_out) {
     constexpr int NT = FT * NL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<FT, PERSIST>& S = *reinterpret_cast<Smem<FT, PERSIST>*>(smem_raw);
@@ -557,6 +557,23 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
     if (tid == 0 && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// register budget by "at least MINB resident CTAs" ...
+template <int FT, bool WANT_H, int MINB, int NPAIR, bool PERSIST>
+__global__ void __launch_bounds__(FT * NL, MINB)
+fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
+                const float* __restrict__ xg, const float* __restrict__ meas, const float* __restrict__ wts,
+                float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
+    fte_eval_body<FT, WANT_H, NPAIR, PERSIST>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
+}
+// ... or by an explicit register cap (5 CTAs x 160 threads x 80 registers = 64 000 of the SM's 65 536)
+template <int FT, bool WANT_H, int MAXREG, int NPAIR, bool PERSIST>
+__global__ void __launch_bounds__(FT * NL) __maxnreg__(MAXREG)
+fte_eval_kernel_r(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
+                  const float* __restrict__ xg, const float* __restrict__ meas, const float* __restrict__ wts,
+                  float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
+    fte_eval_body<FT, WANT_H, NPAIR, PERSIST>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
+}
+
 #ifdef ACINO_PHASE_TIMING
 extern "C" void acino_debug_phase_cycles(long long* out16) { cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(long long) * 16); }
 extern "C" void acino_debug_phase_reset() { long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
@@ -619,9 +636,12 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 // ------------------------------------------------------------------------------------------
 static int g_variant = -1;   // ACINO_FTE_VARIANT: experiment selector (frames/CTA, min CTAs/SM, unrolled camera pairs)
 
-template <int FT, int MINB, int NPAIR, bool PERSIST>
-static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+using FteKernel = void (*)(const SceneF, int, int, const float*, const float*, const float*, float*, float*, float*);
+
+template <int FT, bool PERSIST>
+static cudaError_t launch_fte_eval_k(FteKernel kH, FteKernel kN, int ctas_per_sm, const SceneF& scene, int n_frames,
+                                     const float* x, const float* meas, const float* w, float* cost, float* g, float* H,
+                                     cudaStream_t stream) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
     // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
@@ -636,22 +656,39 @@ static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const fl
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         }
-        grid = n_tiles < n_sm * MINB ? n_tiles : n_sm * MINB;
+        grid = n_tiles < n_sm * ctas_per_sm ? n_tiles : n_sm * ctas_per_sm;
     }
-    const size_t smem = sizeof(Smem<FT, PERSIST>);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    static size_t smem_pad = (size_t)-1;    // ACINO_FTE_SMEM_PAD: residency experiment (extra dynamic smem per CTA)
+    if (smem_pad == (size_t)-1) {
+        const char* e = getenv("ACINO_FTE_SMEM_PAD");
+        smem_pad = e ? (size_t)atol(e) : 0;
     }
-    if (H)
-        fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
-    else
-        fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST><<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
+    const size_t smem = sizeof(Smem<FT, PERSIST>) + smem_pad;
+    static FteKernel configured[16];
+    static int n_configured = 0;
+    FteKernel k = H ? kH : kN;
+    bool done = false;
+    for (int i = 0; i < n_configured; ++i) done |= configured[i] == k;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (n_configured < 16) configured[n_configured++] = k;
+    }
+    k<<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     return cudaGetLastError();
+}
+
+template <int FT, int MINB, int NPAIR, bool PERSIST>
+static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+    return launch_fte_eval_k<FT, PERSIST>(fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST>, fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST>,
+                                          MINB, scene, n_frames, x, meas, w, cost, g, H, stream);
+}
+template <int FT, int MAXREG, int CTAS, int NPAIR, bool PERSIST>
+static cudaError_t launch_fte_eval_r(const SceneF& scene, int n_frames, const float* x, const float* meas,
+                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+    return launch_fte_eval_k<FT, PERSIST>(fte_eval_kernel_r<FT, true, MAXREG, NPAIR, PERSIST>, fte_eval_kernel_r<FT, false, MAXREG, NPAIR, PERSIST>,
+                                          CTAS, scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
@@ -672,6 +709,8 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
     if (g_variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
     if (g_variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
     if (g_variant == 10) return launch_fte_eval_v<8, 4, 0, true>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 11) return launch_fte_eval_r<8, 80, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    if (g_variant == 12) return launch_fte_eval_r<8, 88, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
     return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
