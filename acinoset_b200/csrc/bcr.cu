@@ -12,6 +12,8 @@
 //   bcr_backsub  (reverse order)   x_e = R^-T (z - P x_a - Q x_c)
 // fp64 throughout: the smoothness weights (2 q / Ts^4 ~ 1e7..1e9) against data blocks (~1e5) make
 // the system too ill-conditioned for fp32 factorisation; B200 runs fp64 FMA at half the fp32 rate.
+#include <cstdlib>
+
 #include "acino_common.cuh"
 
 namespace acino {
@@ -44,6 +46,12 @@ constexpr int FCS = 76;             // column stride (doubles): 152 words = 24 (
 constexpr int FB = 5;               // pivots per block step (divides 75)
 constexpr int FACTOR_THREADS = 512;
 constexpr size_t BCR_FACTOR_SMEM = (size_t)FCOLS * FCS * sizeof(double);
+// Two-pass variant for the large levels (more blocks than SMs): pass 1 eliminates [D | Lc_e | b] (151 columns) and
+// keeps the multipliers; pass 2 reloads the right-hand buffer with Lc_c^T and replays the elimination on those 75
+// columns - every column is independent once the multipliers are known, so pass 2 needs no CTA barrier at all.
+// 92 KB of shared memory instead of 137 KB: two CTAs per SM, which overlaps the latency chains of two blocks.
+constexpr int FCOLS_2P = 2 * SB + 1;
+constexpr size_t BCR_FACTOR2_SMEM = (size_t)FCOLS_2P * FCS * sizeof(double);
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
@@ -57,11 +65,71 @@ __device__ long long g_bcr_cycles[8];
 #define BCR_MARK(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(FACTOR_THREADS)
+// (a) of a diagonal block in registers, by ONE thread.  For k1 > 0 it first applies the pending rank-FB update of
+// block k1 - FB to the FB x FB entries itself ("look-ahead"): the factorisation of the next diagonal block - a chain
+// of 5 dependent fp64 divisions - then overlaps the trailing update (c) of the current block instead of serialising
+// with it.  Publishes 1/a_qq (sinv) and c_pq = a_pq / a_qq (scpq, FB x FB row-major).
+__device__ __forceinline__ void bcr_diag_block(double* __restrict__ sm, double* __restrict__ sinv, double* __restrict__ scpq,
+                                               int* __restrict__ info, const int e, const int k1) {
+    // every loop runs over the full 0..FB-1 range with a predicate: constant trip counts, so the 5 x 5 arrays
+    // stay in registers (triangular loop bounds made the compiler index them in local memory)
+    double A[FB][FB];
+#pragma unroll
+    for (int r = 0; r < FB; ++r)
+#pragma unroll
+        for (int p = 0; p < FB; ++p) A[r][p] = p <= r ? sm[(k1 + p) * FCS + k1 + r] : 0.0;
+    if (k1 > 0) {
+        const int k0 = k1 - FB;
+        double l[FB][FB];          // l[q][r] = a_(k1+r)(k0+q): panel column q, row k1 + r
+#pragma unroll
+        for (int q = 0; q < FB; ++q)
+#pragma unroll
+            for (int r = 0; r < FB; ++r) l[q][r] = sm[(k0 + q) * FCS + k1 + r];
+#pragma unroll
+        for (int p = 0; p < FB; ++p) {
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const double mq = -(l[q][p] * sinv[k0 + q]);
+#pragma unroll
+                for (int r = 0; r < FB; ++r)
+                    if (r >= p) A[r][p] = fma(l[q][r], mq, A[r][p]);
+            }
+        }
+    }
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < FB; ++q) {
+        const double d = A[q][q];
+        bad |= !(d > 0.0);
+        const double inv = 1.0 / d;
+        sinv[k1 + q] = inv;
+#pragma unroll
+        for (int r = 0; r < FB; ++r) {
+            if (r > q) {
+                const double cq = A[r][q] * inv;          // a_rq / a_qq
+                scpq[r * FB + q] = cq;
+#pragma unroll
+                for (int p = 0; p < FB; ++p)
+                    if (p > q && p <= r) A[r][p] = fma(-cq, A[p][q], A[r][p]);
+            }
+        }
+    }
+    if (bad) atomicExch(info, e + 1);
+#pragma unroll
+    for (int r = 0; r < FB; ++r)
+#pragma unroll
+        for (int p = 0; p < FB; ++p)
+            if (p <= r) sm[(k1 + p) * FCS + k1 + r] = A[r][p];
+}
+
+template <bool TWO_PASS>
+__global__ void __launch_bounds__(FACTOR_THREADS, TWO_PASS ? 2 : 1)
 bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__ D, const double* __restrict__ Lc,
                   double* __restrict__ P, double* __restrict__ Q, double* __restrict__ rhs, int* __restrict__ info) {
-    extern __shared__ __align__(16) double sm[];     // [FCOLS][FCS]
-    __shared__ double sinv[SB], sdi[SB], scpq[FB][FB];
+    constexpr int NCOLS = TWO_PASS ? FCOLS_2P : FCOLS;      // panel columns of the (first) pass
+    constexpr int ZCOL = NCOLS - 1;                          // the right-hand-side vector b is the last column
+    extern __shared__ __align__(16) double sm[];             // [NCOLS][FCS]
+    __shared__ double sinv[SB], sdi[SB], scpq_all[TWO_PASS ? SB / FB : 1][FB][FB];
     const int e = elim[3 * blockIdx.x], a = elim[3 * blockIdx.x + 1], c = elim[3 * blockIdx.x + 2];
     const int tid = threadIdx.x;
 #ifdef ACINO_BCR_TIMING
@@ -76,66 +144,20 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
             const int r = i / SB, cc = i - r * SB;
             cp_async8(&sm[r * FCS + cc], gD + i);                              // symmetric: (r,cc) == (cc,r)
             if (a >= 0) cp_async8(&sm[(SB + cc) * FCS + r], gA + i);           // Lc_e (r, cc)
-            if (c >= 0) cp_async8(&sm[(2 * SB + r) * FCS + cc], gC + i);       // Lc_c^T (cc, r) = Lc_c (r, cc)
+            if (!TWO_PASS && c >= 0) cp_async8(&sm[(2 * SB + r) * FCS + cc], gC + i);   // Lc_c^T (cc, r) = Lc_c (r, cc)
         }
-        if (tid < SB) sm[3 * SB * FCS + tid] = rhs[(size_t)e * SB + tid];
-        if (tid < FCOLS) sm[tid * FCS + SB] = 0.0;                             // row 75: zero padding
+        if (tid < SB) sm[ZCOL * FCS + tid] = rhs[(size_t)e * SB + tid];
+        if (tid < NCOLS) sm[tid * FCS + SB] = 0.0;                             // row 75: zero padding
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
     const int col = tid >> 1, half = tid & 1;
     const bool is_d = col < SB;
-    const bool rhs_on = (tid >= SB && tid < FCOLS) && (tid >= 3 * SB || (tid < 2 * SB ? a >= 0 : c >= 0));   // phase (b)
-    const bool active_col = col < FCOLS && (is_d || col >= 3 * SB || (col < 2 * SB ? a >= 0 : c >= 0));       // phase (c)
+    const bool rhs_on = (tid >= SB && tid < NCOLS) && (tid == ZCOL || (tid < 2 * SB ? a >= 0 : c >= 0));     // phase (b)
+    const bool active_col = col < NCOLS && (is_d || col == ZCOL || (col < 2 * SB ? a >= 0 : c >= 0));         // phase (c)
     double* cj = sm + col * FCS;
     __syncthreads();
-    // (a) of a diagonal block in registers, by ONE thread (FACTOR_THREADS - 1: its column slot is beyond the panel,
-    // so it is otherwise idle).  For k1 > 0 it first applies the pending rank-FB update of block k1 - FB to the
-    // FB x FB entries itself ("look-ahead"): the factorisation of the next diagonal block - a chain of 5 dependent
-    // fp64 divisions - then overlaps the trailing update (c) of the current block instead of serialising with it.
-    auto diag_block = [&](const int k1) {
-        double A[FB][FB];
-#pragma unroll
-        for (int r = 0; r < FB; ++r)
-#pragma unroll
-            for (int p = 0; p <= r; ++p) A[r][p] = sm[(k1 + p) * FCS + k1 + r];
-        if (k1 > 0) {
-            const int k0 = k1 - FB;
-            double l[FB][FB];          // l[q][r] = a_(k1+r)(k0+q): panel column q, row k1 + r
-#pragma unroll
-            for (int q = 0; q < FB; ++q)
-#pragma unroll
-                for (int r = 0; r < FB; ++r) l[q][r] = sm[(k0 + q) * FCS + k1 + r];
-#pragma unroll
-            for (int p = 0; p < FB; ++p) {
-#pragma unroll
-                for (int q = 0; q < FB; ++q) {
-                    const double mq = -(l[q][p] * sinv[k0 + q]);
-#pragma unroll
-                    for (int r = p; r < FB; ++r) A[r][p] = fma(l[q][r], mq, A[r][p]);
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < FB; ++q) {
-            const double d = A[q][q];
-            if (!(d > 0.0)) atomicExch(info, e + 1);
-            const double inv = 1.0 / d;
-            sinv[k1 + q] = inv;
-#pragma unroll
-            for (int r = q + 1; r < FB; ++r) {
-                const double cq = A[r][q] * inv;          // a_rq / a_qq
-                scpq[r][q] = cq;
-#pragma unroll
-                for (int p = q + 1; p <= r; ++p) A[r][p] = fma(-cq, A[p][q], A[r][p]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < FB; ++r)
-#pragma unroll
-            for (int p = 0; p <= r; ++p) sm[(k1 + p) * FCS + k1 + r] = A[r][p];
-    };
-    BCR_MARK(0);
-    if (tid == FACTOR_THREADS - 1) diag_block(0);
+    // (a) by thread FACTOR_THREADS - 1 (its column slot is beyond the panel, so it is otherwise idle)
+    if (tid == FACTOR_THREADS - 1) bcr_diag_block(sm, sinv, &scpq_all[0][0][0], info, e, 0);
     for (int k0 = 0; k0 < SB; k0 += FB) {
         __syncthreads();
         BCR_MARK(k0 == 0 ? 1 : 3);
@@ -150,7 +172,7 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
 #pragma unroll
             for (int p = 1; p < FB; ++p) {
 #pragma unroll
-                for (int q = 0; q < p; ++q) v[p] = fma(-scpq[p][q], v[q], v[p]);
+                for (int q = 0; q < p; ++q) v[p] = fma(-scpq_all[TWO_PASS ? k0 / FB : 0][p][q], v[q], v[p]);
                 base[p * stride] = v[p];
             }
         }
@@ -158,7 +180,7 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
         BCR_MARK(2);
         // ---- (c) rank-FB update of the trailing columns; meanwhile (a) of the next diagonal block
         const int k1 = k0 + FB;
-        if (tid == FACTOR_THREADS - 1 && k1 < SB) diag_block(k1);
+        if (tid == FACTOR_THREADS - 1 && k1 < SB) bcr_diag_block(sm, sinv, &scpq_all[TWO_PASS ? k1 / FB : 0][0][0], info, e, k1);
         if (!active_col || col < k1) continue;
         double m[FB];
 #pragma unroll
@@ -208,15 +230,80 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
     BCR_MARK(3);
     if (tid < SB) sdi[tid] = sqrt(fmax(sinv[tid], 0.0));
     __syncthreads();
-    // ---- write-out: factor in place of D_e, P, Q, z
+    // ---- write-out: factor in place of D_e, P, z (and Q in the one-pass kernel)
     for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
         const int r = i / SB, cc = i - r * SB;
         D[(size_t)e * SB2 + i] = r > cc ? sm[cc * FCS + r] * sinv[cc] : (r == cc ? sdi[r] : 0.0);
         if (a >= 0) P[(size_t)e * SB2 + i] = sm[(SB + cc) * FCS + r] * sdi[r];
-        if (c >= 0) Q[(size_t)e * SB2 + i] = sm[(2 * SB + cc) * FCS + r] * sdi[r];
+        if (!TWO_PASS && c >= 0) Q[(size_t)e * SB2 + i] = sm[(2 * SB + cc) * FCS + r] * sdi[r];
     }
-    if (tid < SB) rhs[(size_t)e * SB + tid] = sm[3 * SB * FCS + tid] * sdi[tid];
+    if (tid < SB) rhs[(size_t)e * SB + tid] = sm[ZCOL * FCS + tid] * sdi[tid];
     BCR_MARK(4);
+    if (!TWO_PASS || c < 0) return;
+
+    // ---- pass 2: Q = R^-1 Lc_c^T.  The right-hand buffer is reloaded with Lc_c^T; every column replays the
+    //      elimination on its own (multipliers c_pq, 1/a_pp and the final panel columns are all in shared
+    //      memory): two threads per column, __syncwarp only
+    __syncthreads();                                   // the write-out above has read the buffer
+    double* chunk = sm + SB * FCS;
+    {
+        const double* gC = Lc + (size_t)c * SB2;
+        for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
+            const int r = i / SB, cc = i - r * SB;
+            cp_async8(&chunk[r * FCS + cc], gC + i);                           // Lc_c^T (cc, r) = Lc_c (r, cc)
+        }
+        if (tid < SB) chunk[tid * FCS + SB] = 0.0;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    if (col < SB) {
+        const unsigned mask = __activemask();          // whole warps except the last (150 threads)
+        double* cq = chunk + col * FCS;
+        for (int k0 = 0; k0 < SB; k0 += FB) {
+            double u[FB], m[FB];
+#pragma unroll
+            for (int p = 0; p < FB; ++p) u[p] = cq[k0 + p];
+#pragma unroll
+            for (int p = 1; p < FB; ++p)
+#pragma unroll
+                for (int q = 0; q < p; ++q) u[p] = fma(-scpq_all[TWO_PASS ? k0 / FB : 0][p][q], u[q], u[p]);
+            __syncwarp(mask);                          // both threads of the column have read the pivot rows
+            if (half == 0) {
+#pragma unroll
+                for (int p = 1; p < FB; ++p) cq[k0 + p] = u[p];
+            }
+#pragma unroll
+            for (int p = 0; p < FB; ++p) m[p] = -(u[p] * sinv[k0 + p]);
+            const double* pk = sm + k0 * FCS;
+            int i = k0 + FB;
+            if (i & 1) {
+                if (half == 0 && i < SB) {
+                    double v = cq[i];
+#pragma unroll
+                    for (int p = 0; p < FB; ++p) v = fma(pk[p * FCS + i], m[p], v);
+                    cq[i] = v;
+                }
+                ++i;
+            }
+            i += 2 * half;
+            for (; i < SB; i += 4) {
+                double2 q0 = *reinterpret_cast<double2*>(cq + i);
+#pragma unroll
+                for (int p = 0; p < FB; ++p) {
+                    const double2 l0 = *reinterpret_cast<const double2*>(pk + p * FCS + i);
+                    q0.x = fma(l0.x, m[p], q0.x);
+                    q0.y = fma(l0.y, m[p], q0.y);
+                }
+                *reinterpret_cast<double2*>(cq + i) = q0;
+            }
+            __syncwarp(mask);                          // the next step's pivot rows may belong to the other thread
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
+        const int r = i / SB, cc = i - r * SB;
+        Q[(size_t)e * SB2 + i] = chunk[cc * FCS + r] * sdi[r];
+    }
 }
 
 #ifdef ACINO_BCR_TIMING
@@ -443,14 +530,22 @@ cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const doub
                               double* rhs, int* info, cudaStream_t s) {
     if (n_elim <= 0) return cudaSuccess;
     static bool set = false;
+    static int two_pass_from = 149;      // ACINO_BCR_TWO_PASS_FROM: levels with at least this many blocks use the two-pass kernel
     if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(bcr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(bcr_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(bcr_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR2_SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE_SMEM);
         if (e != cudaSuccess) return e;
+        const char* env = getenv("ACINO_BCR_TWO_PASS_FROM");
+        if (env) two_pass_from = atoi(env);
         set = true;
     }
-    bcr_factor_kernel<<<n_elim, FACTOR_THREADS, BCR_FACTOR_SMEM, s>>>(elim, D, Lc, P, Q, rhs, info);
+    if (n_elim >= two_pass_from)
+        bcr_factor_kernel<true><<<n_elim, FACTOR_THREADS, BCR_FACTOR2_SMEM, s>>>(elim, D, Lc, P, Q, rhs, info);
+    else
+        bcr_factor_kernel<false><<<n_elim, FACTOR_THREADS, BCR_FACTOR_SMEM, s>>>(elim, D, Lc, P, Q, rhs, info);
     return cudaGetLastError();
 }
 
