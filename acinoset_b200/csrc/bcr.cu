@@ -457,6 +457,96 @@ bcr_update_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict__
     }
 }
 
+// Two-stage variant for the large levels (more surviving blocks than SMs): two operand buffers instead of three
+// (92 KB) and 256 threads with up to 128 registers -> two CTAs per SM.
+//   stage 1: buf0 = Q_el, buf1 = P_er: the two SYRKs in parallel (threads 0..119 / 128..247), D_j updated by the
+//            P_er group first, then (after a barrier) by the Q_el group; b_j
+//   stage 2: buf1 <- P_el: the GEMM Lc_j = -Q_el^T P_el on 225 threads
+constexpr int UPDATE2_THREADS = 256;
+constexpr size_t BCR_UPDATE2_SMEM = (size_t)(2 * SB * LD + 2 * SB) * sizeof(double);
+
+__device__ __forceinline__ void rmw_tile(double* __restrict__ Dj, const int ty, const int tx, const double acc[5][5]) {
+    double nv[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) nv[r][c] = Dj[(5 * ty + r) * SB + 5 * tx + c];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            nv[r][c] -= acc[r][c];
+            Dj[(5 * ty + r) * SB + 5 * tx + c] = nv[r][c];
+            if (ty != tx) Dj[(5 * tx + c) * SB + 5 * ty + r] = nv[r][c];
+        }
+}
+
+__global__ void __launch_bounds__(UPDATE2_THREADS, 2)
+bcr_update2_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict__ D, double* __restrict__ Lc,
+                   const double* __restrict__ P, const double* __restrict__ Q, double* __restrict__ rhs) {
+    extern __shared__ __align__(16) double sm[];
+    double* b0 = sm;                       // Q_el
+    double* b1 = sm + SB * LD;             // P_er, then P_el
+    double* szl = sm + 2 * SB * LD;        // z_el
+    double* szr = szl + SB;                // z_er
+    const int j = surv[3 * blockIdx.x], el = surv[3 * blockIdx.x + 1], er = surv[3 * blockIdx.x + 2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < SB * SB; i += UPDATE2_THREADS) {
+        const int r = i / SB, c = i - r * SB;
+        if (el >= 0) cp_async8(&b0[r * LD + c], Q + (size_t)el * SB2 + i);
+        if (er >= 0) cp_async8(&b1[r * LD + c], P + (size_t)er * SB2 + i);
+    }
+    if (tid < SB) {
+        szl[tid] = el >= 0 ? rhs[(size_t)el * SB + tid] : 0.0;
+        szr[tid] = er >= 0 ? rhs[(size_t)er * SB + tid] : 0.0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    double acc[5][5];
+    double* Dj = D + (size_t)j * SB2;
+    // ---- stage 1: SYRKs (upper tiles), group A = threads 0..127 (Q_el), group B = 128..255 (P_er)
+    const int t = tid & 127;
+    const bool grpB = tid >= 128;
+    const bool have = t < 120 && (grpB ? er >= 0 : el >= 0);
+    int ty = 0, tx = 0;
+    if (t < 120) {
+        ty = c_tri_tiles.ty[t];
+        tx = c_tri_tiles.tx[t];
+    }
+    if (have) {
+        const double* M = grpB ? b1 : b0;
+        tile_atb(M, M, 5 * ty, 5 * tx, acc);
+        if (grpB) rmw_tile(Dj, ty, tx, acc);
+    }
+    // b_j -= Q_el^T z_el + P_er^T z_er   (threads 120..127 and 248..255 are idle above: any thread may do it after its tile)
+    if (tid < SB) {
+        double sacc = 0.0;
+        if (el >= 0)
+            for (int k = 0; k < SB; ++k) sacc = fma(b0[k * LD + tid], szl[k], sacc);
+        if (er >= 0)
+            for (int k = 0; k < SB; ++k) sacc = fma(b1[k * LD + tid], szr[k], sacc);
+        rhs[(size_t)j * SB + tid] -= sacc;
+    }
+    __syncthreads();                       // group B's update of D_j is visible; P_er no longer needed
+    if (have && !grpB) rmw_tile(Dj, ty, tx, acc);
+    if (el < 0) return;
+    // ---- stage 2: Lc_j = -Q_el^T P_el
+    for (int i = tid; i < SB * SB; i += UPDATE2_THREADS) {
+        const int r = i / SB, c = i - r * SB;
+        cp_async8(&b1[r * LD + c], P + (size_t)el * SB2 + i);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const int gy = tid >> 4, gx = tid & 15;
+    if (gy < 15 && gx < 15) {
+        tile_atb(b0, b1, 5 * gy, 5 * gx, acc);
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) Lc[(size_t)j * SB2 + (5 * gy + r) * SB + 5 * gx + c] = -acc[r][c];
+    }
+}
+
 // x_e = R^-T (z - P x_a - Q x_c), R = L Delta^1/2 stored by bcr_factor in D_e.  256 threads.
 //   1. v = z - [P | Q] [x_a ; x_c]: thread (row, third) reads 50 contiguous doubles of the row's 150 - all loads
 //      independent and issued at once; L is staged in shared memory meanwhile
@@ -552,7 +642,21 @@ cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const doub
 cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
                               double* rhs, cudaStream_t s) {
     if (n_surv <= 0) return cudaSuccess;
-    bcr_update_kernel<<<n_surv, UPDATE_THREADS, BCR_UPDATE_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
+    static bool set = false;
+    static int two_stage_from = 149;     // ACINO_BCR_TWO_PASS_FROM: levels with at least this many blocks use the two-stage kernel
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(bcr_update2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE2_SMEM);
+        if (e != cudaSuccess) return e;
+        const char* env = getenv("ACINO_BCR_TWO_PASS_FROM");
+        if (env) two_stage_from = atoi(env);
+        set = true;
+    }
+    if (n_surv >= two_stage_from)
+        bcr_update2_kernel<<<n_surv, UPDATE2_THREADS, BCR_UPDATE2_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
+    else
+        bcr_update_kernel<<<n_surv, UPDATE_THREADS, BCR_UPDATE_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
     return cudaGetLastError();
 }
 
