@@ -61,6 +61,12 @@ def _load():
     lib.acino_undistort_points.restype = ci
     lib.acino_triangulate_points.argtypes = [vp, ci] + [vp] * 11
     lib.acino_triangulate_points.restype = ci
+    lib.acino_project_points_pinhole.argtypes = [vp, ci, vp, vp, vp, ci, vp, vp, vp]
+    lib.acino_project_points_pinhole.restype = ci
+    lib.acino_undistort_points_pinhole.argtypes = [vp, ci, vp, vp, vp, ci, ci, vp]
+    lib.acino_undistort_points_pinhole.restype = ci
+    lib.acino_triangulate_points_pinhole.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, vp]
+    lib.acino_triangulate_points_pinhole.restype = ci
     lib.acino_triangulate_pairwise.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     lib.acino_triangulate_pairwise.restype = ci
     i64 = ctypes.c_int64
@@ -107,6 +113,7 @@ EXPORTED = [
     "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
     "acino_fk_project_dev", "acino_fk_project", "acino_fte_jac_dev", "acino_fte_jac", "acino_project_points", "acino_undistort_points",
     "acino_triangulate_points", "acino_triangulate_pairwise", "acino_generic_fk",
+    "acino_project_points_pinhole", "acino_undistort_points_pinhole", "acino_triangulate_points_pinhole",
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
     "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_eval_dev",
@@ -243,6 +250,45 @@ class Handle:
         self._check(lib.acino_triangulate_points(self._h, uv1.shape[0], _np_ptr(uv1), _np_ptr(uv2), _np_ptr(K1),
                                                  _np_ptr(D1), _np_ptr(R1), _np_ptr(t1), _np_ptr(K2), _np_ptr(D2),
                                                  _np_ptr(R2), _np_ptr(t2), _np_ptr(X)), "acino_triangulate_points")
+        return X
+
+    # ---- pinhole twins (cv2.projectPoints / cv2.undistortPoints / triangulate_points)
+    @staticmethod
+    def _pincam(K, d, R=None, t=None):
+        K = _host(K, np.float64).reshape(9)
+        d = np.zeros(0) if d is None else _host(d, np.float64).reshape(-1)
+        R = None if R is None else _host(R, np.float64).reshape(9)
+        t = None if t is None else _host(t, np.float64).reshape(3)
+        return K, d, R, t
+
+    def project_points_pinhole(self, X, K, d, R, t):
+        X = _host(X, np.float64).reshape(-1, 3)
+        K, d, R, t = self._pincam(K, d, R, t)
+        uv = np.empty((X.shape[0], 2), np.float64)
+        self._check(lib.acino_project_points_pinhole(self._h, X.shape[0], _np_ptr(X), _np_ptr(K), _np_ptr(d), d.size,
+                                                     _np_ptr(R), _np_ptr(t), _np_ptr(uv)), "acino_project_points_pinhole")
+        return uv
+
+    def undistort_points_pinhole(self, uv, K, d, to_pixels=False):
+        uv = _host(uv, np.float64).reshape(-1, 2)
+        K, d, _, _ = self._pincam(K, d)
+        out = np.empty_like(uv)
+        self._check(lib.acino_undistort_points_pinhole(self._h, uv.shape[0], _np_ptr(uv), _np_ptr(K), _np_ptr(d), d.size,
+                                                       1 if to_pixels else 0, _np_ptr(out)), "acino_undistort_points_pinhole")
+        return out
+
+    def triangulate_points_pinhole(self, uv1, uv2, cam1, cam2):
+        uv1 = _host(uv1, np.float64).reshape(-1, 2)
+        uv2 = _host(uv2, np.float64).reshape(-1, 2)
+        if uv1.shape != uv2.shape:
+            raise ValueError("img_pts_1 and img_pts_2 must hold the same number of points")
+        K1, d1, R1, t1 = self._pincam(*cam1)
+        K2, d2, R2, t2 = self._pincam(*cam2)
+        X = np.empty((uv1.shape[0], 3), np.float64)
+        self._check(lib.acino_triangulate_points_pinhole(self._h, uv1.shape[0], _np_ptr(uv1), _np_ptr(uv2), _np_ptr(K1),
+                                                         _np_ptr(d1), d1.size, _np_ptr(R1), _np_ptr(t1), _np_ptr(K2),
+                                                         _np_ptr(d2), d2.size, _np_ptr(R2), _np_ptr(t2), _np_ptr(X)),
+                    "acino_triangulate_points_pinhole")
         return X
 
     def triangulate_pairwise(self, uv, valid):

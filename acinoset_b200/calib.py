@@ -3,6 +3,7 @@
 
     project_points_fisheye(obj_pts, k, d, r, t) -> (n,2) float64            calib.py:132-136
     triangulate_points_fisheye(img_pts_1, img_pts_2, k1,d1,r1,t1, k2,d2,r2,t2) -> (n,3)   :121-130
+    project_points / triangulate_points / create_undistort_point_function (pinhole twins)   :25-30,52-66
     get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr, triangulate_func)
         -> DataFrame[frame, marker, x, y, z]                                :394-423
 The SBA entry points of the same reference module live in acinoset_b200.sba and are re-exported
@@ -40,6 +41,39 @@ def triangulate_points_fisheye(img_pts_1, img_pts_2, k1, d1, r1, t1, k2, d2, r2,
                                 np.asarray(img_pts_2, dtype=np.float64).reshape(-1, 2),
                                 (k1, np.asarray(d1).reshape(-1)[:4], r1, t1),
                                 (k2, np.asarray(d2).reshape(-1)[:4], r2, t2))
+
+
+# ---- standard (pinhole) camera model twins, calib.py:25-30,52-66 ----------------------------------
+def _as_rmat(r):
+    """cv2.projectPoints takes a rotation matrix or a Rodrigues vector; a matrix goes through
+    cv2.Rodrigues -> rvec -> matrix inside OpenCV (projection onto SO(3)), reproduced here."""
+    r = np.asarray(r, dtype=np.float64)
+    if r.size == 9:
+        return rodrigues_to_mat(rodrigues_to_vec(r.reshape(3, 3)))
+    return rodrigues_to_mat(r.reshape(3))
+
+
+def project_points(obj_pts, k, d, r, t, device=0):
+    """cv2.projectPoints(obj_pts, r, t, k, d)[0].reshape(-1, 2) (calib.py:64-66); d = up to 12 OpenCV
+    coefficients (plumb-bob, rational model of calib.py:18, thin prism) or None."""
+    obj_pts = np.asarray(obj_pts, dtype=np.float64).reshape((-1, 3))
+    return _fte.get_handle(device).project_points_pinhole(obj_pts, k, d, _as_rmat(r), t)
+
+
+def create_undistort_point_function(k, d, device=0):
+    """calib.py:25-30: pixels -> undistorted pixels (cv2.undistortPoints(pts, k, d, P=k))."""
+    def undistort_points(pts):
+        pts = np.asarray(pts, dtype=np.float64).reshape((-1, 2))
+        return _fte.get_handle(device).undistort_points_pinhole(pts, k, d, to_pixels=True)
+    return undistort_points
+
+
+def triangulate_points(img_pts_1, img_pts_2, k1, d1, r1, t1, k2, d2, r2, t2, device=0):
+    """Two-view DLT after cv2.undistortPoints (calib.py:52-61); r is used as given ([r | t], no Rodrigues)."""
+    h = _fte.get_handle(device)
+    return h.triangulate_points_pinhole(np.asarray(img_pts_1, dtype=np.float64).reshape(-1, 2),
+                                        np.asarray(img_pts_2, dtype=np.float64).reshape(-1, 2),
+                                        (k1, d1, r1, t1), (k2, d2, r2, t2))
 
 
 def triangulate_pairwise_dense(uv, valid, k_arr, d_arr, r_arr, t_arr, device=0):

@@ -19,6 +19,13 @@ cudaError_t launch_triangulate_points_f64(const CamD& c1, const CamD& c2, int n,
                                           double* out, cudaStream_t s);
 cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_frames, int L, const double* uv,
                                             const unsigned char* valid, double* pos, int* count, cudaStream_t s);
+cudaError_t launch_project_points_pinhole(const double* K, const double* d, int nd, const double* R, const double* t, int n,
+                                          const double* X, double* uv, cudaStream_t s);
+cudaError_t launch_undistort_points_pinhole(const double* K, const double* d, int nd, int to_pixels, int n, const double* uv,
+                                            double* out, cudaStream_t s);
+cudaError_t launch_triangulate_points_pinhole(const double* K1, const double* d1, int nd1, const double* R1, const double* t1,
+                                              const double* K2, const double* d2, int nd2, const double* R2, const double* t2,
+                                              int n, const double* uv1, const double* uv2, double* out, cudaStream_t s);
 cudaError_t launch_generic_fk(int n_frames, int n_parts, int n_links, const int* dof_mask, const int* link_parent,
                               const int* link_child, const int* link_flags, const double* link_tv, const double* x,
                               double* pos, cudaStream_t s);
@@ -429,6 +436,83 @@ int acino_triangulate_points(acino_handle* h, int n, const double* uv1, const do
     CK(cudaMemcpyAsync(d1, uv1, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d2, uv2, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(launch_triangulate_points_f64(make_cam(K1, D1, R1, t1), make_cam(K2, D2, R2, t2), n, d1, d2, dX, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(X, dX, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+// ---- pinhole twins (calib.py:52-66)
+static bool bad_dist(const double* d, int nd) {
+    if (nd < 0 || nd > 14 || (nd > 0 && !d)) return true;
+    for (int i = 12; i < nd; ++i)
+        if (d[i] != 0.0) return true;      // tilted-sensor terms are not implemented
+    return false;
+}
+
+int acino_project_points_pinhole(acino_handle* h, int n, const double* X, const double* K, const double* dist, int n_dist,
+                                 const double* R, const double* t, double* uv) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_project_points_pinhole: NULL handle");
+    if (n < 0 || !K || !R || !t || (n > 0 && (!X || !uv))) return fail(h, ACINO_ERR_ARG, "acino_project_points_pinhole: bad arguments");
+    if (bad_dist(dist, n_dist)) return fail(h, ACINO_ERR_ARG, "acino_project_points_pinhole: 0..12 distortion coefficients (tilt terms must be 0)");
+    if (n == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nx = pad64((size_t)n * 3), nu = (size_t)n * 2;
+    int rc = ensure_ws(h, (nx + nu) * sizeof(double));
+    if (rc) return rc;
+    double* dX = (double*)h->ws;
+    double* dU = dX + nx;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dX, X, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_project_points_pinhole(K, dist, n_dist < 12 ? n_dist : 12, R, t, n, dX, dU, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(uv, dU, nu * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_undistort_points_pinhole(acino_handle* h, int n, const double* uv, const double* K, const double* dist, int n_dist,
+                                   int to_pixels, double* out) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_undistort_points_pinhole: NULL handle");
+    if (n < 0 || !K || (n > 0 && (!uv || !out))) return fail(h, ACINO_ERR_ARG, "acino_undistort_points_pinhole: bad arguments");
+    if (bad_dist(dist, n_dist)) return fail(h, ACINO_ERR_ARG, "acino_undistort_points_pinhole: 0..12 distortion coefficients (tilt terms must be 0)");
+    if (n == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nu = pad64((size_t)n * 2);
+    int rc = ensure_ws(h, 2 * nu * sizeof(double));
+    if (rc) return rc;
+    double* dU = (double*)h->ws;
+    double* dO = dU + nu;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dU, uv, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_undistort_points_pinhole(K, dist, n_dist < 12 ? n_dist : 12, to_pixels, n, dU, dO, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out, dO, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+int acino_triangulate_points_pinhole(acino_handle* h, int n, const double* uv1, const double* uv2, const double* K1,
+                                     const double* dist1, int n_dist1, const double* R1, const double* t1, const double* K2,
+                                     const double* dist2, int n_dist2, const double* R2, const double* t2, double* X) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_triangulate_points_pinhole: NULL handle");
+    if (n < 0 || !K1 || !R1 || !t1 || !K2 || !R2 || !t2 || (n > 0 && (!uv1 || !uv2 || !X)))
+        return fail(h, ACINO_ERR_ARG, "acino_triangulate_points_pinhole: bad arguments");
+    if (bad_dist(dist1, n_dist1) || bad_dist(dist2, n_dist2))
+        return fail(h, ACINO_ERR_ARG, "acino_triangulate_points_pinhole: 0..12 distortion coefficients (tilt terms must be 0)");
+    if (n == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nu = pad64((size_t)n * 2);
+    int rc = ensure_ws(h, (2 * nu + (size_t)n * 3) * sizeof(double));
+    if (rc) return rc;
+    double* d1 = (double*)h->ws;
+    double* d2 = d1 + nu;
+    double* dX = d2 + nu;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(d1, uv1, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d2, uv2, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_triangulate_points_pinhole(K1, dist1, n_dist1 < 12 ? n_dist1 : 12, R1, t1, K2, dist2, n_dist2 < 12 ? n_dist2 : 12, R2, t2,
+                                         n, d1, d2, dX, s));
     h->launches += 1;
     CK(cudaMemcpyAsync(X, dX, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

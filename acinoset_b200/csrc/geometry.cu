@@ -221,6 +221,91 @@ __global__ void triangulate_pairwise_kernel(const __grid_constant__ CamTableD ta
     if (count) count[i] = cnt;
 }
 
+// ---- pinhole twins (calib.py:52-66): cv2.projectPoints / cv2.undistortPoints with the plumb-bob, rational
+//      (CALIB_RATIONAL_MODEL, calib.py:18) and thin-prism coefficients d = [k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4];
+//      shorter vectors are zero-padded by the caller, the tilt terms (tauX, tauY) are rejected on the host ----
+struct PinCamD {
+    double R[9];
+    double t[3];
+    double fx, fy, cx, cy;
+    double d[12];
+};
+
+__global__ void project_points_pinhole_kernel(const PinCamD cam, const int n, const double* __restrict__ X,
+                                              double* __restrict__ uv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X0 = X[3 * i], X1 = X[3 * i + 1], X2 = X[3 * i + 2];
+    const double xc = cam.R[0] * X0 + cam.R[1] * X1 + cam.R[2] * X2 + cam.t[0];
+    const double yc = cam.R[3] * X0 + cam.R[4] * X1 + cam.R[5] * X2 + cam.t[1];
+    double zc = cam.R[6] * X0 + cam.R[7] * X1 + cam.R[8] * X2 + cam.t[2];
+    zc = zc != 0.0 ? 1.0 / zc : 1.0;                       // OpenCV: z = z ? 1/z : 1
+    const double x = xc * zc, y = yc * zc;
+    const double* k = cam.d;
+    const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+    const double cdist = 1 + k[0] * r2 + k[1] * r4 + k[4] * r6;
+    const double icdist2 = 1.0 / (1 + k[5] * r2 + k[6] * r4 + k[7] * r6);
+    const double xd = x * cdist * icdist2 + k[2] * a1 + k[3] * a2 + k[8] * r2 + k[9] * r4;
+    const double yd = y * cdist * icdist2 + k[2] * a3 + k[3] * a1 + k[10] * r2 + k[11] * r4;
+    uv[2 * i] = xd * cam.fx + cam.cx;
+    uv[2 * i + 1] = yd * cam.fy + cam.cy;
+}
+
+// cv2.undistortPoints(pts, k, d[, P]) with its default criteria: exactly 5 fixed-point iterations, no
+// convergence test; a negative inverse-distortion factor returns the plain normalised point
+__device__ __forceinline__ void undistort_point_pinhole(const PinCamD& cam, const double u, const double v, double& xo,
+                                                        double& yo) {
+    const double* k = cam.d;
+    double x = (u - cam.cx) / cam.fx, y = (v - cam.cy) / cam.fy;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) {
+            x = x0;
+            y = y0;
+            break;
+        }
+        const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - dx) * icdist;
+        y = (y0 - dy) * icdist;
+    }
+    xo = x;
+    yo = y;
+}
+
+// to_pixels: the `P=k` form of create_undistort_point_function (calib.py:25-30)
+__global__ void undistort_points_pinhole_kernel(const PinCamD cam, const int n, const int to_pixels,
+                                                const double* __restrict__ uv, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y;
+    undistort_point_pinhole(cam, uv[2 * i], uv[2 * i + 1], x, y);
+    out[2 * i] = to_pixels ? x * cam.fx + cam.cx : x;
+    out[2 * i + 1] = to_pixels ? y * cam.fy + cam.cy : y;
+}
+
+__global__ void triangulate_points_pinhole_kernel(const PinCamD cam1, const PinCamD cam2, const int n,
+                                                  const double* __restrict__ uv1, const double* __restrict__ uv2,
+                                                  double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CamT<double> c1, c2;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { c1.R[j] = cam1.R[j]; c2.R[j] = cam2.R[j]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { c1.t[j] = cam1.t[j]; c2.t[j] = cam2.t[j]; }
+    double x1, y1, x2, y2, X[3];
+    undistort_point_pinhole(cam1, uv1[2 * i], uv1[2 * i + 1], x1, y1);
+    undistort_point_pinhole(cam2, uv2[2 * i], uv2[2 * i + 1], x2, y2);
+    dlt_pair<double>(c1, c2, x1, y1, x2, y2, X);
+    out[3 * i] = X[0];
+    out[3 * i + 1] = X[1];
+    out[3 * i + 2] = X[2];
+}
+
 // ---- launchers --------------------------------------------------------------------------------
 static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 
@@ -247,6 +332,35 @@ cudaError_t launch_triangulate_pairwise_f64(const CamD* cams, int n_cams, int n_
     for (int c = 0; c < n_cams; ++c) tab.cam[c] = cams[c];
     tab.n_cams = n_cams;
     triangulate_pairwise_kernel<double><<<nblk((long long)n_frames * L, 64), 64, 0, s>>>(tab, n_frames, L, uv, valid, pos, count);
+    return cudaGetLastError();
+}
+
+static PinCamD make_pincam(const double* K, const double* d, int nd, const double* R, const double* t) {
+    PinCamD c;
+    for (int i = 0; i < 9; ++i) c.R[i] = R ? R[i] : (i % 4 == 0 ? 1.0 : 0.0);
+    for (int i = 0; i < 3; ++i) c.t[i] = t ? t[i] : 0.0;
+    for (int i = 0; i < 12; ++i) c.d[i] = i < nd ? d[i] : 0.0;
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    return c;
+}
+cudaError_t launch_project_points_pinhole(const double* K, const double* d, int nd, const double* R, const double* t, int n,
+                                          const double* X, double* uv, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    project_points_pinhole_kernel<<<nblk(n, 128), 128, 0, s>>>(make_pincam(K, d, nd, R, t), n, X, uv);
+    return cudaGetLastError();
+}
+cudaError_t launch_undistort_points_pinhole(const double* K, const double* d, int nd, int to_pixels, int n, const double* uv,
+                                            double* out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    undistort_points_pinhole_kernel<<<nblk(n, 128), 128, 0, s>>>(make_pincam(K, d, nd, nullptr, nullptr), n, to_pixels, uv, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_triangulate_points_pinhole(const double* K1, const double* d1, int nd1, const double* R1, const double* t1,
+                                              const double* K2, const double* d2, int nd2, const double* R2, const double* t2,
+                                              int n, const double* uv1, const double* uv2, double* out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    triangulate_points_pinhole_kernel<<<nblk(n, 64), 64, 0, s>>>(make_pincam(K1, d1, nd1, R1, t1), make_pincam(K2, d2, nd2, R2, t2),
+                                                                n, uv1, uv2, out);
     return cudaGetLastError();
 }
 

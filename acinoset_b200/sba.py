@@ -483,3 +483,28 @@ def sba_board_points_fisheye(scene_fpath, points_fpaths, out_fpath, manual_point
                                                                            d_arr, r_arr, t_arr)
     utils.save_scene(out_fpath, k_arr, d_arr, r_new, t_new, cam_res)
     return res
+
+
+def sba_points_fisheye(scene_fpath, points_2d_df, device=0):
+    """``app.sba_points_fisheye(scene_fpath, points_2d_df) -> (points_3d_df, residuals)`` as called at
+    all_optimizations.py:874 and SBA.ipynb:99 (the callee is missing from the reference snapshot; semantics from
+    the call sites and from bundle_adjust_points_only, calib.py:327-341): triangulate every (frame, marker) from
+    adjacent camera pairs, then refine the 3-D points alone against all cameras that saw them (cameras fixed,
+    Cauchy loss, f_scale = 50)."""
+    from . import calib, utils
+
+    k_arr, d_arr, r_arr, t_arr, _ = utils.load_scene(scene_fpath)
+    assert len(k_arr) == points_2d_df["camera"].nunique()
+    points_3d_df = calib.get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr,
+                                                        calib.triangulate_points_fisheye, device=device)
+    points_3d_df = points_3d_df.reset_index(drop=True)
+    points_3d_df["point_index"] = points_3d_df.index
+    points_df = points_2d_df.merge(points_3d_df, how="inner", on=["frame", "marker"], suffixes=("_cam", ""))
+    points_2d = points_df[["x_cam", "y_cam"]].to_numpy(dtype=np.float32)
+    point_indices = points_df["point_index"].to_numpy(dtype=np.int64)
+    camera_indices = points_df["camera"].to_numpy(dtype=np.int64)
+    points_3d = points_3d_df[["x", "y", "z"]].to_numpy(dtype=np.float32)
+    pts, residuals = bundle_adjust_points_only(points_2d, points_3d, point_indices, camera_indices, k_arr, d_arr, r_arr,
+                                               t_arr)
+    points_3d_df[["x", "y", "z"]] = pts
+    return points_3d_df, residuals

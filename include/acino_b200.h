@@ -111,6 +111,23 @@ int acino_triangulate_points(acino_handle* h, int n, const double* uv1, const do
                              const double* K2, const double* D2, const double* R2, const double* t2,
                              double* X);
 
+/* Pinhole twins of the three calls above: project_points (calib.py:64-66, cv2.projectPoints),
+ * create_undistort_point_function (:25-30, cv2.undistortPoints with P = K: to_pixels = 1) and
+ * triangulate_points (:52-61, cv2.undistortPoints x2 + cv2.triangulatePoints).  dist holds n_dist <= 14
+ * coefficients in OpenCV order [k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 tauX tauY] (the reference calibrates the
+ * 8-coefficient rational model, calib.py:18); missing ones are 0, non-zero tilt terms are ACINO_ERR_ARG.
+ * Undistortion = OpenCV's default criteria: exactly 5 fixed-point iterations. */
+int acino_project_points_pinhole(acino_handle* h, int n, const double* X, const double* K,
+                                 const double* dist, int n_dist, const double* R, const double* t,
+                                 double* uv);
+int acino_undistort_points_pinhole(acino_handle* h, int n, const double* uv, const double* K,
+                                   const double* dist, int n_dist, int to_pixels, double* out);
+int acino_triangulate_points_pinhole(acino_handle* h, int n, const double* uv1, const double* uv2,
+                                     const double* K1, const double* dist1, int n_dist1,
+                                     const double* R1, const double* t1, const double* K2,
+                                     const double* dist2, int n_dist2, const double* R2,
+                                     const double* t2, double* X);
+
 /* get_pairwise_3d_points_from_df (calib.py:394-423) on dense tensors, cameras from
  * acino_set_cameras: uv [N][C][L][2], valid [N][C][L] (1 = the row survives the caller's likelihood
  * filter) -> pos [N][L][3] = unweighted mean of the adjacent-pair (c, c+1) triangulations in the

@@ -213,13 +213,48 @@ def gen_sba(calib, utils):
     np.savez_compressed(os.path.join(HERE, "sba.npz"), **out)
 
 
+def gen_pinhole(calib, utils):
+    """project_points / create_undistort_point_function / triangulate_points (calib.py:25-30,52-66) run through
+    the reference's own functions with the rational (8-coefficient, calib.py:18), plumb-bob (5) and
+    thin-prism (12) coefficient sets."""
+    import cv2
+
+    rng = np.random.default_rng(11)
+    K1 = np.array([[1210.0, 0, 1352.0], [0, 1198.0, 761.0], [0, 0, 1]])
+    K2 = np.array([[1180.0, 0, 1330.0], [0, 1185.0, 770.0], [0, 0, 1]])
+    dists = {
+        "d5": np.array([-0.21, 0.07, 0.0012, -0.0008, -0.011]),
+        "d8": np.array([0.11, -0.05, 0.001, -0.002, 0.01, 0.02, -0.01, 0.003]),
+        "d12": np.array([0.08, -0.03, 0.0007, 0.0011, 0.004, 0.015, -0.006, 0.001, 0.0009, -0.0004, 0.0006, 0.0003]),
+    }
+    r1 = cv2.Rodrigues(np.array([0.1, -0.2, 0.05]))[0]
+    t1 = np.array([[0.1], [0.2], [0.3]])
+    r2 = cv2.Rodrigues(np.array([-0.05, 0.35, 0.02]))[0]
+    t2 = np.array([[-1.4], [0.1], [0.5]])
+    X = rng.normal(0, 0.8, (200, 3)) + [0, 0, 5.0]
+    out = dict(K1=K1, K2=K2, r1=r1, t1=t1, r2=r2, t2=t2, X=X)
+    for tag, d in dists.items():
+        uv1 = calib.project_points(X, K1, d, r1, t1)
+        uv2 = calib.project_points(X, K2, d, r2, t2)
+        uv1_rvec = calib.project_points(X, K1, d, cv2.Rodrigues(r1)[0], t1)
+        und = calib.create_undistort_point_function(K1, d)(uv1.astype(np.float64))
+        noisy1 = uv1 + rng.normal(0, 1.0, uv1.shape)
+        noisy2 = uv2 + rng.normal(0, 1.0, uv2.shape)
+        tri = calib.triangulate_points(noisy1, noisy2, K1, d, r1, t1, K2, d, r2, t2)
+        tri0 = calib.triangulate_points(uv1, uv2, K1, d, r1, t1, K2, d, r2, t2)
+        out.update({f"{tag}": d, f"{tag}_uv1": uv1, f"{tag}_uv2": uv2, f"{tag}_uv1_rvec": uv1_rvec, f"{tag}_und": und,
+                    f"{tag}_noisy1": noisy1, f"{tag}_noisy2": noisy2, f"{tag}_tri": tri, f"{tag}_tri_clean": tri0})
+        print("pinhole", tag, "clean triangulation max err", np.abs(tri0 - X).max())
+    np.savez_compressed(os.path.join(HERE, "pinhole.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-sympy-jac", action="store_true")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     calib, utils = ref_shim.load_reference_calib()
-    todo = args.only.split(",") if args.only else ["fk", "fisheye", "loss", "tri", "generic", "sba"]
+    todo = args.only.split(",") if args.only else ["fk", "fisheye", "loss", "tri", "generic", "sba", "pinhole"]
     if "fisheye" in todo:
         gen_fisheye(calib, utils)
     if "loss" in todo:
@@ -230,6 +265,8 @@ def main():
         gen_generic_fk()
     if "sba" in todo:
         gen_sba(calib, utils)
+    if "pinhole" in todo:
+        gen_pinhole(calib, utils)
     if "fk" in todo:
         gen_cheetah_fk(args.skip_sympy_jac)
 

@@ -72,3 +72,66 @@ def test_fte_reference_signature_writes_pickle(tmp_path, dummy_cams):
         ok = np.abs(uv) < 1e4                       # behind-camera points project "validly" far outside the image
         assert np.abs(dense[:, c] - uv)[ok].max() < 1e-6 * np.abs(uv[ok]).max() + 1e-6
     assert np.all(lik == 1.0)
+
+
+def _write_run(tmp_path, p, cams, n):
+    import pandas as pd
+    from acinoset_b200 import fte, utils
+
+    K, D, R, t, res = cams
+    data = tmp_path / "run"
+    (data / "dlc").mkdir(parents=True)
+    (tmp_path / "extrinsic_calib").mkdir()
+    utils.save_scene(str(tmp_path / "extrinsic_calib" / "6_cam_scene_sba.json"), K, D.reshape(-1, 4, 1), R, t.reshape(-1, 3, 1), res)
+    cols = pd.MultiIndex.from_product([["scorer"], fte.MARKERS, ["x", "y", "likelihood"]], names=["scorer", "bodyparts", "coords"])
+    for c in range(6):
+        arr = np.concatenate([p["meas"][:, c], p["lik"][:, c, :, None]], axis=-1).reshape(n, -1)
+        pd.DataFrame(arr, columns=cols).to_csv(data / "dlc" / f"cam{c + 1}DLC.csv")
+    return data
+
+
+def test_pipeline_tri_sba_ekf_by_reference_names(tmp_path, dummy_cams):
+    """all_optimizations.tri / sba / ekf (:569-936) on a synthetic run directory."""
+    import synth
+    from acinoset_b200 import all_optimizations as ao
+    from oracle import fisheye, skeleton
+
+    n = 40
+    rng = np.random.default_rng(5)
+    x_true = synth.make_trajectory(n, rng, fps=synth.FPS * 4)
+    P = skeleton.cheetah_fk_active(x_true)
+    meas, lik = synth.make_measurements(P, dummy_cams, fisheye.project, rng, noise_px=0.5, outlier_frac=0.0)
+    data = _write_run(tmp_path, dict(meas=meas, lik=lik), dummy_cams, n)
+    pos = ao.tri(str(data), 1, -1, 0.5)
+    assert pos.shape == (n, 20, 3)
+    seen = ~np.isnan(pos[..., 0])
+    assert seen.mean() > 0.5
+    err_tri = np.linalg.norm(pos[seen] - P[seen], axis=-1)
+    assert np.median(err_tri) < 0.02
+    with open(data / "tri" / "tri.pickle", "rb") as f:
+        saved = pickle.load(f)
+    assert np.array_equal(np.isnan(saved["positions"]), np.isnan(pos)) and saved["start_frame"] == 0
+    pos_sba, residuals = ao.sba(str(data), 1, -1, 0.5)
+    assert pos_sba.shape == (n, 20, 3) and set(residuals) == {"before", "after"}
+    err_sba = np.linalg.norm(pos_sba[seen] - P[seen], axis=-1)
+    # refining each point against every camera that saw it cannot be worse than the adjacent-pair mean
+    assert 0.5 * np.sum(np.log1p((residuals["after"] / 50) ** 2)) <= 0.5 * np.sum(np.log1p((residuals["before"] / 50) ** 2)) + 1e-9
+    assert np.median(err_sba) <= np.median(err_tri) * 1.05
+    out = ao.ekf(str(data), 1, -1, 0.5, fps=synth.FPS)
+    assert out["positions"].shape == (n, 20, 3) and out["smoothed_x"].shape == (n, 25) and out["start_frame"] == 0
+    assert os.path.exists(data / "ekf" / "ekf.pickle") and len(list((data / "ekf").glob("cam*_ekf.csv"))) == 6
+
+
+def test_pt3d_to_2d_scalar_and_array(dummy_cams):
+    from acinoset_b200 import all_optimizations as ao
+    from oracle import fisheye
+
+    K, D, R, t, _ = dummy_cams
+    X = np.array([[1.0, 6.0, 0.5], [2.5, 7.0, 0.2], [0.3, 5.0, 1.0]])
+    ref = fisheye.project(X, K[1], D[1], R[1], t[1])
+    u, v = ao.pt3d_to_2d(X[0, 0], X[0, 1], X[0, 2], K[1], D[1], R[1], t[1])
+    assert isinstance(u, float) and abs(u - ref[0, 0]) < 1e-9 and abs(v - ref[0, 1]) < 1e-9
+    uu, vv = ao.pt3d_to_2d(X[:, 0], X[:, 1], X[:, 2], K[1], D[1], R[1], t[1])
+    assert np.abs(uu - ref[:, 0]).max() < 1e-9 and np.abs(vv - ref[:, 1]).max() < 1e-9
+    assert abs(ao.pt3d_to_x2d(*X[2], K[1], D[1], R[1], t[1]) - ref[2, 0]) < 1e-9
+    assert abs(ao.pt3d_to_y2d(*X[2], K[1], D[1], R[1], t[1]) - ref[2, 1]) < 1e-9

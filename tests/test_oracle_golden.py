@@ -270,3 +270,22 @@ def test_smooth_term_gradient_and_band():
                     gb[n + k] += band[n, k] * xa[n]
     assert np.abs(gb - g).max() < 1e-9 * np.abs(g).max()
     assert fte.smooth_cost(xa[:3], Ts) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["d5", "d8", "d12"])
+def test_pinhole_twins_match_reference(tag):
+    """project_points / create_undistort_point_function / triangulate_points (calib.py:25-30,52-66)."""
+    from oracle import pinhole
+
+    g = golden("pinhole.npz")
+    d = g[tag]
+    uv1 = pinhole.project_points(g["X"], g["K1"], d, g["r1"], g["t1"])
+    assert np.abs(uv1 - g[f"{tag}_uv1"]).max() < 1e-9
+    assert np.abs(uv1 - g[f"{tag}_uv1_rvec"]).max() < 1e-9
+    uv2 = pinhole.project_points(g["X"], g["K2"], d, g["r2"], g["t2"])
+    assert np.abs(uv2 - g[f"{tag}_uv2"]).max() < 1e-9
+    und = pinhole.undistort_points(g[f"{tag}_uv1"], g["K1"], d, to_pixels=True)
+    assert np.abs(und - g[f"{tag}_und"]).max() < 1e-9
+    tri = pinhole.triangulate_points(g[f"{tag}_noisy1"], g[f"{tag}_noisy2"], g["K1"], d, g["r1"], g["t1"],
+                                     g["K2"], d, g["r2"], g["t2"])
+    assert np.abs(tri - g[f"{tag}_tri"]).max() < 1e-8
