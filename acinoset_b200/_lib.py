@@ -72,6 +72,23 @@ def _load():
     i64 = ctypes.c_int64
     lib.acino_generic_fk.argtypes = [vp, ci, ci, ci] + [vp] * 7
     lib.acino_generic_fk.restype = ci
+    u64p = vp
+    lib.acino_skel_set.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, u64p, ci, cd, cd, cd, cd]
+    lib.acino_skel_set.restype = ci
+    lib.acino_skel_eval_dev.argtypes = [vp, ci] + [vp] * 7
+    lib.acino_skel_eval_dev.restype = ci
+    lib.acino_skel_eval.argtypes = [vp, ci] + [vp] * 6
+    lib.acino_skel_eval.restype = ci
+    lib.acino_skel_prepare_dev.argtypes = [vp, ci, ci] + [vp] * 9
+    lib.acino_skel_prepare_dev.restype = ci
+    lib.acino_skel_assemble_dev.argtypes = [vp, ci, vp, vp, vp, vp, cd, vp, vp, vp]
+    lib.acino_skel_assemble_dev.restype = ci
+    lib.acino_band_solve_dev.argtypes = [vp, i64, ci, vp, vp, vp, vp]
+    lib.acino_band_solve_dev.restype = ci
+    lib.acino_skel_trial_dev.argtypes = [vp, ci, ci] + [vp] * 6
+    lib.acino_skel_trial_dev.restype = ci
+    lib.acino_skel_pred_dev.argtypes = [vp, ci] + [vp] * 8
+    lib.acino_skel_pred_dev.restype = ci
     lib.acino_lm_prepare_dev.argtypes = [vp, ci, i64, i64] + [vp] * 9
     lib.acino_lm_prepare_dev.restype = ci
     lib.acino_lm_assemble_dev.argtypes = [vp, ci, i64, i64, ci, vp, vp, vp, vp, cd, vp, vp, vp, vp]
@@ -114,6 +131,8 @@ EXPORTED = [
     "acino_fk_project_dev", "acino_fk_project", "acino_fte_jac_dev", "acino_fte_jac", "acino_project_points", "acino_undistort_points",
     "acino_triangulate_points", "acino_triangulate_pairwise", "acino_generic_fk",
     "acino_project_points_pinhole", "acino_undistort_points_pinhole", "acino_triangulate_points_pinhole",
+    "acino_skel_set", "acino_skel_eval_dev", "acino_skel_eval", "acino_skel_prepare_dev", "acino_skel_assemble_dev",
+    "acino_band_solve_dev", "acino_skel_trial_dev", "acino_skel_pred_dev",
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
     "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_eval_dev",
@@ -251,6 +270,34 @@ class Handle:
                                                  _np_ptr(D1), _np_ptr(R1), _np_ptr(t1), _np_ptr(K2), _np_ptr(D2),
                                                  _np_ptr(R2), _np_ptr(t2), _np_ptr(X)), "acino_triangulate_points")
         return X
+
+    # ---- generic-skeleton FTE (build.py variant), fp64
+    def skel_set(self, flat, loss="abs", abc=(3.0, 10.0, 20.0), delta=0.05):
+        """flat: acinoset_b200.skeleton.flatten_skeleton(skel_dict); cameras must be set first."""
+        n_parts, n_links, n_out = len(flat["parts"]), len(flat["link_parent"]), len(flat["out_order"])
+        kind = {"redescending": 0, "abs": 1}[loss]
+        dm = _host(flat["dof_mask"], np.int32)
+        lp, lf = _host(flat["link_parent"], np.int32), _host(flat["link_flags"], np.int32)
+        tv, path = _host(flat["link_tv"], np.float64), _host(flat["out_path"], np.uint64)
+        self._check(lib.acino_skel_set(self._h, n_parts, n_links, n_out, _np_ptr(dm), _np_ptr(lp), _np_ptr(lf), _np_ptr(tv),
+                                       _np_ptr(path), kind, float(abc[0]), float(abc[1]), float(abc[2]), float(delta)),
+                    "acino_skel_set")
+        self.skel_shape = (3 + 3 * n_parts, n_out)
+
+    def skel_eval(self, x, meas, w, want_H=True):
+        """x (N,P), meas (N,C,n_out,2), w (N,C,n_out) -> cost (N,), g (N,P), H (N,P(P+1)/2) fp64 (host buffers)."""
+        P, n_out = self.skel_shape
+        x = _host(x, np.float64)
+        N = x.shape[0]
+        x = _host(x, np.float64, (N, P))
+        meas = _host(meas, np.float64, (N, self.n_cams, n_out, 2))
+        w = _host(w, np.float64, (N, self.n_cams, n_out))
+        cost = np.empty(N)
+        g = np.empty((N, P))
+        H = np.empty((N, P * (P + 1) // 2)) if want_H else None
+        self._check(lib.acino_skel_eval(self._h, N, _np_ptr(x), _np_ptr(meas), _np_ptr(w), _np_ptr(cost), _np_ptr(g),
+                                        _np_ptr(H)), "acino_skel_eval")
+        return cost, g, H
 
     # ---- pinhole twins (cv2.projectPoints / cv2.undistortPoints / triangulate_points)
     @staticmethod

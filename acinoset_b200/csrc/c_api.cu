@@ -6,6 +6,7 @@
 #include <string>
 
 #include "acino_common.cuh"
+#include "skel_body.cuh"
 
 namespace acino {
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
@@ -29,6 +30,19 @@ cudaError_t launch_triangulate_points_pinhole(const double* K1, const double* d1
 cudaError_t launch_generic_fk(int n_frames, int n_parts, int n_links, const int* dof_mask, const int* link_parent,
                               const int* link_child, const int* link_flags, const double* link_tv, const double* x,
                               double* pos, cudaStream_t s);
+size_t skel_eval_smem_bytes(int n_links, int n_out);
+cudaError_t launch_skel_eval(const SkelDesc* d_skel, int n_links, int n_out, int P, int n_frames, const double* x,
+                             const double* meas, const double* w, double* cost, double* g, double* H, cudaStream_t s);
+cudaError_t launch_skel_prepare(int N, int P, int last_free, const double* x, const double* g, const double* sw,
+                                const double* lo, const double* hi, double* gtot, unsigned char* fixed, double* cost_s,
+                                cudaStream_t s);
+cudaError_t launch_skel_assemble(int N, int P, const double* H, const double* gtot, const unsigned char* fixed,
+                                 const double* sw, double lam, double* AB, double* rhs, cudaStream_t s);
+cudaError_t launch_band_solve(long long n, int hb, double* AB, double* x, int* info, cudaStream_t s);
+cudaError_t launch_skel_trial(int N, int P, int last_free, const double* x, const double* d, const double* lo,
+                              const double* hi, double* xt, cudaStream_t s);
+cudaError_t launch_skel_pred(int N, int P, const double* x, const double* xt, const double* gtot, const double* H,
+                             const double* sw, double* pred, double* step, cudaStream_t s);
 cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, const double* x_ext, const float* g,
                               const double* sw, const double* lo, const double* hi, double* gtot, unsigned char* fixed,
                               double* cost_s, cudaStream_t s);
@@ -85,6 +99,10 @@ struct acino_handle {
     static constexpr int kMaxChunks = 64;
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
     bool pipe_ready = false;
+    // generic-skeleton variant (build.py): host copy + device copy of the descriptor
+    SkelDesc skel;
+    SkelDesc* d_skel = nullptr;
+    bool have_skel = false;
 };
 
 static thread_local std::string g_err;
@@ -168,6 +186,7 @@ int acino_destroy(acino_handle* h) {
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->red_ws) cudaFree(h->red_ws);
+    if (h->d_skel) cudaFree(h->d_skel);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->pipe_ready) {
         cudaStreamDestroy(h->s_h2d);
@@ -589,6 +608,152 @@ int acino_generic_fk(acino_handle* h, int n_frames, int n_parts, int n_links, co
     if (!h) return fail(nullptr, ACINO_ERR_ARG, name ": NULL handle");          \
     CK(cudaSetDevice(h->device));                                               \
     cudaStream_t s = (cudaStream_t)cuda_stream
+
+// ---- generic-skeleton FTE (build.py variant) ----------------------------------------------------------------
+int acino_skel_set(acino_handle* h, int n_parts, int n_links, int n_out, const int32_t* dof_mask, const int32_t* link_parent,
+                   const int32_t* link_flag, const double* link_tv, const uint64_t* path, int loss_kind, double a, double b,
+                   double c, double delta) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_skel_set: NULL handle");
+    if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_skel_set: cameras not set (acino_set_cameras first)");
+    if (n_parts < 1 || n_parts > SK_MAX_PARTS || n_links < 0 || n_links > SK_MAX_LINKS || n_out < 1 || n_out > SK_MAX_PARTS ||
+        !dof_mask || !path || (n_links > 0 && (!link_parent || !link_flag || !link_tv)))
+        return fail(h, ACINO_ERR_ARG, "acino_skel_set: need 1..32 parts / output rows, 0..40 links and non-NULL tables");
+    if (loss_kind != 0 && loss_kind != 1) return fail(h, ACINO_ERR_ARG, "acino_skel_set: loss_kind is 0 (redescending) or 1 (abs)");
+    if (loss_kind == 0 && !(a > 0 && b > a && c > b)) return fail(h, ACINO_ERR_ARG, "acino_skel_set: need 0 < a < b < c");
+    if (loss_kind == 1 && !(delta > 0)) return fail(h, ACINO_ERR_ARG, "acino_skel_set: delta must be > 0");
+    SkelDesc& S = h->skel;
+    memset(&S, 0, sizeof(S));
+    S.n_parts = n_parts; S.n_links = n_links; S.n_out = n_out; S.n_cams = h->scene.n_cams;
+    for (int i = 0; i < n_parts; ++i) S.dof_mask[i] = dof_mask[i] & 7;
+    for (int l = 0; l < n_links; ++l) {
+        if (link_parent[l] < 0 || link_parent[l] >= n_parts) return fail(h, ACINO_ERR_ARG, "acino_skel_set: link parent out of range");
+        S.link_parent[l] = link_parent[l];
+        S.link_flag[l] = link_flag[l] & 1;
+        for (int i = 0; i < 3; ++i) S.link_tv[l][i] = link_tv[3 * l + i];
+    }
+    for (int r = 0; r < n_out; ++r) {
+        if (n_links < 64 && (path[r] >> n_links) != 0) return fail(h, ACINO_ERR_ARG, "acino_skel_set: path names a link that does not exist");
+        S.path[r] = path[r];
+    }
+    int k = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        S.part_ptr[p] = k;
+        for (int l = 0; l < n_links; ++l)
+            if (S.link_parent[l] == p) S.part_links[k++] = l;
+    }
+    for (int p = n_parts; p <= SK_MAX_PARTS; ++p) S.part_ptr[p] = k;
+    S.loss_kind = loss_kind; S.la = a; S.lb = b; S.lc = c; S.delta = delta;
+    for (int cI = 0; cI < S.n_cams; ++cI) {
+        const CamD& cd = h->cam_d[cI];
+        SkelCam& sc = S.cam[cI];
+        for (int i = 0; i < 9; ++i) sc.R[i] = cd.R[i];
+        for (int i = 0; i < 3; ++i) sc.t[i] = cd.t[i];
+        for (int i = 0; i < 4; ++i) sc.D[i] = cd.D[i];
+        sc.fx = cd.fx; sc.fy = cd.fy; sc.cx = cd.cx; sc.cy = cd.cy;
+    }
+    CK(cudaSetDevice(h->device));
+    if (!h->d_skel) CK(cudaMalloc(&h->d_skel, sizeof(SkelDesc)));
+    CK(cudaMemcpy(h->d_skel, &S, sizeof(SkelDesc), cudaMemcpyHostToDevice));
+    h->have_skel = true;
+    return ACINO_OK;
+}
+
+int acino_skel_eval_dev(acino_handle* h, int n_frames, const double* x, const double* meas, const double* w, double* cost,
+                        double* g, double* H, void* cuda_stream) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_skel_eval_dev: NULL handle");
+    if (!h->have_skel) return fail(h, ACINO_ERR_STATE, "acino_skel_eval_dev: skeleton not set");
+    if (n_frames < 0 || (n_frames > 0 && (!x || !meas || !w))) return fail(h, ACINO_ERR_ARG, "acino_skel_eval_dev: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    CK(launch_skel_eval(h->d_skel, h->skel.n_links, h->skel.n_out, 3 + 3 * h->skel.n_parts, n_frames, x, meas, w, cost, g, H,
+                        (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_skel_eval(acino_handle* h, int n_frames, const double* x, const double* meas, const double* w, double* cost, double* g,
+                    double* H) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_skel_eval: NULL handle");
+    if (!h->have_skel) return fail(h, ACINO_ERR_STATE, "acino_skel_eval: skeleton not set");
+    if (n_frames < 0 || (n_frames > 0 && (!x || !meas || !w))) return fail(h, ACINO_ERR_ARG, "acino_skel_eval: bad arguments");
+    if (n_frames == 0) return ACINO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t N = (size_t)n_frames, P = 3 + 3 * (size_t)h->skel.n_parts, NU = P * (P + 1) / 2;
+    const size_t CO = (size_t)h->skel.n_cams * h->skel.n_out;
+    const size_t nx = pad64(N * P), nm = pad64(N * CO * 2), nw = pad64(N * CO), nc = pad64(N), ng = pad64(N * P);
+    int rc = ensure_ws(h, (nx + nm + nw + nc + ng + N * NU) * sizeof(double));
+    if (rc) return rc;
+    double* dx = (double*)h->ws;
+    double* dm = dx + nx;
+    double* dw = dm + nm;
+    double* dc = dw + nw;
+    double* dg = dc + nc;
+    double* dH = dg + ng;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dx, x, N * P * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dm, meas, N * CO * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dw, w, N * CO * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(launch_skel_eval(h->d_skel, h->skel.n_links, h->skel.n_out, (int)P, n_frames, dx, dm, dw, cost ? dc : nullptr,
+                        g ? dg : nullptr, H ? dH : nullptr, s));
+    h->launches += 1;
+    if (cost) CK(cudaMemcpyAsync(cost, dc, N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (g) CK(cudaMemcpyAsync(g, dg, N * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (H) CK(cudaMemcpyAsync(H, dH, N * NU * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+#define SKEL_PRE(name)                                                                           \
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, name ": NULL handle");                           \
+    if (!h->have_skel) return fail(h, ACINO_ERR_STATE, name ": skeleton not set");               \
+    if (n_frames <= 0) return fail(h, ACINO_ERR_ARG, name ": n_frames must be positive");        \
+    CK(cudaSetDevice(h->device));                                                                \
+    const int P = 3 + 3 * h->skel.n_parts;
+
+int acino_skel_prepare_dev(acino_handle* h, int n_frames, int last_free, const double* x, const double* g, const double* sw,
+                           const double* lo, const double* hi, double* gtot, uint8_t* fixed, double* cost_s, void* cuda_stream) {
+    SKEL_PRE("acino_skel_prepare_dev")
+    if (!x || !g || !sw || !lo || !hi || !gtot || !fixed || !cost_s) return fail(h, ACINO_ERR_ARG, "acino_skel_prepare_dev: NULL pointer");
+    CK(launch_skel_prepare(n_frames, P, last_free, x, g, sw, lo, hi, gtot, fixed, cost_s, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_skel_assemble_dev(acino_handle* h, int n_frames, const double* H, const double* gtot, const uint8_t* fixed,
+                            const double* sw, double lambda, double* AB, double* rhs, void* cuda_stream) {
+    SKEL_PRE("acino_skel_assemble_dev")
+    if (!H || !gtot || !fixed || !sw || !AB || !rhs) return fail(h, ACINO_ERR_ARG, "acino_skel_assemble_dev: NULL pointer");
+    CK(launch_skel_assemble(n_frames, P, H, gtot, fixed, sw, lambda, AB, rhs, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_band_solve_dev(acino_handle* h, int64_t n, int half_bandwidth, double* AB, double* x, int32_t* info, void* cuda_stream) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_band_solve_dev: NULL handle");
+    if (n <= 0 || half_bandwidth < 0 || !AB || !x || !info) return fail(h, ACINO_ERR_ARG, "acino_band_solve_dev: bad arguments");
+    CK(cudaSetDevice(h->device));
+    CK(launch_band_solve(n, half_bandwidth, AB, x, info, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_skel_trial_dev(acino_handle* h, int n_frames, int last_free, const double* x, const double* d, const double* lo,
+                         const double* hi, double* xt, void* cuda_stream) {
+    SKEL_PRE("acino_skel_trial_dev")
+    if (!x || !d || !lo || !hi || !xt) return fail(h, ACINO_ERR_ARG, "acino_skel_trial_dev: NULL pointer");
+    CK(launch_skel_trial(n_frames, P, last_free, x, d, lo, hi, xt, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_skel_pred_dev(acino_handle* h, int n_frames, const double* x, const double* xt, const double* gtot, const double* H,
+                        const double* sw, double* pred, double* step, void* cuda_stream) {
+    SKEL_PRE("acino_skel_pred_dev")
+    if (!x || !xt || !gtot || !H || !sw || !pred || !step) return fail(h, ACINO_ERR_ARG, "acino_skel_pred_dev: NULL pointer");
+    CK(launch_skel_pred(n_frames, P, x, xt, gtot, H, sw, pred, step, (cudaStream_t)cuda_stream));
+    h->launches += 1;
+    return ACINO_OK;
+}
 
 int acino_lm_prepare_dev(acino_handle* h, int n_frames, int64_t frame0, int64_t ng, const double* x_ext, const float* g,
                          const double* sw, const double* lo, const double* hi, double* gtot, uint8_t* fixed,

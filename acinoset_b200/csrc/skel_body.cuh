@@ -1,0 +1,447 @@
+// Generic-skeleton FTE (the data-driven variant of the reference, /root/reference/src/build.py:28-302), fp64.
+//
+// The bodies below are written as phase loops `for (t = ctx.tid; t < n; t += ctx.nthreads)` separated by ctx.sync():
+// on the GPU ctx is (threadIdx.x, blockDim.x, __syncthreads) - see skel.cu - and the very same source, compiled for
+// the host with ctx = (0, 1, no-op), is what tests/host_harness runs on the CPU to check the kernels against the
+// NumPy oracle before they ever see a GPU.  The harness is test infrastructure; the library has no host path.
+//
+// Forward kinematics of build.py:43-80 (quirks kept, see acinoset_b200/skeleton.py): a part's pose is the root
+// (x, y, z) plus one increment per link on its path, d_l = M_a tv_l, where M_a is the LOCAL rotation
+// Rz(psi_a) Rx(phi_a) Ry(theta_a) of the link's parent a (or its transpose, link flag) - rotations do not chain.
+// So d pose_r / d angle_k(a) = sum over the links l of a on r's path of D_{l,k} = (d M_a / d angle_k) tv_l, and
+//   g[a,k]          = sum_{l in links(a)} D_{l,k} . Sb_l            Sb_l      = sum_{r: l in path(r)} b_r
+//   H[(a,k),(a',k')] = sum_{l,l'} D_{l,k}^T SA_{l,l'} D_{l',k'}      SA_{l,l'} = sum_{r: l,l' in path(r)} A_r
+// with A_r, b_r the 3x3 normal block and gradient of output row r accumulated over the cameras.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SKEL_HD __host__ __device__ __forceinline__
+#else
+#define SKEL_HD inline
+#endif
+
+namespace acino {
+
+constexpr int SK_MAX_PARTS = 32;
+constexpr int SK_MAX_LINKS = 40;
+constexpr int SK_MAX_CAMS = 16;
+
+struct SkelCam {
+    double R[9], t[3], fx, fy, cx, cy, D[4];
+};
+
+struct SkelDesc {
+    int n_parts;                     // L: state is [x,y,z, phi_0..L-1, theta_0..L-1, psi_0..L-1], P = 3 + 3L
+    int n_links;
+    int n_out;                       // output rows (pose_dict order) = measured markers
+    int n_cams;
+    int dof_mask[SK_MAX_PARTS];      // bit0 phi (x), bit1 theta (y), bit2 psi (z)
+    int link_parent[SK_MAX_LINKS];
+    int link_flag[SK_MAX_LINKS];     // 1: parent's local rotation used transposed
+    double link_tv[SK_MAX_LINKS][3];
+    unsigned long long path[SK_MAX_PARTS];   // per output row: bit l set <=> link l is on its path
+    int part_ptr[SK_MAX_PARTS + 1];  // CSR: links whose parent is part a
+    int part_links[SK_MAX_LINKS];
+    int loss_kind;                   // 0: redescending(a,b,c) of |w r| (all_optimizations.py:497); 1: |w r| (build.py:299)
+    double la, lb, lc;               // redescending break points
+    double delta;                    // loss_kind 1: curvature weight 1 / max(|w r|, delta)
+    SkelCam cam[SK_MAX_CAMS];
+};
+
+// dynamic shared memory (doubles) of one frame
+struct SkelSmemLayout {
+    int d, D, pose, A, b, costp, Sb, SA, Atot, btot, total;
+    SKEL_HD SkelSmemLayout(int n_links, int n_out) {
+        int o = 0;
+        d = o; o += n_links * 3;
+        D = o; o += n_links * 9;
+        pose = o; o += n_out * 3;
+        A = o; o += n_out * 6;
+        b = o; o += n_out * 3;
+        costp = o; o += n_out;
+        Sb = o; o += n_links * 3;
+        SA = o; o += (n_links * (n_links + 1) / 2) * 6;
+        Atot = o; o += 6;
+        btot = o; o += 3;
+        total = o;
+    }
+};
+
+SKEL_HD int sk_pair_index(int l, int m, int n) {   // l <= m < n, row-major packed upper
+    return l * n - (l * (l - 1)) / 2 + (m - l);
+}
+
+// literal logistic blend of build.py:382-395 and its derivative, e >= 0
+SKEL_HD void sk_redescending(double a, double b, double c, double e, double& rho, double& drho, double& floor_) {
+    const double sa = 1.0 / (1.0 + exp(-(e - a))), sb = 1.0 / (1.0 + exp(-(e - b))), sc = 1.0 / (1.0 + exp(-(e - c)));
+    const double dsa = sa * (1 - sa), dsb = sb * (1 - sb), dsc = sc * (1 - sc);
+    const double p1 = 0.5 * e * e, p2 = a * e - a * a / 2;
+    const double u = (c - e) / (c - b), k3 = a * (c - b) / 2;
+    const double p3 = a * b - a * a / 2 + k3 * (1 - u * u), dp3 = a * u;
+    const double p4 = a * b - a * a / 2 + k3;
+    rho = (1 - sa) * p1 + (sa - sb) * p2 + (sb - sc) * p3 + sc * p4;
+    drho = (1 - sa) * e - dsa * p1 + (dsa - dsb) * p2 + (sa - sb) * a + (dsb - dsc) * p3 + (sb - sc) * dp3 + dsc * p4;
+    floor_ = 1 - sa;
+}
+
+// c = a b (3x3 row-major)
+SKEL_HD void sk_mm(const double* a, const double* b, double* c) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+
+// One frame: x [P] -> cost, g [P], H [P(P+1)/2] (packed upper, row-major); any output may be NULL.
+// meas [C][n_out][2], w [C][n_out].  sm: SkelSmemLayout(...).total doubles.
+template <typename Ctx>
+SKEL_HD void skel_eval_frame(const SkelDesc& S, const Ctx& ctx, const double* __restrict__ x, const double* __restrict__ meas,
+                             const double* __restrict__ w, double* __restrict__ cost, double* __restrict__ g,
+                             double* __restrict__ H, double* sm) {
+    const int L = S.n_parts, NLk = S.n_links, NO = S.n_out, P = 3 + 3 * L;
+    const SkelSmemLayout lay(NLk, NO);
+    double* s_d = sm + lay.d;
+    double* s_D = sm + lay.D;
+    double* s_pose = sm + lay.pose;
+    double* s_A = sm + lay.A;
+    double* s_b = sm + lay.b;
+    double* s_cost = sm + lay.costp;
+    double* s_Sb = sm + lay.Sb;
+    double* s_SA = sm + lay.SA;
+    double* s_Atot = sm + lay.Atot;
+    double* s_btot = sm + lay.btot;
+
+    // ---- S1: link increments and their derivatives w.r.t. the parent's (phi, theta, psi)
+    for (int l = ctx.tid; l < NLk; l += ctx.nthreads) {
+        const int a = S.link_parent[l], m = S.dof_mask[a];
+        const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double Ry[9], Rx[9], Rz[9], dRy[9], dRx[9], dRz[9];
+        for (int i = 0; i < 9; ++i) { Ry[i] = Rx[i] = Rz[i] = I3[i]; dRy[i] = dRx[i] = dRz[i] = Z3[i]; }
+        if (m & 2) {   // rot_y (build.py:407-414): [[c,0,-s],[0,1,0],[s,0,c]]
+            const double c = cos(x[3 + L + a]), s = sin(x[3 + L + a]);
+            Ry[0] = c; Ry[2] = -s; Ry[6] = s; Ry[8] = c;
+            dRy[0] = -s; dRy[2] = -c; dRy[6] = c; dRy[8] = -s;
+        }
+        if (m & 1) {   // rot_x (:399-405): [[1,0,0],[0,c,s],[0,-s,c]]
+            const double c = cos(x[3 + a]), s = sin(x[3 + a]);
+            Rx[4] = c; Rx[5] = s; Rx[7] = -s; Rx[8] = c;
+            dRx[4] = -s; dRx[5] = c; dRx[7] = -c; dRx[8] = -s;
+        }
+        if (m & 4) {   // rot_z (:416-423): [[c,s,0],[-s,c,0],[0,0,1]]
+            const double c = cos(x[3 + 2 * L + a]), s = sin(x[3 + 2 * L + a]);
+            Rz[0] = c; Rz[1] = s; Rz[3] = -s; Rz[4] = c;
+            dRz[0] = -s; dRz[1] = c; dRz[3] = -c; dRz[4] = -s;
+        }
+        double XY[9], dXY_phi[9], dXY_th[9], M[4][9];
+        sk_mm(Rx, Ry, XY);
+        sk_mm(dRx, Ry, dXY_phi);
+        sk_mm(Rx, dRy, dXY_th);
+        sk_mm(Rz, XY, M[0]);          // M = Rz Rx Ry  (build.py:54-59)
+        sk_mm(Rz, dXY_phi, M[1]);     // d/d phi
+        sk_mm(Rz, dXY_th, M[2]);      // d/d theta
+        sk_mm(dRz, XY, M[3]);         // d/d psi
+        const double* tv = S.link_tv[l];
+        const bool tr = S.link_flag[l] & 1;
+        for (int q = 0; q < 4; ++q) {
+            double* out = q == 0 ? s_d + 3 * l : s_D + 9 * l + 3 * (q - 1);
+            for (int i = 0; i < 3; ++i)
+                out[i] = tr ? (M[q][i] * tv[0] + M[q][3 + i] * tv[1] + M[q][6 + i] * tv[2])
+                            : (M[q][3 * i] * tv[0] + M[q][3 * i + 1] * tv[1] + M[q][3 * i + 2] * tv[2]);
+        }
+    }
+    ctx.sync();
+
+    // ---- S2 + S3: pose of every output row, then projection + loss over the cameras
+    for (int r = ctx.tid; r < NO; r += ctx.nthreads) {
+        double p0 = x[0], p1 = x[1], p2 = x[2];
+        const unsigned long long path = S.path[r];
+        for (int l = 0; l < NLk; ++l)
+            if ((path >> l) & 1ull) { p0 += s_d[3 * l]; p1 += s_d[3 * l + 1]; p2 += s_d[3 * l + 2]; }
+        s_pose[3 * r] = p0; s_pose[3 * r + 1] = p1; s_pose[3 * r + 2] = p2;
+        double A[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0}, cst = 0;
+        for (int c = 0; c < S.n_cams; ++c) {
+            const SkelCam& cam = S.cam[c];
+            const double wt = w[c * NO + r];
+            const double xc = cam.R[0] * p0 + cam.R[1] * p1 + cam.R[2] * p2 + cam.t[0];
+            const double yc = cam.R[3] * p0 + cam.R[4] * p1 + cam.R[5] * p2 + cam.t[1];
+            const double zc = cam.R[6] * p0 + cam.R[7] * p1 + cam.R[8] * p2 + cam.t[2];
+            // pt3d_to_2d (build.py:457-473) and its Jacobian w.r.t. the camera-frame point
+            const double iz = 1.0 / zc, aa = xc * iz, bb = yc * iz;
+            const double r2 = aa * aa + bb * bb + 1e-12, rr = sqrt(r2), ir = 1.0 / rr;
+            const double th = atan(rr), th2 = th * th;
+            const double td = th * (1 + th2 * (cam.D[0] + th2 * (cam.D[1] + th2 * (cam.D[2] + th2 * cam.D[3]))));
+            const double dtd = 1 + th2 * (3 * cam.D[0] + th2 * (5 * cam.D[1] + th2 * (7 * cam.D[2] + th2 * 9 * cam.D[3])));
+            const double sd = td * ir;
+            const double q = (dtd / (1 + r2) - sd) * (ir * ir);
+            const double m00 = sd + aa * aa * q, m01 = aa * bb * q, m11 = sd + bb * bb * q;
+            const double fxi = cam.fx * iz, fyi = cam.fy * iz;
+            const double ju[3] = {fxi * m00, fxi * m01, -fxi * (m00 * aa + m01 * bb)};
+            const double jv[3] = {fyi * m01, fyi * m11, -fyi * (m01 * aa + m11 * bb)};
+            double Ju[3], Jv[3];      // world-frame rows: j^T R
+            for (int j = 0; j < 3; ++j) {
+                Ju[j] = ju[0] * cam.R[j] + ju[1] * cam.R[3 + j] + ju[2] * cam.R[6 + j];
+                Jv[j] = jv[0] * cam.R[j] + jv[1] * cam.R[3 + j] + jv[2] * cam.R[6 + j];
+            }
+            const double res[2] = {wt != 0 ? cam.fx * aa * sd + cam.cx - meas[(c * NO + r) * 2] : 0.0,
+                                   wt != 0 ? cam.fy * bb * sd + cam.cy - meas[(c * NO + r) * 2 + 1] : 0.0};
+            for (int dd = 0; dd < 2; ++dd) {
+                const double* J = dd ? Jv : Ju;
+                const double e = fabs(wt * res[dd]);
+                double rho, gw, hw;     // d rho / d r = gw w^2 r ; curvature weight hw w^2
+                if (S.loss_kind == 0) {
+                    double drho, fl;
+                    sk_redescending(S.la, S.lb, S.lc, e, rho, drho, fl);
+                    gw = e > 0 ? drho / e : 0.0;
+                    hw = e > 0 ? fmax(gw, fl) : fl;
+                } else {
+                    rho = e;
+                    gw = e > 0 ? 1.0 / e : 0.0;
+                    hw = 1.0 / fmax(e, S.delta);
+                }
+                cst += rho;
+                const double w2 = wt * wt, gs = gw * w2 * res[dd], hs = hw * w2;
+                b[0] += gs * J[0]; b[1] += gs * J[1]; b[2] += gs * J[2];
+                A[0] += hs * J[0] * J[0]; A[1] += hs * J[0] * J[1]; A[2] += hs * J[0] * J[2];
+                A[3] += hs * J[1] * J[1]; A[4] += hs * J[1] * J[2]; A[5] += hs * J[2] * J[2];
+            }
+        }
+        for (int i = 0; i < 6; ++i) s_A[6 * r + i] = A[i];
+        for (int i = 0; i < 3; ++i) s_b[3 * r + i] = b[i];
+        s_cost[r] = cst;
+    }
+    ctx.sync();
+
+    // ---- S4: sums over the rows carried by each link / link pair (fixed order: rows ascending)
+    const int n_pairs = NLk * (NLk + 1) / 2;
+    for (int t = ctx.tid; t < n_pairs + NLk + 1; t += ctx.nthreads) {
+        if (t < n_pairs) {
+            int l = 0, rem = t;
+            while (rem >= NLk - l) { rem -= NLk - l; ++l; }
+            const int m = l + rem;
+            const unsigned long long need = (1ull << l) | (1ull << m);
+            double a[6] = {0, 0, 0, 0, 0, 0};
+            for (int r = 0; r < NO; ++r)
+                if ((S.path[r] & need) == need)
+                    for (int i = 0; i < 6; ++i) a[i] += s_A[6 * r + i];
+            for (int i = 0; i < 6; ++i) s_SA[6 * t + i] = a[i];
+        } else if (t < n_pairs + NLk) {
+            const int l = t - n_pairs;
+            double a[3] = {0, 0, 0};
+            for (int r = 0; r < NO; ++r)
+                if ((S.path[r] >> l) & 1ull)
+                    for (int i = 0; i < 3; ++i) a[i] += s_b[3 * r + i];
+            for (int i = 0; i < 3; ++i) s_Sb[3 * l + i] = a[i];
+        } else {
+            double a[6] = {0, 0, 0, 0, 0, 0}, bt[3] = {0, 0, 0}, c = 0;
+            for (int r = 0; r < NO; ++r) {
+                for (int i = 0; i < 6; ++i) a[i] += s_A[6 * r + i];
+                for (int i = 0; i < 3; ++i) bt[i] += s_b[3 * r + i];
+                c += s_cost[r];
+            }
+            for (int i = 0; i < 6; ++i) s_Atot[i] = a[i];
+            for (int i = 0; i < 3; ++i) s_btot[i] = bt[i];
+            if (cost) *cost = c;
+        }
+    }
+    ctx.sync();
+
+    // ---- S5: gradient and packed upper triangle.  slot p >= 3: k = (p-3) / L (0 phi, 1 theta, 2 psi), a = (p-3) % L
+    if (g)
+        for (int p = ctx.tid; p < P; p += ctx.nthreads) {
+            if (p < 3) { g[p] = s_btot[p]; continue; }
+            const int k = (p - 3) / L, a = (p - 3) - k * L;
+            double acc = 0;
+            for (int i = S.part_ptr[a]; i < S.part_ptr[a + 1]; ++i) {
+                const int l = S.part_links[i];
+                const double* Dk = s_D + 9 * l + 3 * k;
+                acc += Dk[0] * s_Sb[3 * l] + Dk[1] * s_Sb[3 * l + 1] + Dk[2] * s_Sb[3 * l + 2];
+            }
+            g[p] = acc;
+        }
+    if (H) {
+        const int NU = P * (P + 1) / 2;
+        for (int idx = ctx.tid; idx < NU; idx += ctx.nthreads) {
+            int p = 0, rem = idx;
+            while (rem >= P - p) { rem -= P - p; ++p; }
+            const int q = p + rem;
+            double acc = 0;
+            if (q < 3) {
+                const int ii = p == 0 ? q : (p == 1 ? 2 + q : 5);     // (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
+                acc = s_Atot[ii];
+            } else {
+                const int kq = (q - 3) / L, aq = (q - 3) - kq * L;
+                for (int i = S.part_ptr[aq]; i < S.part_ptr[aq + 1]; ++i) {
+                    const int lq = S.part_links[i];
+                    const double* Dq = s_D + 9 * lq + 3 * kq;
+                    if (p < 3) {
+                        const double* a = s_SA + 6 * sk_pair_index(lq, lq, NLk);
+                        const double row[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
+                        acc += row[p][0] * Dq[0] + row[p][1] * Dq[1] + row[p][2] * Dq[2];
+                    } else {
+                        const int kp = (p - 3) / L, ap = (p - 3) - kp * L;
+                        for (int j = S.part_ptr[ap]; j < S.part_ptr[ap + 1]; ++j) {
+                            const int lp = S.part_links[j];
+                            const double* Dp = s_D + 9 * lp + 3 * kp;
+                            const double* a = s_SA + 6 * (lp <= lq ? sk_pair_index(lp, lq, NLk) : sk_pair_index(lq, lp, NLk));
+                            const double y0 = a[0] * Dq[0] + a[1] * Dq[1] + a[2] * Dq[2];
+                            const double y1 = a[1] * Dq[0] + a[3] * Dq[1] + a[4] * Dq[2];
+                            const double y2 = a[2] * Dq[0] + a[4] * Dq[1] + a[5] * Dq[2];
+                            acc += Dp[0] * y0 + Dp[1] * y1 + Dp[2] * y2;
+                        }
+                    }
+                }
+            }
+            H[idx] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt building blocks for the generic variant.  Objective (build.py:287-302 with the dynamics of
+// :231-261 eliminated exactly like SURVEY.md B6): F = sum rho(w r) + sum_{n>=3,p} q_p (third difference / h^2)^2,
+// sw[p] = 2 q_p / h^4; box bounds lo/hi per slot (build.py:263-266), `last_free` = the reference's range(1, N) leaves
+// the last frame unbounded.
+
+SKEL_HD double sk_d3tsd3(const double* x, int N, int P, int n, int p) {   // (D3^T D3 x)[n][p]
+    const double c[4] = {1, -3, 3, -1};
+    double acc = 0;
+    for (int m = n > 3 ? n : 3; m <= n + 3 && m < N; ++m) {       // rows m use frames m..m-3, coefficient c[m - frame]
+        const double tdiff = x[(size_t)m * P + p] - 3 * x[(size_t)(m - 1) * P + p] + 3 * x[(size_t)(m - 2) * P + p] - x[(size_t)(m - 3) * P + p];
+        acc += c[m - n] * tdiff;
+    }
+    return acc;
+}
+
+SKEL_HD double sk_smooth_entry(int N, int n, int k) {   // (D3^T D3)[n][n-k], k = 0..3
+    const double c[4] = {1, -3, 3, -1};
+    double acc = 0;
+    for (int m = n > 3 ? n : 3; m <= n - k + 3 && m < N; ++m) acc += c[m - n] * c[m - (n - k)];
+    return acc;
+}
+
+// per (frame, slot): total gradient and the frozen flag; per frame: smoothness cost
+template <typename Ctx>
+SKEL_HD void skel_prepare(const Ctx& ctx, int N, int P, int last_free, const double* x, const double* g, const double* sw,
+                          const double* lo, const double* hi, double* gtot, unsigned char* fixed, double* cost_s) {
+    for (long long i = ctx.tid; i < (long long)N * P; i += ctx.nthreads) {
+        const int n = (int)(i / P), p = (int)(i - (long long)n * P);
+        const double gt = g[i] + sw[p] * sk_d3tsd3(x, N, P, n, p);
+        gtot[i] = gt;
+        const bool bounded = !(last_free && n == N - 1);
+        fixed[i] = bounded && ((x[i] <= lo[p] && gt > 0) || (x[i] >= hi[p] && gt < 0));
+    }
+    for (int n = ctx.tid; n < N; n += ctx.nthreads) {
+        double c = 0;
+        if (n >= 3)
+            for (int p = 0; p < P; ++p) {
+                const double td = x[(size_t)n * P + p] - 3 * x[(size_t)(n - 1) * P + p] + 3 * x[(size_t)(n - 2) * P + p] - x[(size_t)(n - 3) * P + p];
+                c += 0.5 * sw[p] * td * td;
+            }
+        cost_s[n] = c;
+    }
+}
+
+// lower band of (B + lam diag B) with frozen rows/columns replaced by identity; AB [N P][3P + 1], AB[i][k] = B[i][i-k]
+template <typename Ctx>
+SKEL_HD void skel_assemble(const Ctx& ctx, int N, int P, const double* H, const double* gtot, const unsigned char* fixed,
+                           const double* sw, double lam, double* AB, double* rhs) {
+    const int hb = 3 * P, W = hb + 1;
+    const long long n_rows = (long long)N * P;
+    for (long long e = ctx.tid; e < n_rows * W; e += ctx.nthreads) {
+        const long long i = e / W;
+        const int k = (int)(e - i * W);
+        const long long j = i - k;
+        double v = 0;
+        if (j >= 0) {
+            const int n = (int)(i / P), p = (int)(i - (long long)n * P);
+            const int nj = (int)(j / P), pj = (int)(j - (long long)nj * P);
+            if (nj == n) v = H[(size_t)n * (P * (P + 1) / 2) + (pj * P - (pj * (pj - 1)) / 2 + (p - pj))];
+            if (pj == p) v += sw[p] * sk_smooth_entry(N, n, n - nj);
+            if (k == 0) v *= 1 + lam;
+            if (fixed[i] || fixed[j]) v = k == 0 ? 1.0 : 0.0;
+        }
+        AB[e] = v;
+    }
+    for (long long i = ctx.tid; i < n_rows; i += ctx.nthreads) rhs[i] = fixed[i] ? 0.0 : -gtot[i];
+}
+
+// In-place band Cholesky B = L L^T (row-wise lower band storage, half bandwidth hb) and solve of B x = rhs.
+// ONE cooperating group of threads (a CTA); right-looking, column by column.  info = first non-positive pivot + 1.
+template <typename Ctx>
+SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, double* AB, double* x, int* info) {
+    const int W = hb + 1;
+    for (long long j = 0; j < n; ++j) {
+        const double djj = AB[j * W];
+        if (!(djj > 0)) {
+            if (ctx.tid == 0 && *info == 0) *info = (int)(j + 1);
+            return;                                    // uniform: every thread reads the same pivot
+        }
+        const double inv = 1.0 / sqrt(djj);
+        const int m = (int)((n - 1 - j) < hb ? (n - 1 - j) : hb);   // rows below the pivot inside the band
+        ctx.sync();                                    // every thread has read the pivot
+        for (int r = ctx.tid; r <= m; r += ctx.nthreads) AB[(j + r) * W + r] *= inv;      // column j (r = 0: the pivot)
+        ctx.sync();
+        // trailing update: B[j+r][j+c] -= L[j+r][j] L[j+c][j], 1 <= c <= r <= m
+        for (int e = ctx.tid; e < m * m; e += ctx.nthreads) {
+            const int r = e / m + 1, c = e - (r - 1) * m + 1;
+            if (c <= r) AB[(j + r) * W + (r - c)] -= AB[(j + r) * W + r] * AB[(j + c) * W + c];
+        }
+        ctx.sync();                                    // the next pivot is final
+    }
+    // forward L y = rhs, backward L^T x = y: one thread (n hb flops; the factorisation above dominates)
+    if (ctx.tid == 0) {
+        for (long long i = 0; i < n; ++i) {
+            double s = x[i];
+            const int kk = (int)(i < hb ? i : hb);
+            for (int k = 1; k <= kk; ++k) s -= AB[i * W + k] * x[i - k];
+            x[i] = s / AB[i * W];
+        }
+        for (long long i = n - 1; i >= 0; --i) {
+            double s = x[i];
+            const int kk = (int)((n - 1 - i) < hb ? (n - 1 - i) : hb);
+            for (int k = 1; k <= kk; ++k) s -= AB[(i + k) * W + k] * x[i + k];
+            x[i] = s / AB[i * W];
+        }
+    }
+    ctx.sync();
+}
+
+// trial point xt = clip(x + d)
+template <typename Ctx>
+SKEL_HD void skel_trial(const Ctx& ctx, int N, int P, int last_free, const double* x, const double* d, const double* lo,
+                        const double* hi, double* xt) {
+    for (long long i = ctx.tid; i < (long long)N * P; i += ctx.nthreads) {
+        const int n = (int)(i / P), p = (int)(i - (long long)n * P);
+        double v = x[i] + d[i];
+        if (!(last_free && n == N - 1)) v = fmin(fmax(v, lo[p]), hi[p]);
+        xt[i] = v;
+    }
+}
+
+// quadratic-model reduction and step norm per frame, s = xt - x:
+//   pred[n] = -(gtot . s) - 1/2 s^T H_n s - 1/2 sw (D3 s)_n^2, step[n] = max |s|
+template <typename Ctx>
+SKEL_HD void skel_pred(const Ctx& ctx, int N, int P, const double* x, const double* xt, const double* gtot, const double* H,
+                       const double* sw, double* pred, double* step) {
+    for (int n = ctx.tid; n < N; n += ctx.nthreads) {
+        const double* Hn = H + (size_t)n * (P * (P + 1) / 2);
+        double lin = 0, quad = 0, smax = 0;
+        for (int p = 0; p < P; ++p) {
+            const double sp = xt[(size_t)n * P + p] - x[(size_t)n * P + p];
+            lin += gtot[(size_t)n * P + p] * sp;
+            smax = fmax(smax, fabs(sp));
+            double row = 0.5 * Hn[p * P - (p * (p - 1)) / 2] * sp;
+            for (int q = p + 1; q < P; ++q) row += Hn[p * P - (p * (p - 1)) / 2 + (q - p)] * (xt[(size_t)n * P + q] - x[(size_t)n * P + q]);
+            quad += sp * row;
+            if (n >= 3) {
+                const double td = (xt[(size_t)n * P + p] - x[(size_t)n * P + p]) - 3 * (xt[(size_t)(n - 1) * P + p] - x[(size_t)(n - 1) * P + p]) +
+                                  3 * (xt[(size_t)(n - 2) * P + p] - x[(size_t)(n - 2) * P + p]) - (xt[(size_t)(n - 3) * P + p] - x[(size_t)(n - 3) * P + p]);
+                quad += 0.5 * sw[p] * td * td;
+            }
+        }
+        pred[n] = -lin - quad;
+        step[n] = smax;
+    }
+}
+
+}  // namespace acino

@@ -42,15 +42,19 @@ def flatten_skeleton(skel_dict):
                         dtype=np.int32)
     transposed = {p: True for p in parts}       # rot_dict[p + "_i"] starts as the transpose (build.py:61)
     out_order, lp, lc, lf, tv = [], [], [], [], []
+    path = {}                                   # part -> bitmask of the links whose increments sum to its pose
     for link in links:
         if len(link) == 1:
             if link[0] not in out_order:
                 out_order.append(link[0])
+            path[link[0]] = 0
             continue
         a, b = link
         if a not in out_order:
             out_order.append(a)
+            path[a] = 0
         transposed[b] = not transposed[b]       # build.py:79 (before the pose of b is formed)
+        path[b] = path[a] | (1 << len(lp))      # build.py:80: pose[b] = pose[a] (as it is NOW) + this link's increment
         lp.append(idx[a])
         lc.append(idx[b])
         lf.append(1 if transposed[a] else 0)
@@ -60,7 +64,7 @@ def flatten_skeleton(skel_dict):
     return dict(parts=parts, dof_mask=dof_mask, link_parent=np.array(lp, dtype=np.int32),
                 link_child=np.array(lc, dtype=np.int32), link_flags=np.array(lf, dtype=np.int32),
                 link_tv=np.array(tv, dtype=np.float64).reshape(-1, 3), out_order=[idx[p] for p in out_order],
-                out_names=out_order)
+                out_names=out_order, out_path=np.array([path[p] for p in out_order], dtype=np.uint64))
 
 
 def build_pose_function(skel_dict, device=0):

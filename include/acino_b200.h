@@ -145,6 +145,47 @@ int acino_generic_fk(acino_handle* h, int n_frames, int n_parts, int n_links, co
                      const int32_t* link_parent, const int32_t* link_child, const int32_t* link_flags,
                      const double* link_tv, const double* x, double* pos);
 
+/* ---- generic-skeleton FTE: the data-driven variant of the reference (src/build.py:28-332), fp64 ---------------
+ * Any skeleton pickle {links, dofs, positions, markers}; state per frame x [P], P = 3 + 3 n_parts =
+ * [x,y,z, phi_0.., theta_0.., psi_0..] (build.py:47-49,88); output rows = parts in pose_dict order (:82-86), which
+ * the reference pairs index-by-index with the measured markers (:189-198,276-285).
+ * acino_skel_set: the flattened builder tables of acinoset_b200/skeleton.py (see acino_generic_fk) plus, per output
+ * row, path = bit mask of the links whose increments sum to its pose; cameras come from acino_set_cameras (call it
+ * first).  loss_kind 0: redescending_loss(|w r|, a, b, c) (all_optimizations.py:497); 1: |w r| (build.py:299) with
+ * Gauss-Newton curvature weight 1 / max(|w r|, delta).  n_parts, n_out <= 32, n_links <= 40. */
+int acino_skel_set(acino_handle* h, int n_parts, int n_links, int n_out, const int32_t* dof_mask,
+                   const int32_t* link_parent, const int32_t* link_flag, const double* link_tv,
+                   const uint64_t* path, int loss_kind, double a, double b, double c, double delta);
+/* Replaces pose_constraint + measurement_constraints + the measurement term of obj (build.py:219-224,276-285,
+ * 294-300) and their differentiation:  x [N][P], meas [N][C][n_out][2], w [N][C][n_out] (meas_err_weight,
+ * :166-172; 0 = skipped) -> cost [N], g [N][P], H [N][P(P+1)/2] packed upper triangle of sum psi w^2 J^T J.
+ * Any output may be NULL.  _dev: device pointers, stream-ordered; the other: host pointers. */
+int acino_skel_eval_dev(acino_handle* h, int n_frames, const double* x, const double* meas,
+                        const double* w, double* cost, double* g, double* H, void* cuda_stream);
+int acino_skel_eval(acino_handle* h, int n_frames, const double* x, const double* meas, const double* w,
+                    double* cost, double* g, double* H);
+/* Levenberg-Marquardt building blocks replacing opt.solve (build.py:306-332) on
+ *   F = sum rho(w r) + sum_{n>=3,p} q_p (third difference / h^2)^2     (backwards_euler_* + constant_acc, :231-261)
+ * sw [P] = 2 q_p / h^4 (q_p = 0.002, :173-177), lo / hi [P] box bounds (:263-266), last_free = 1: the last frame is
+ * unbounded like the reference's range(1, N).  fixed [N][P]: variables frozen at a bound; cost_s [N] smoothness cost.
+ * AB [N P][3P + 1] row-wise lower band of (B + lambda diag B), AB[i][k] = B[i][i-k]; rhs [N P] = -gradient. */
+int acino_skel_prepare_dev(acino_handle* h, int n_frames, int last_free, const double* x, const double* g,
+                           const double* sw, const double* lo, const double* hi, double* gtot,
+                           uint8_t* fixed, double* cost_s, void* cuda_stream);
+int acino_skel_assemble_dev(acino_handle* h, int n_frames, const double* H, const double* gtot,
+                            const uint8_t* fixed, const double* sw, double lambda, double* AB,
+                            double* rhs, void* cuda_stream);
+/* in-place band Cholesky of AB [n][half_bandwidth + 1] and solve: x (rhs in, solution out); info != 0: index + 1
+ * of the first non-positive pivot (AB, x then undefined) */
+int acino_band_solve_dev(acino_handle* h, int64_t n, int half_bandwidth, double* AB, double* x,
+                         int32_t* info, void* cuda_stream);
+int acino_skel_trial_dev(acino_handle* h, int n_frames, int last_free, const double* x, const double* d,
+                         const double* lo, const double* hi, double* xt, void* cuda_stream);
+/* pred [N]: decrease of the quadratic model for s = xt - x; step [N] = max |s| per frame */
+int acino_skel_pred_dev(acino_handle* h, int n_frames, const double* x, const double* xt,
+                        const double* gtot, const double* H, const double* sw, double* pred,
+                        double* step, void* cuda_stream);
+
 /* ---- FTE solve building blocks (device pointers, stream-ordered) ------------------------------
  * Together they replace `opt.solve(m)` (all_optimizations.py:503-524): a projected
  * Levenberg-Marquardt loop on  F(x) = sum rho(w r) + sum_{n>=3,p} q_p (third difference / Ts^2)^2

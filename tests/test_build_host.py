@@ -1,0 +1,82 @@
+"""CPU: host logic of the generic-skeleton variant (acinoset_b200/build.py, skeleton.py) - no GPU calls."""
+import json
+
+import numpy as np
+
+from conftest import golden
+from oracle import skel_fte
+
+
+def _skel(tag="K1"):
+    return json.loads(str(golden("generic_fk.npz")[tag + "_skeleton_json"]))
+
+
+def test_path_masks_reproduce_the_builder_fk():
+    """pose_r = root + sum of the link increments named by out_path[r] (incl. the twice-assigned hip1)."""
+    from acinoset_b200 import skeleton
+
+    for tag in ("K1", "K2"):
+        skel = _skel(tag)
+        flat = skeleton.flatten_skeleton(skel)
+        f, names = skel_fte.pose_function(skel)
+        assert names == flat["out_names"]
+        x = np.array(golden("generic_fk.npz")[tag + "_x"][3], dtype=np.float64)
+        L = len(flat["parts"])
+        inc = []
+        for l in range(len(flat["link_parent"])):
+            a = flat["link_parent"][l]
+            M = np.eye(3)
+            m = flat["dof_mask"][a]
+            if m & 2:
+                M = skel_fte._rot(1, x[3 + L + a]) @ M
+            if m & 1:
+                M = skel_fte._rot(0, x[3 + a]) @ M
+            if m & 4:
+                M = skel_fte._rot(2, x[3 + 2 * L + a]) @ M
+            inc.append((M.T if flat["link_flags"][l] else M) @ flat["link_tv"][l])
+        pos = np.array([x[:3] + sum((inc[l] for l in range(len(inc)) if (int(flat["out_path"][r]) >> l) & 1), np.zeros(3))
+                        for r in range(len(names))])
+        assert np.abs(pos - f(x)).max() < 1e-14
+        # hip2 -> hip1 overwrites shoulder1 -> hip1 (build.py:80): knee1 hangs off the second assignment
+        k1, h2 = names.index("knee1"), names.index("hip2")
+        assert int(flat["out_path"][k1]) & int(flat["out_path"][h2]) == int(flat["out_path"][h2])
+
+
+def test_model_from_arrays_pairing_and_weights():
+    from acinoset_b200 import build
+
+    skel = _skel("K1")
+    markers = list(skel["markers"])
+    rng = np.random.default_rng(0)
+    N, C = 4, 3
+    meas = rng.normal(size=(N, C, len(markers), 2))
+    lik = rng.uniform(0, 1, (N, C, len(markers)))
+    K = np.tile(np.eye(3), (C, 1, 1))
+    cams = (K, np.zeros((C, 4)), K.copy(), np.zeros((C, 3)))
+    m = build.model_from_arrays(skel, cams, meas, lik, pair_by="index")
+    names = m.flat["out_names"]
+    assert m.P == 3 + 3 * 15 and m.N == N and m.x0.shape == (N, 48)
+    for r in range(len(names)):
+        if markers[r] == "neck":
+            assert np.all(m.w[:, :, r] == 0)
+        else:                                       # FK row r is compared with DLC marker markers[r] (by index)
+            assert np.array_equal(m.meas[:, :, r], meas[:, :, r])
+            assert np.array_equal(m.w[:, :, r] > 0, lik[:, :, r] > 0.4)
+            assert set(np.unique(m.w[:, :, r])) <= {0.0, 1.0 / 3.0}
+    mn = build.model_from_arrays(skel, cams, meas, lik, pair_by="name")
+    for r, nm in enumerate(names):
+        if nm == "neck":
+            assert np.all(mn.w[:, :, r] == 0)
+        else:
+            assert np.array_equal(mn.meas[:, :, r], meas[:, :, markers.index(nm)])
+    lo, hi = build.bounds(15)
+    lo2, hi2 = skel_fte.bounds(15)
+    assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
+    assert lo[2] == -np.pi / 2 and np.isinf(lo[0]) and np.isinf(lo[3 * 15 - 1]) and lo[3 * 15 - 2] == -np.pi / 2
+
+
+def test_redescending_loss_name_matches_reference_vectors():
+    from acinoset_b200 import build
+
+    g = golden("loss.npz")
+    assert np.abs(build.redescending_loss(g["e"], 3, 10, 20) - g["rho_3_10_20"]).max() < 1e-12
