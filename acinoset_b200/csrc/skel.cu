@@ -47,9 +47,11 @@ __global__ void skel_assemble_kernel(int N, int P, const double* H, const double
     skel_assemble(ctx, N, P, H, gtot, fixed, sw, lam, AB, rhs);
 }
 
+constexpr int BAND_NB = 16;     // panel width of the blocked band Cholesky
 __global__ void __launch_bounds__(1024) band_solve_kernel(long long n, int hb, double* AB, double* x, int* info) {
+    extern __shared__ double band_sm[];
     const CtaCtx ctx{(int)threadIdx.x, (int)blockDim.x};
-    band_cholesky_solve(ctx, n, hb, AB, x, info);
+    band_cholesky_solve(ctx, n, hb, BAND_NB, AB, x, info, band_sm);
 }
 
 __global__ void skel_trial_kernel(int N, int P, int last_free, const double* x, const double* d, const double* lo,
@@ -96,7 +98,14 @@ cudaError_t launch_skel_assemble(int N, int P, const double* H, const double* gt
     return cudaGetLastError();
 }
 cudaError_t launch_band_solve(long long n, int hb, double* AB, double* x, int* info, cudaStream_t s) {
-    band_solve_kernel<<<1, 1024, 0, s>>>(n, hb, AB, x, info);
+    const size_t smem = band_panel_doubles(hb, BAND_NB) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    band_solve_kernel<<<1, 1024, smem, s>>>(n, hb, AB, x, info);
     return cudaGetLastError();
 }
 cudaError_t launch_skel_trial(int N, int P, int last_free, const double* x, const double* d, const double* lo,

@@ -365,45 +365,110 @@ SKEL_HD void skel_assemble(const Ctx& ctx, int N, int P, const double* H, const 
     for (long long i = ctx.tid; i < n_rows; i += ctx.nthreads) rhs[i] = fixed[i] ? 0.0 : -gtot[i];
 }
 
-// In-place band Cholesky B = L L^T (row-wise lower band storage, half bandwidth hb) and solve of B x = rhs.
-// ONE cooperating group of threads (a CTA); right-looking, column by column.  info = first non-positive pivot + 1.
+// In-place band Cholesky B = L L^T (row-wise lower band storage AB[i][k] = B[i][i-k], half bandwidth hb) and solve of
+// B x = rhs, by ONE cooperating group of threads (a CTA).  Blocked right-looking: a panel of nb columns (rows
+// j0 .. j0+nb-1+hb) is staged in shared memory and factored there; the trailing band is then updated ONCE per panel
+// (rank-nb), so every entry of the band makes one global round trip per panel instead of one per column.  The
+// right-hand side rides along as an extra row of the matrix (forward substitution for free); the backward
+// substitution walks the panels right to left.  info = index + 1 of the first non-positive pivot.
+// sm: (nb + hb) * (nb + 1) + nb doubles.
+SKEL_HD size_t band_panel_doubles(int hb, int nb) { return (size_t)(nb + hb) * (nb + 1) + nb; }
+
 template <typename Ctx>
-SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, double* AB, double* x, int* info) {
-    const int W = hb + 1;
-    for (long long j = 0; j < n; ++j) {
-        const double djj = AB[j * W];
-        if (!(djj > 0)) {
-            if (ctx.tid == 0 && *info == 0) *info = (int)(j + 1);
-            return;                                    // uniform: every thread reads the same pivot
+SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, double* AB, double* x, int* info, double* sm) {
+    const int W = hb + 1, LD = nb + 1;
+    double* Lp = sm;                                   // [(nb + hb)][LD] panel rows, column c at Lp[r * LD + c]
+    double* yp = sm + (size_t)(nb + hb) * LD;          // [nb] right-hand side of the panel columns
+    for (long long j0 = 0; j0 < n; j0 += nb) {
+        const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
+        const long long j1 = j0 + nbp;
+        const long long rmax = (j1 - 1 + hb) < (n - 1) ? (j1 - 1 + hb) : (n - 1);
+        const int Rn = (int)(rmax - j0 + 1);           // panel rows
+        // ---- A: stage the panel
+        for (int e = ctx.tid; e < Rn * nbp; e += ctx.nthreads) {
+            const int r = e / nbp, c = e - r * nbp;
+            const int k = r - c;                       // distance below the diagonal of column j0 + c
+            Lp[r * LD + c] = (k >= 0 && k <= hb) ? AB[(j0 + r) * W + k] : 0.0;
         }
-        const double inv = 1.0 / sqrt(djj);
-        const int m = (int)((n - 1 - j) < hb ? (n - 1 - j) : hb);   // rows below the pivot inside the band
-        ctx.sync();                                    // every thread has read the pivot
-        for (int r = ctx.tid; r <= m; r += ctx.nthreads) AB[(j + r) * W + r] *= inv;      // column j (r = 0: the pivot)
+        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) yp[c] = x[j0 + c];
         ctx.sync();
-        // trailing update: B[j+r][j+c] -= L[j+r][j] L[j+c][j], 1 <= c <= r <= m
-        for (int e = ctx.tid; e < m * m; e += ctx.nthreads) {
-            const int r = e / m + 1, c = e - (r - 1) * m + 1;
-            if (c <= r) AB[(j + r) * W + (r - c)] -= AB[(j + r) * W + r] * AB[(j + c) * W + c];
+        // ---- B: factor the panel in shared memory, column by column
+        for (int c = 0; c < nbp; ++c) {
+            const double piv = Lp[c * LD + c];
+            if (!(piv > 0)) {
+                if (ctx.tid == 0 && *info == 0) *info = (int)(j0 + c + 1);
+                return;                                // uniform: every thread reads the same pivot
+            }
+            const double inv = 1.0 / sqrt(piv);
+            ctx.sync();                                // every thread has read the pivot
+            for (int r = c + ctx.tid; r <= Rn; r += ctx.nthreads) {
+                if (r < Rn) Lp[r * LD + c] *= inv;
+                else yp[c] *= inv;                     // the right-hand side "row"
+            }
+            ctx.sync();
+            const int nc = nbp - 1 - c;                // panel columns right of c
+            for (int e = ctx.tid; e < (Rn - c) * nc; e += ctx.nthreads) {   // rows c+1 .. Rn (Rn = rhs row), columns c+1 ..
+                const int rr = e / nc, cc = c + 1 + (e - rr * nc);
+                const int r = c + 1 + rr;
+                const double m = Lp[cc * LD + c];
+                if (r < Rn) {
+                    if (r >= cc) Lp[r * LD + cc] -= Lp[r * LD + c] * m;
+                } else {
+                    yp[cc] -= yp[c] * m;
+                }
+            }
+            ctx.sync();
         }
-        ctx.sync();                                    // the next pivot is final
+        // ---- C: write the panel back; rank-nbp update of the trailing band and of the right-hand side
+        for (int e = ctx.tid; e < Rn * nbp; e += ctx.nthreads) {
+            const int r = e / nbp, c = e - r * nbp;
+            const int k = r - c;
+            if (k >= 0 && k <= hb) AB[(j0 + r) * W + k] = Lp[r * LD + c];
+        }
+        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) x[j0 + c] = yp[c];
+        const int T = (int)(rmax - j1 + 1);            // trailing rows j1 .. rmax
+        for (int e = ctx.tid; e < T * (T + 1); e += ctx.nthreads) {
+            const int a = e / (T + 1), b = e - a * (T + 1);      // b == T: the right-hand side
+            const double* La = Lp + (size_t)(nbp + a) * LD;
+            if (b == T) {
+                double acc = 0;
+                for (int c = 0; c < nbp; ++c) acc += La[c] * yp[c];
+                x[j1 + a] -= acc;
+            } else if (b <= a) {
+                const double* Lb = Lp + (size_t)(nbp + b) * LD;
+                double acc = 0;
+                for (int c = 0; c < nbp; ++c) acc += La[c] * Lb[c];
+                AB[(j1 + a) * W + (a - b)] -= acc;
+            }
+        }
+        ctx.sync();
     }
-    // forward L y = rhs, backward L^T x = y: one thread (n hb flops; the factorisation above dominates)
-    if (ctx.tid == 0) {
-        for (long long i = 0; i < n; ++i) {
-            double s = x[i];
-            const int kk = (int)(i < hb ? i : hb);
-            for (int k = 1; k <= kk; ++k) s -= AB[i * W + k] * x[i - k];
-            x[i] = s / AB[i * W];
+    // ---- backward substitution L^T x = y, panels right to left
+    const long long n_panels = (n + nb - 1) / nb;
+    for (long long p = n_panels - 1; p >= 0; --p) {
+        const long long j0 = p * nb;
+        const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
+        const long long j1 = j0 + nbp;
+        // contributions of the already solved rows i >= j1 to each panel column
+        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) {
+            const long long j = j0 + c;
+            const long long imax = (j + hb) < (n - 1) ? (j + hb) : (n - 1);
+            double acc = 0;
+            for (long long i = j1; i <= imax; ++i) acc += AB[i * W + (i - j)] * x[i];
+            yp[c] = x[j] - acc;
         }
-        for (long long i = n - 1; i >= 0; --i) {
-            double s = x[i];
-            const int kk = (int)((n - 1 - i) < hb ? (n - 1 - i) : hb);
-            for (int k = 1; k <= kk; ++k) s -= AB[(i + k) * W + k] * x[i + k];
-            x[i] = s / AB[i * W];
+        ctx.sync();
+        if (ctx.tid == 0) {                            // nbp x nbp triangle
+            for (int c = nbp - 1; c >= 0; --c) {
+                double sacc = yp[c];
+                for (int r = c + 1; r < nbp && r - c <= hb; ++r) sacc -= AB[(j0 + r) * W + (r - c)] * yp[r];
+                yp[c] = sacc / AB[(j0 + c) * W];
+            }
         }
+        ctx.sync();
+        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) x[j0 + c] = yp[c];
+        ctx.sync();
     }
-    ctx.sync();
 }
 
 // trial point xt = clip(x + d)

@@ -66,7 +66,10 @@ void skel_host_assemble(int N, int P, const double* H, const double* gtot, const
                         double lam, double* AB, double* rhs) {
     skel_assemble(HostCtx(), N, P, H, gtot, fixed, sw, lam, AB, rhs);
 }
-void skel_host_band_solve(long long n, int hb, double* AB, double* x, int* info) { band_cholesky_solve(HostCtx(), n, hb, AB, x, info); }
+void skel_host_band_solve(long long n, int hb, int nb, double* AB, double* x, int* info) {
+    std::vector<double> sm(band_panel_doubles(hb, nb));
+    band_cholesky_solve(HostCtx(), n, hb, nb, AB, x, info, sm.data());
+}
 void skel_host_trial(int N, int P, int last_free, const double* x, const double* d, const double* lo, const double* hi, double* xt) {
     skel_trial(HostCtx(), N, P, last_free, x, d, lo, hi, xt);
 }

@@ -127,9 +127,17 @@ def test_lm_building_blocks_match_dense_algebra(harness, dummy_cams):
     assert np.abs(dense - Bd).max() < 1e-12 * np.abs(Bd).max()
     d_ref = np.linalg.solve(Bd, np.where(f, 0.0, -gt_ref.ravel()))
     info = np.zeros(1, dtype=np.int32)
-    harness.skel_host_band_solve(ctypes.c_longlong(N * P), hb, _ptr(AB), _ptr(rhs), _ptr(info))
-    assert info[0] == 0
-    assert np.abs(rhs - d_ref).max() < 1e-8 * np.abs(d_ref).max()
+    for nb in (16, 7, 1):                     # the kernel's panel width, a ragged one, and the unblocked limit
+        ABc, xs = AB.copy(), rhs.copy()
+        info[:] = 0
+        harness.skel_host_band_solve(ctypes.c_longlong(N * P), hb, nb, _ptr(ABc), _ptr(xs), _ptr(info))
+        assert info[0] == 0
+        assert np.abs(xs - d_ref).max() < 1e-8 * np.abs(d_ref).max()
+    Lf = np.linalg.cholesky(Bd)               # the band holds the Cholesky factor itself
+    for i in range(0, N * P, 37):
+        for k in range(min(i, hb) + 1):
+            assert abs(ABc[i, k] - Lf[i, i - k]) < 1e-9 * max(1.0, abs(Lf[i, i - k]))
+    rhs = xs
     xt = np.zeros_like(x)
     d = rhs.reshape(N, P).copy()
     harness.skel_host_trial(N, P, 1, _ptr(x), _ptr(d), _ptr(lo), _ptr(hi), _ptr(xt))
@@ -146,5 +154,27 @@ def test_lm_building_blocks_match_dense_algebra(harness, dummy_cams):
     bad = np.array([[1.0, 0.0], [0.5, 2.0]])     # B = [[1,2],[2,0.5]]: second pivot 0.5 - 4 < 0
     xb = np.ones(2)
     info[:] = 0
-    harness.skel_host_band_solve(ctypes.c_longlong(2), 1, _ptr(bad), _ptr(xb), _ptr(info))
+    harness.skel_host_band_solve(ctypes.c_longlong(2), 1, 16, _ptr(bad), _ptr(xb), _ptr(info))
     assert info[0] == 2
+
+
+def test_band_cholesky_random_systems(harness):
+    """Blocked band Cholesky + substitution on random SPD band systems, sizes that are not multiples of the panel."""
+    rng = np.random.default_rng(4)
+    for n, hb, nb in [(1, 0, 16), (5, 2, 16), (50, 7, 16), (131, 20, 16), (200, 45, 8), (64, 63, 16), (97, 30, 32)]:
+        A = np.zeros((n, n))
+        for i in range(n):
+            for k in range(1, min(i, hb) + 1):
+                A[i, i - k] = A[i - k, i] = rng.normal()
+        A += np.diag(np.abs(A).sum(1) + rng.uniform(0.5, 2.0, n))
+        AB = np.zeros((n, hb + 1))
+        for i in range(n):
+            for k in range(min(i, hb) + 1):
+                AB[i, k] = A[i, i - k]
+        b = rng.normal(size=n)
+        x = b.copy()
+        info = np.zeros(1, dtype=np.int32)
+        harness.skel_host_band_solve(ctypes.c_longlong(n), hb, nb, _ptr(AB), _ptr(x), _ptr(info))
+        assert info[0] == 0
+        ref = np.linalg.solve(A, b)
+        assert np.abs(x - ref).max() < 1e-10 * max(1.0, np.abs(ref).max()), (n, hb, nb)
