@@ -32,6 +32,7 @@
 
 namespace acino {
 
+constexpr int PREFETCH_DIST = 148 * 4;   // tiles one resident wave ahead (experiment, ACINO_FTE_EXP bit 0)
 constexpr int N_PAIR = NANG * (NANG + 1) / 2;  // 253 unordered angle pairs (incl. the diagonal)
 
 // One entry per unordered pair of angle slots.  Related pairs (one joint is an ancestor-or-self of
@@ -210,6 +211,16 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             issue_x(tile, 0, true);
             issue_mw(tile);
         }
+        // experiment (use_bulk bit 2): pull the inputs of the tile that will run in this CTA slot one wave later into
+        // L2, so that its own bulk copies do not pay the full HBM latency at CTA start
+        if (!PERSIST && (use_bulk & 4)) {
+            const int tp = tile + PREFETCH_DIST;
+            if ((tp + 1) * FT <= n_frames) {
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xg + (size_t)tp * FT * NA), "r"(bx) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(meas + (size_t)tp * FT * C * NL * 2), "r"(FT * bm) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wts + (size_t)tp * FT * C * NL), "r"(FT * bw) : "memory");
+            }
+        }
     }
     if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
     bool tab_ready = false;
@@ -244,7 +255,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     for (int t = tid; t < FT * NANG; t += NT) {
         const int a = t / FT, f = t - a * FT;
         float sn, cs;
-        sincosf(Sx[f][3 + a], &sn, &cs);
+        if (use_bulk & 8) {            // experiment: range-reduced MUFU sin / cos
+            const float xa = Sx[f][3 + a];
+            const float xr = fmaf(-6.283185307179586f, rintf(xa * 0.15915494309189535f), xa);
+            sn = __sinf(xr);
+            cs = __cosf(xr);
+        } else {
+            sincosf(Sx[f][3 + a], &sn, &cs);
+        }
         S.sc[f][a] = make_float2(sn, cs);
     }
     __syncthreads();
@@ -645,8 +663,15 @@ static cudaError_t launch_fte_eval_k(FteKernel kH, FteKernel kN, int ctas_per_sm
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
     // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
-    const int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
-                         (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
+    static int g_exp = -1;               // ACINO_FTE_EXP: bit 0 L2 prefetch of a later tile, bit 1 MUFU sin / cos
+    if (g_exp < 0) {
+        const char* e = getenv("ACINO_FTE_EXP");
+        g_exp = e ? atoi(e) : 0;
+    }
+    int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
+                   (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
+    if ((g_exp & 1) && (use_bulk & 1)) use_bulk |= 4;
+    if (g_exp & 2) use_bulk |= 8;
     const int n_tiles = (n_frames + FT - 1) / FT;
     int grid = n_tiles;
     if (PERSIST) {       // one wave of resident CTAs, each walking tiles blockIdx.x, blockIdx.x + grid, ...

@@ -371,14 +371,17 @@ SKEL_HD void skel_assemble(const Ctx& ctx, int N, int P, const double* H, const 
 // (rank-nb), so every entry of the band makes one global round trip per panel instead of one per column.  The
 // right-hand side rides along as an extra row of the matrix (forward substitution for free); the backward
 // substitution walks the panels right to left.  info = index + 1 of the first non-positive pivot.
-// sm: (nb + hb) * (nb + 1) + nb doubles.
-SKEL_HD size_t band_panel_doubles(int hb, int nb) { return (size_t)(nb + hb) * (nb + 1) + nb; }
+// sm: band_panel_doubles(hb, nb) doubles.
+SKEL_HD size_t band_panel_doubles(int hb, int nb) {
+    const size_t fwd = (size_t)(nb + hb) * (nb + 1), bwd = (size_t)nb * 32 + (size_t)nb * nb;
+    return (fwd > bwd ? fwd : bwd) + nb;
+}
 
 template <typename Ctx>
 SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, double* AB, double* x, int* info, double* sm) {
     const int W = hb + 1, LD = nb + 1;
     double* Lp = sm;                                   // [(nb + hb)][LD] panel rows, column c at Lp[r * LD + c]
-    double* yp = sm + (size_t)(nb + hb) * LD;          // [nb] right-hand side of the panel columns
+    double* yp = sm + band_panel_doubles(hb, nb) - nb; // [nb] right-hand side of the panel columns
     for (long long j0 = 0; j0 < n; j0 += nb) {
         const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
         const long long j1 = j0 + nbp;
@@ -392,33 +395,43 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
         }
         for (int c = ctx.tid; c < nbp; c += ctx.nthreads) yp[c] = x[j0 + c];
         ctx.sync();
-        // ---- B: factor the panel in shared memory, column by column
+        // ---- B: factor the panel in shared memory, ONE barrier per column: step c updates the columns right of c with
+        //      the still unscaled column c (factor 1 / pivot) and scales column c-1, which nobody reads any more
+        double inv_prev = 0;
         for (int c = 0; c < nbp; ++c) {
             const double piv = Lp[c * LD + c];
             if (!(piv > 0)) {
                 if (ctx.tid == 0 && *info == 0) *info = (int)(j0 + c + 1);
                 return;                                // uniform: every thread reads the same pivot
             }
-            const double inv = 1.0 / sqrt(piv);
-            ctx.sync();                                // every thread has read the pivot
-            for (int r = c + ctx.tid; r <= Rn; r += ctx.nthreads) {
-                if (r < Rn) Lp[r * LD + c] *= inv;
-                else yp[c] *= inv;                     // the right-hand side "row"
-            }
-            ctx.sync();
+            const double ip = 1.0 / piv;
             const int nc = nbp - 1 - c;                // panel columns right of c
-            for (int e = ctx.tid; e < (Rn - c) * nc; e += ctx.nthreads) {   // rows c+1 .. Rn (Rn = rhs row), columns c+1 ..
-                const int rr = e / nc, cc = c + 1 + (e - rr * nc);
-                const int r = c + 1 + rr;
-                const double m = Lp[cc * LD + c];
-                if (r < Rn) {
-                    if (r >= cc) Lp[r * LD + cc] -= Lp[r * LD + c] * m;
+            const int n_upd = (Rn - c) * nc;           // rows c+1 .. Rn (row Rn = the right-hand side)
+            const int n_scl = c > 0 ? Rn - c + 2 : 0;  // column c-1: rows c-1 .. Rn
+            for (int e = ctx.tid; e < n_upd + n_scl; e += ctx.nthreads) {
+                if (e < n_upd) {
+                    const int rr = e / nc, cc = c + 1 + (e - rr * nc);
+                    const int r = c + 1 + rr;
+                    const double m = Lp[cc * LD + c] * ip;
+                    if (r < Rn) {
+                        if (r >= cc) Lp[r * LD + cc] -= Lp[r * LD + c] * m;
+                    } else {
+                        yp[cc] -= yp[c] * m;
+                    }
                 } else {
-                    yp[cc] -= yp[c] * m;
+                    const int r = c - 1 + (e - n_upd);
+                    if (r < Rn) Lp[r * LD + c - 1] *= inv_prev;
+                    else yp[c - 1] *= inv_prev;
                 }
             }
+            inv_prev = 1.0 / sqrt(piv);
             ctx.sync();
         }
+        for (int r = nbp - 1 + ctx.tid; r <= Rn; r += ctx.nthreads) {      // the last column
+            if (r < Rn) Lp[r * LD + nbp - 1] *= inv_prev;
+            else yp[nbp - 1] *= inv_prev;
+        }
+        ctx.sync();
         // ---- C: write the panel back; rank-nbp update of the trailing band and of the right-hand side
         for (int e = ctx.tid; e < Rn * nbp; e += ctx.nthreads) {
             const int r = e / nbp, c = e - r * nbp;
@@ -427,42 +440,77 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
         }
         for (int c = ctx.tid; c < nbp; c += ctx.nthreads) x[j0 + c] = yp[c];
         const int T = (int)(rmax - j1 + 1);            // trailing rows j1 .. rmax
-        for (int e = ctx.tid; e < T * (T + 1); e += ctx.nthreads) {
-            const int a = e / (T + 1), b = e - a * (T + 1);      // b == T: the right-hand side
-            const double* La = Lp + (size_t)(nbp + a) * LD;
-            if (b == T) {
+        // register-tiled rank-nbp update: a task owns rows {ta + i nt} x {tb + j nt}, i, j < 4 (strided so that
+        // neighbouring threads read neighbouring panel rows: conflict-free with the odd row stride LD); only the
+        // entries on or below the diagonal (i > j, or i == j with tb <= ta) exist
+        const int nt = (T + 3) / 4;
+        for (int e = ctx.tid; e < nt * nt + T; e += ctx.nthreads) {
+            if (e >= nt * nt) {                        // the right-hand side row
+                const int a = e - nt * nt;
+                const double* La = Lp + (size_t)(nbp + a) * LD;
                 double acc = 0;
                 for (int c = 0; c < nbp; ++c) acc += La[c] * yp[c];
                 x[j1 + a] -= acc;
-            } else if (b <= a) {
-                const double* Lb = Lp + (size_t)(nbp + b) * LD;
-                double acc = 0;
-                for (int c = 0; c < nbp; ++c) acc += La[c] * Lb[c];
-                AB[(j1 + a) * W + (a - b)] -= acc;
+                continue;
             }
+            const int ta = e / nt, tb = e - ta * nt;
+            double acc[4][4];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+            for (int c = 0; c < nbp; ++c) {
+                double la[4], lb[4];
+                for (int i = 0; i < 4; ++i) {
+                    const int a = ta + i * nt, b = tb + i * nt;
+                    la[i] = a < T ? Lp[(size_t)(nbp + a) * LD + c] : 0.0;
+                    lb[i] = b < T ? Lp[(size_t)(nbp + b) * LD + c] : 0.0;
+                }
+                for (int i = 0; i < 4; ++i)
+                    for (int j = 0; j <= i; ++j) acc[i][j] += la[i] * lb[j];
+            }
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    const int a = ta + i * nt, b = tb + j * nt;
+                    if (a < T && b <= a) AB[(j1 + a) * W + (a - b)] -= acc[i][j];
+                }
         }
         ctx.sync();
     }
-    // ---- backward substitution L^T x = y, panels right to left
+    // ---- backward substitution L^T x = y, panels right to left.  Per panel: the contributions of the already
+    //      solved rows in NSEG interleaved partial sums per column (fixed order), the nb x nb triangle from shared memory
+    constexpr int NSEG = 32;
+    double* part = sm;                                 // [nb][NSEG]
+    double* tri = sm + (size_t)nb * NSEG;              // [nb][nb]
     const long long n_panels = (n + nb - 1) / nb;
     for (long long p = n_panels - 1; p >= 0; --p) {
         const long long j0 = p * nb;
         const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
         const long long j1 = j0 + nbp;
-        // contributions of the already solved rows i >= j1 to each panel column
-        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) {
-            const long long j = j0 + c;
-            const long long imax = (j + hb) < (n - 1) ? (j + hb) : (n - 1);
-            double acc = 0;
-            for (long long i = j1; i <= imax; ++i) acc += AB[i * W + (i - j)] * x[i];
-            yp[c] = x[j] - acc;
+        for (int e = ctx.tid; e < nbp * NSEG + nbp * nbp; e += ctx.nthreads) {
+            if (e < nbp * NSEG) {
+                const int c = e / NSEG, sg = e - c * NSEG;
+                const long long j = j0 + c;
+                const long long imax = (j + hb) < (n - 1) ? (j + hb) : (n - 1);
+                double acc = 0;
+                for (long long i = j1 + sg; i <= imax; i += NSEG) acc += AB[i * W + (i - j)] * x[i];
+                part[e] = acc;
+            } else {
+                const int q = e - nbp * NSEG, r = q / nbp, c = q - r * nbp;
+                tri[r * nb + c] = (r >= c && r - c <= hb) ? AB[(j0 + r) * W + (r - c)] : 0.0;
+            }
+        }
+        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) yp[c] = x[j0 + c];
+        ctx.sync();
+        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) {       // fold the partial sums (fixed order)
+            double sacc = yp[c];
+            for (int sg = 0; sg < NSEG; ++sg) sacc -= part[c * NSEG + sg];
+            yp[c] = sacc;
         }
         ctx.sync();
-        if (ctx.tid == 0) {                            // nbp x nbp triangle
+        if (ctx.tid == 0) {
             for (int c = nbp - 1; c >= 0; --c) {
                 double sacc = yp[c];
-                for (int r = c + 1; r < nbp && r - c <= hb; ++r) sacc -= AB[(j0 + r) * W + (r - c)] * yp[r];
-                yp[c] = sacc / AB[(j0 + c) * W];
+                for (int r = c + 1; r < nbp; ++r) sacc -= tri[r * nb + c] * yp[r];
+                yp[c] = sacc / tri[c * nb + c];
             }
         }
         ctx.sync();
