@@ -374,14 +374,19 @@ SKEL_HD void skel_assemble(const Ctx& ctx, int N, int P, const double* H, const 
 // sm: band_panel_doubles(hb, nb) doubles.
 SKEL_HD size_t band_panel_doubles(int hb, int nb) {
     const size_t fwd = (size_t)(nb + hb) * (nb + 1), bwd = (size_t)nb * 32 + (size_t)nb * nb;
-    return (fwd > bwd ? fwd : bwd) + nb;
+    return (fwd > bwd ? fwd : bwd) + nb + 6;
 }
 
 template <typename Ctx>
 SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, double* AB, double* x, int* info, double* sm) {
     const int W = hb + 1, LD = nb + 1;
     double* Lp = sm;                                   // [(nb + hb)][LD] panel rows, column c at Lp[r * LD + c]
-    double* yp = sm + band_panel_doubles(hb, nb) - nb; // [nb] right-hand side of the panel columns
+    double* yp = sm + band_panel_doubles(hb, nb) - nb - 6; // [nb] right-hand side of the panel columns
+    double* scal = yp + nb;                            // 2 x {pivot, 1 / pivot, 1 / sqrt(pivot)}
+    // 2-D thread mapping of the panel update without integer division in the loop: tx over the (<= nb) columns
+    const int nbq = nb <= 16 ? 16 : (nb <= 32 ? 32 : 64);
+    const int tx = ctx.tid % nbq, ty = ctx.tid / nbq;
+    const int sx = ctx.nthreads < nbq ? ctx.nthreads : nbq, sy = ctx.nthreads / nbq > 0 ? ctx.nthreads / nbq : 1;
     for (long long j0 = 0; j0 < n; j0 += nb) {
         const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
         const long long j1 = j0 + nbp;
@@ -396,35 +401,55 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
         for (int c = ctx.tid; c < nbp; c += ctx.nthreads) yp[c] = x[j0 + c];
         ctx.sync();
         // ---- B: factor the panel in shared memory, ONE barrier per column: step c updates the columns right of c with
-        //      the still unscaled column c (factor 1 / pivot) and scales column c-1, which nobody reads any more
+        //      the still unscaled column c (factor 1 / pivot) and scales column c-1, which nobody reads any more.  The
+        //      pivot's reciprocal and inverse square root are computed ONCE, by the thread that finishes the pivot, and
+        //      handed over through a double-buffered slot (a redundant fp64 divide + sqrt in all 32 warps of the CTA cost
+        //      more than the whole update)
+        if (ctx.tid == 0) {
+            const double piv = Lp[0];
+            scal[0] = piv;
+            scal[1] = piv > 0 ? 1.0 / piv : 0.0;
+            scal[2] = piv > 0 ? 1.0 / sqrt(piv) : 0.0;
+        }
+        ctx.sync();
         double inv_prev = 0;
         for (int c = 0; c < nbp; ++c) {
-            const double piv = Lp[c * LD + c];
+            const double* sc = scal + 3 * (c & 1);
+            double* sn = scal + 3 * ((c + 1) & 1);
+            const double piv = sc[0], ip = sc[1];
             if (!(piv > 0)) {
                 if (ctx.tid == 0 && *info == 0) *info = (int)(j0 + c + 1);
                 return;                                // uniform: every thread reads the same pivot
             }
-            const double ip = 1.0 / piv;
             const int nc = nbp - 1 - c;                // panel columns right of c
-            const int n_upd = (Rn - c) * nc;           // rows c+1 .. Rn (row Rn = the right-hand side)
-            const int n_scl = c > 0 ? Rn - c + 2 : 0;  // column c-1: rows c-1 .. Rn
-            for (int e = ctx.tid; e < n_upd + n_scl; e += ctx.nthreads) {
-                if (e < n_upd) {
-                    const int rr = e / nc, cc = c + 1 + (e - rr * nc);
-                    const int r = c + 1 + rr;
+            const int rows = Rn - c;                   // rows c+1 .. Rn (row Rn = the right-hand side)
+            for (int rr = ty; rr < rows; rr += sy) {
+                const int r = c + 1 + rr;
+                const double lrc = r < Rn ? Lp[r * LD + c] : yp[c];
+                for (int q = tx; q < nc; q += sx) {
+                    const int cc = c + 1 + q;
                     const double m = Lp[cc * LD + c] * ip;
                     if (r < Rn) {
-                        if (r >= cc) Lp[r * LD + cc] -= Lp[r * LD + c] * m;
+                        if (r >= cc) {
+                            const double v = Lp[r * LD + cc] - lrc * m;
+                            Lp[r * LD + cc] = v;
+                            if (r == cc && cc == c + 1) {      // the next pivot is final: prepare its scalars
+                                sn[0] = v;
+                                sn[1] = v > 0 ? 1.0 / v : 0.0;
+                                sn[2] = v > 0 ? 1.0 / sqrt(v) : 0.0;
+                            }
+                        }
                     } else {
-                        yp[cc] -= yp[c] * m;
+                        yp[cc] -= lrc * m;
                     }
-                } else {
-                    const int r = c - 1 + (e - n_upd);
+                }
+            }
+            if (c > 0)
+                for (int r = c - 1 + ctx.tid; r <= Rn; r += ctx.nthreads) {
                     if (r < Rn) Lp[r * LD + c - 1] *= inv_prev;
                     else yp[c - 1] *= inv_prev;
                 }
-            }
-            inv_prev = 1.0 / sqrt(piv);
+            inv_prev = sc[2];
             ctx.sync();
         }
         for (int r = nbp - 1 + ctx.tid; r <= Rn; r += ctx.nthreads) {      // the last column

@@ -55,8 +55,34 @@ for _ in range(10):
     h.call_dev("acino_skel_eval_dev", M, xb, mb, wb, cost, gg, HH)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
+# per-kernel time of one LM attempt (CUDA events, 5 repetitions, device resident)
+def timed(name, *a):
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(5):
+        h.call_dev(name, *a)
+    a1.record(); torch.cuda.synchronize()
+    return a0.elapsed_time(a1) / 5
+st, tr = solver.st
+phases = {}
+phases["skel_eval"] = timed("acino_skel_eval_dev", N, st["x"], solver.meas, solver.w, st["cost"], st["g"], st["H"])
+phases["skel_prepare"] = timed("acino_skel_prepare_dev", N, 1, st["x"], st["g"], solver.sw, solver.lo, solver.hi, st["gtot"], st["fixed"], st["cost_s"])
+phases["skel_assemble"] = timed("acino_skel_assemble_dev", N, st["H"], st["gtot"], st["fixed"], solver.sw, 1e-3, solver.AB, solver.d)
+def band():
+    h.call_dev("acino_skel_assemble_dev", N, st["H"], st["gtot"], st["fixed"], solver.sw, 1e-3, solver.AB, solver.d)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    h.call_dev("acino_band_solve_dev", N * P, 3 * P, solver.AB, solver.d, solver.info)
+    a1.record(); torch.cuda.synchronize()
+    return a0.elapsed_time(a1)
+phases["band_solve"] = float(np.median([band() for _ in range(5)]))
+phases["skel_trial"] = timed("acino_skel_trial_dev", N, 1, st["x"], solver.d, solver.lo, solver.hi, tr["x"])
+phases["skel_pred"] = timed("acino_skel_pred_dev", N, st["x"], tr["x"], st["gtot"], st["H"], solver.sw, solver.pred, solver.step)
 bytes_per_frame = 8 * (P + 4 * 15 * 3 + 1 + P + P * (P + 1) // 2)
 print(json.dumps({"frames": N, "P": P, "iters": info["iters"], "attempts": info["n_solve"], "seconds": dt,
                   "ms_per_attempt": 1e3 * dt / info["n_solve"], "F0": info["F0"], "F": info["F"], "converged": info["converged"],
                   "marker_median_err_m": float(np.median(err)), "eval_frames": M, "eval_ms": ms,
-                  "eval_frames_per_s": M / ms * 1e3, "eval_GBps": M * bytes_per_frame / ms / 1e6}))
+                  "eval_frames_per_s": M / ms * 1e3, "eval_GBps": M * bytes_per_frame / ms / 1e6,
+                  "attempt_kernel_ms": {k: round(v, 4) for k, v in phases.items()}}))
