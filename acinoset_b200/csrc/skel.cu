@@ -51,7 +51,7 @@ constexpr int BAND_NB = 16;     // panel width of the blocked band Cholesky
 __global__ void __launch_bounds__(1024) band_solve_kernel(long long n, int hb, double* AB, double* x, int* info) {
     extern __shared__ double band_sm[];
     const CtaCtx ctx{(int)threadIdx.x, (int)blockDim.x};
-    band_cholesky_solve(ctx, n, hb, BAND_NB, AB, x, info, band_sm);
+    band_cholesky_solve<BAND_NB>(ctx, n, hb, AB, x, info, band_sm);
 }
 
 __global__ void skel_trial_kernel(int N, int P, int last_free, const double* x, const double* d, const double* lo,

@@ -366,52 +366,68 @@ SKEL_HD void skel_assemble(const Ctx& ctx, int N, int P, const double* H, const 
 }
 
 // In-place band Cholesky B = L L^T (row-wise lower band storage AB[i][k] = B[i][i-k], half bandwidth hb) and solve of
-// B x = rhs, by ONE cooperating group of threads (a CTA).  Blocked right-looking: a panel of nb columns (rows
-// j0 .. j0+nb-1+hb) is staged in shared memory and factored there; the trailing band is then updated ONCE per panel
-// (rank-nb), so every entry of the band makes one global round trip per panel instead of one per column.  The
-// right-hand side rides along as an extra row of the matrix (forward substitution for free); the backward
-// substitution walks the panels right to left.  info = index + 1 of the first non-positive pivot.
-// sm: band_panel_doubles(hb, nb) doubles.
+// B x = rhs, by ONE cooperating group of threads (a CTA).  Blocked right-looking, panel width NB (compile time):
+//   A   the panel (rows j0 .. j0+NB-1+hb, NB columns) and its right-hand side entries are staged in shared memory;
+//   B1  its NB x NB triangle (+ the right-hand side as an extra row: forward substitution for free) is factored column
+//       by column - one barrier per column, a handful of warps busy, the pivot's 1/p and 1/sqrt(p) computed once by
+//       the thread that finishes the pivot (Newton on the fp32 rsqrt) and handed over through a double-buffered slot;
+//   B2  the hb rows below the triangle are a triangular solve with NB columns per row: one thread per row, the row in
+//       registers, no barriers;
+//   C   write-back, then ONE rank-NB update of the trailing band per panel, register tiled (4 x 4 strided rows), so
+//       every entry of the band makes one global round trip per panel instead of one per column.
+// The backward substitution walks the panels right to left.  info = index + 1 of the first non-positive pivot.
+// sm: band_panel_doubles(hb, NB) doubles.  (ncu of the first, column-at-a-time-over-the-whole-panel version: 47 % of
+// the instructions in the panel step, 45 % in the trailing update, 32 warps waiting on one - profiles/r01_skel.md.)
 SKEL_HD size_t band_panel_doubles(int hb, int nb) {
     const size_t fwd = (size_t)(nb + hb) * (nb + 1), bwd = (size_t)nb * 32 + (size_t)nb * nb;
-    return (fwd > bwd ? fwd : bwd) + nb + 6;
+    return (fwd > bwd ? fwd : bwd) + 2 * nb + 6;
 }
 
-template <typename Ctx>
-SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, double* AB, double* x, int* info, double* sm) {
-    const int W = hb + 1, LD = nb + 1;
-    double* Lp = sm;                                   // [(nb + hb)][LD] panel rows, column c at Lp[r * LD + c]
-    double* yp = sm + band_panel_doubles(hb, nb) - nb - 6; // [nb] right-hand side of the panel columns
-    double* scal = yp + nb;                            // 2 x {pivot, 1 / pivot, 1 / sqrt(pivot)}
-    // 2-D thread mapping of the panel update without integer division in the loop: tx over the (<= nb) columns
-    const int nbq = nb <= 16 ? 16 : (nb <= 32 ? 32 : 64);
-    const int tx = ctx.tid % nbq, ty = ctx.tid / nbq;
-    const int sx = ctx.nthreads < nbq ? ctx.nthreads : nbq, sy = ctx.nthreads / nbq > 0 ? ctx.nthreads / nbq : 1;
-    for (long long j0 = 0; j0 < n; j0 += nb) {
-        const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
+SKEL_HD double sk_rsqrt(double a) {
+#ifdef __CUDA_ARCH__
+    if (a > 1e-30 && a < 1e30) {
+        double y = (double)rsqrtf((float)a);           // 22 bits, then three Newton steps
+        y = y * (1.5 - 0.5 * a * y * y);
+        y = y * (1.5 - 0.5 * a * y * y);
+        y = y * (1.5 - 0.5 * a * y * y);
+        return y;
+    }
+#endif
+    return 1.0 / sqrt(a);
+}
+
+template <int NB, typename Ctx>
+SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, double* AB, double* x, int* info, double* sm) {
+    constexpr int LD = NB + 1;
+    constexpr int NBQ = NB <= 4 ? 4 : (NB <= 8 ? 8 : (NB <= 16 ? 16 : 32));   // power of two >= NB (NB <= 32)
+    const int W = hb + 1;
+    double* Lp = sm;                                   // [(NB + hb)][LD] panel rows, column c at Lp[r * LD + c]
+    double* yp = sm + band_panel_doubles(hb, NB) - 2 * NB - 6;   // [NB] right-hand side of the panel columns
+    double* isd = yp + NB;                             // [NB] 1 / L_cc
+    double* scal = isd + NB;                           // 2 x {pivot, 1 / pivot, 1 / sqrt(pivot)}
+    const int tx = ctx.tid % NBQ, ty = ctx.tid / NBQ;
+    const int sx = ctx.nthreads < NBQ ? ctx.nthreads : NBQ, sy = ctx.nthreads / NBQ > 0 ? ctx.nthreads / NBQ : 1;
+    for (long long j0 = 0; j0 < n; j0 += NB) {
+        const int nbp = (int)((n - j0) < NB ? (n - j0) : NB);
         const long long j1 = j0 + nbp;
         const long long rmax = (j1 - 1 + hb) < (n - 1) ? (j1 - 1 + hb) : (n - 1);
         const int Rn = (int)(rmax - j0 + 1);           // panel rows
         // ---- A: stage the panel
-        for (int e = ctx.tid; e < Rn * nbp; e += ctx.nthreads) {
-            const int r = e / nbp, c = e - r * nbp;
-            const int k = r - c;                       // distance below the diagonal of column j0 + c
-            Lp[r * LD + c] = (k >= 0 && k <= hb) ? AB[(j0 + r) * W + k] : 0.0;
-        }
+        for (int r = ty; r < Rn; r += sy)
+            for (int c = tx; c < nbp; c += sx) {
+                const int k = r - c;                   // distance below the diagonal of column j0 + c
+                Lp[r * LD + c] = (k >= 0 && k <= hb) ? AB[(j0 + r) * W + k] : 0.0;
+            }
         for (int c = ctx.tid; c < nbp; c += ctx.nthreads) yp[c] = x[j0 + c];
-        ctx.sync();
-        // ---- B: factor the panel in shared memory, ONE barrier per column: step c updates the columns right of c with
-        //      the still unscaled column c (factor 1 / pivot) and scales column c-1, which nobody reads any more.  The
-        //      pivot's reciprocal and inverse square root are computed ONCE, by the thread that finishes the pivot, and
-        //      handed over through a double-buffered slot (a redundant fp64 divide + sqrt in all 32 warps of the CTA cost
-        //      more than the whole update)
         if (ctx.tid == 0) {
-            const double piv = Lp[0];
+            const double piv = AB[j0 * W];
             scal[0] = piv;
-            scal[1] = piv > 0 ? 1.0 / piv : 0.0;
-            scal[2] = piv > 0 ? 1.0 / sqrt(piv) : 0.0;
+            const double y = piv > 0 ? sk_rsqrt(piv) : 0.0;
+            scal[1] = y * y;
+            scal[2] = y;
         }
         ctx.sync();
+        // ---- B1: the nbp x nbp triangle and the right-hand side row (row index nbp here)
         double inv_prev = 0;
         for (int c = 0; c < nbp; ++c) {
             const double* sc = scal + 3 * (c & 1);
@@ -421,76 +437,101 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
                 if (ctx.tid == 0 && *info == 0) *info = (int)(j0 + c + 1);
                 return;                                // uniform: every thread reads the same pivot
             }
-            const int nc = nbp - 1 - c;                // panel columns right of c
-            const int rows = Rn - c;                   // rows c+1 .. Rn (row Rn = the right-hand side)
-            for (int rr = ty; rr < rows; rr += sy) {
+            const int nc = nbp - 1 - c;                // columns right of c
+            for (int rr = ty; rr <= nc; rr += sy) {    // triangle rows c+1 .. nbp-1, then the right-hand side (rr == nc)
+                const bool rhs = rr == nc;
                 const int r = c + 1 + rr;
-                const double lrc = r < Rn ? Lp[r * LD + c] : yp[c];
+                const double lrc = rhs ? yp[c] : Lp[r * LD + c];
                 for (int q = tx; q < nc; q += sx) {
                     const int cc = c + 1 + q;
                     const double m = Lp[cc * LD + c] * ip;
-                    if (r < Rn) {
-                        if (r >= cc) {
-                            const double v = Lp[r * LD + cc] - lrc * m;
-                            Lp[r * LD + cc] = v;
-                            if (r == cc && cc == c + 1) {      // the next pivot is final: prepare its scalars
-                                sn[0] = v;
-                                sn[1] = v > 0 ? 1.0 / v : 0.0;
-                                sn[2] = v > 0 ? 1.0 / sqrt(v) : 0.0;
-                            }
-                        }
-                    } else {
+                    if (rhs) {
                         yp[cc] -= lrc * m;
+                    } else if (r >= cc) {
+                        const double v = Lp[r * LD + cc] - lrc * m;
+                        Lp[r * LD + cc] = v;
+                        if (r == cc && q == 0) {       // the next pivot is final: prepare its scalars
+                            sn[0] = v;
+                            const double y = v > 0 ? sk_rsqrt(v) : 0.0;
+                            sn[1] = y * y;
+                            sn[2] = y;
+                        }
                     }
                 }
             }
             if (c > 0)
-                for (int r = c - 1 + ctx.tid; r <= Rn; r += ctx.nthreads) {
-                    if (r < Rn) Lp[r * LD + c - 1] *= inv_prev;
+                for (int r = c - 1 + ctx.tid; r <= nbp; r += ctx.nthreads) {   // scale column c-1 (nobody reads it any more)
+                    if (r < nbp) Lp[r * LD + c - 1] *= inv_prev;
                     else yp[c - 1] *= inv_prev;
                 }
             inv_prev = sc[2];
+            if (ctx.tid == 0) isd[c] = inv_prev;
             ctx.sync();
         }
-        for (int r = nbp - 1 + ctx.tid; r <= Rn; r += ctx.nthreads) {      // the last column
-            if (r < Rn) Lp[r * LD + nbp - 1] *= inv_prev;
+        for (int r = nbp - 1 + ctx.tid; r <= nbp; r += ctx.nthreads) {         // the last column
+            if (r < nbp) Lp[r * LD + nbp - 1] *= inv_prev;
             else yp[nbp - 1] *= inv_prev;
         }
         ctx.sync();
-        // ---- C: write the panel back; rank-nbp update of the trailing band and of the right-hand side
-        for (int e = ctx.tid; e < Rn * nbp; e += ctx.nthreads) {
-            const int r = e / nbp, c = e - r * nbp;
-            const int k = r - c;
-            if (k >= 0 && k <= hb) AB[(j0 + r) * W + k] = Lp[r * LD + c];
+        // ---- B2: rows below the triangle: l[c] = (a[c] - sum_{k<c} l[k] L11[c][k]) / L11[c][c], one thread per row
+        for (int r = nbp + ctx.tid; r < Rn; r += ctx.nthreads) {
+            double l[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) l[c] = c < nbp ? Lp[r * LD + c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < nbp) {
+                    double v = l[c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) v -= l[k] * Lp[c * LD + k];
+                    l[c] = v * isd[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (c < nbp) Lp[r * LD + c] = l[c];
         }
+        ctx.sync();
+        // ---- C: write the panel back; rank-nbp update of the trailing band and of the right-hand side
+        for (int r = ty; r < Rn; r += sy)
+            for (int c = tx; c < nbp; c += sx) {
+                const int k = r - c;
+                if (k >= 0 && k <= hb) AB[(j0 + r) * W + k] = Lp[r * LD + c];
+            }
         for (int c = ctx.tid; c < nbp; c += ctx.nthreads) x[j0 + c] = yp[c];
         const int T = (int)(rmax - j1 + 1);            // trailing rows j1 .. rmax
-        // register-tiled rank-nbp update: a task owns rows {ta + i nt} x {tb + j nt}, i, j < 4 (strided so that
-        // neighbouring threads read neighbouring panel rows: conflict-free with the odd row stride LD); only the
-        // entries on or below the diagonal (i > j, or i == j with tb <= ta) exist
+        // register-tiled update: a task owns rows {ta + i nt} x {tb + j nt}, i, j < 4 (strided so that neighbouring
+        // threads read neighbouring panel rows: conflict-free with the odd row stride LD); only the entries on or below
+        // the diagonal (i > j, or i == j with tb <= ta) exist
         const int nt = (T + 3) / 4;
         for (int e = ctx.tid; e < nt * nt + T; e += ctx.nthreads) {
             if (e >= nt * nt) {                        // the right-hand side row
                 const int a = e - nt * nt;
                 const double* La = Lp + (size_t)(nbp + a) * LD;
                 double acc = 0;
-                for (int c = 0; c < nbp; ++c) acc += La[c] * yp[c];
+                for (int c = 0; c < NB; ++c) acc += c < nbp ? La[c] * yp[c] : 0.0;
                 x[j1 + a] -= acc;
                 continue;
             }
             const int ta = e / nt, tb = e - ta * nt;
+            const double* Pa[4];
+            const double* Pb[4];
+            for (int i = 0; i < 4; ++i) {              // rows past the end read row 0 of the trailing part; never stored
+                const int a = ta + i * nt, b = tb + i * nt;
+                Pa[i] = Lp + (size_t)(nbp + (a < T ? a : 0)) * LD;
+                Pb[i] = Lp + (size_t)(nbp + (b < T ? b : 0)) * LD;
+            }
             double acc[4][4];
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0;
-            for (int c = 0; c < nbp; ++c) {
-                double la[4], lb[4];
-                for (int i = 0; i < 4; ++i) {
-                    const int a = ta + i * nt, b = tb + i * nt;
-                    la[i] = a < T ? Lp[(size_t)(nbp + a) * LD + c] : 0.0;
-                    lb[i] = b < T ? Lp[(size_t)(nbp + b) * LD + c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < nbp) {
+                    double la[4], lb[4];
+                    for (int i = 0; i < 4; ++i) { la[i] = Pa[i][c]; lb[i] = Pb[i][c]; }
+                    for (int i = 0; i < 4; ++i)
+                        for (int j = 0; j <= i; ++j) acc[i][j] += la[i] * lb[j];
                 }
-                for (int i = 0; i < 4; ++i)
-                    for (int j = 0; j <= i; ++j) acc[i][j] += la[i] * lb[j];
             }
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j <= i; ++j) {
@@ -501,16 +542,16 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
         ctx.sync();
     }
     // ---- backward substitution L^T x = y, panels right to left.  Per panel: the contributions of the already
-    //      solved rows in NSEG interleaved partial sums per column (fixed order), the nb x nb triangle from shared memory
+    //      solved rows in NSEG interleaved partial sums per column (fixed order), the triangle from shared memory
     constexpr int NSEG = 32;
-    double* part = sm;                                 // [nb][NSEG]
-    double* tri = sm + (size_t)nb * NSEG;              // [nb][nb]
-    const long long n_panels = (n + nb - 1) / nb;
+    double* part = sm;                                 // [NB][NSEG]
+    double* tri = sm + (size_t)NB * NSEG;              // [NB][NB]
+    const long long n_panels = (n + NB - 1) / NB;
     for (long long p = n_panels - 1; p >= 0; --p) {
-        const long long j0 = p * nb;
-        const int nbp = (int)((n - j0) < nb ? (n - j0) : nb);
+        const long long j0 = p * NB;
+        const int nbp = (int)((n - j0) < NB ? (n - j0) : NB);
         const long long j1 = j0 + nbp;
-        for (int e = ctx.tid; e < nbp * NSEG + nbp * nbp; e += ctx.nthreads) {
+        for (int e = ctx.tid; e < nbp * NSEG + nbp * NB; e += ctx.nthreads) {
             if (e < nbp * NSEG) {
                 const int c = e / NSEG, sg = e - c * NSEG;
                 const long long j = j0 + c;
@@ -519,8 +560,8 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
                 for (long long i = j1 + sg; i <= imax; i += NSEG) acc += AB[i * W + (i - j)] * x[i];
                 part[e] = acc;
             } else {
-                const int q = e - nbp * NSEG, r = q / nbp, c = q - r * nbp;
-                tri[r * nb + c] = (r >= c && r - c <= hb) ? AB[(j0 + r) * W + (r - c)] : 0.0;
+                const int q = e - nbp * NSEG, r = q / NB, c = q - r * NB;
+                tri[r * NB + c] = (c < nbp && r >= c && r - c <= hb) ? AB[(j0 + r) * W + (r - c)] : 0.0;
             }
         }
         for (int c = ctx.tid; c < nbp; c += ctx.nthreads) yp[c] = x[j0 + c];
@@ -532,14 +573,21 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, int nb, do
         }
         ctx.sync();
         if (ctx.tid == 0) {
-            for (int c = nbp - 1; c >= 0; --c) {
-                double sacc = yp[c];
-                for (int r = c + 1; r < nbp; ++r) sacc -= tri[r * nb + c] * yp[r];
-                yp[c] = sacc / tri[c * nb + c];
+            double xs[NB];
+#pragma unroll
+            for (int c = NB - 1; c >= 0; --c) {
+                xs[c] = 0;
+                if (c < nbp) {
+                    double sacc = yp[c];
+#pragma unroll
+                    for (int r = c + 1; r < NB; ++r) sacc -= r < nbp ? tri[r * NB + c] * xs[r] : 0.0;
+                    xs[c] = sacc / tri[c * NB + c];
+                }
             }
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (c < nbp) x[j0 + c] = xs[c];
         }
-        ctx.sync();
-        for (int c = ctx.tid; c < nbp; c += ctx.nthreads) x[j0 + c] = yp[c];
         ctx.sync();
     }
 }

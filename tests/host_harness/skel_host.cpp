@@ -66,9 +66,18 @@ void skel_host_assemble(int N, int P, const double* H, const double* gtot, const
                         double lam, double* AB, double* rhs) {
     skel_assemble(HostCtx(), N, P, H, gtot, fixed, sw, lam, AB, rhs);
 }
-void skel_host_band_solve(long long n, int hb, int nb, double* AB, double* x, int* info) {
+int skel_host_band_solve(long long n, int hb, int nb, double* AB, double* x, int* info) {
     std::vector<double> sm(band_panel_doubles(hb, nb));
-    band_cholesky_solve(HostCtx(), n, hb, nb, AB, x, info, sm.data());
+    HostCtx ctx;
+    switch (nb) {                                      // the panel width is a compile-time parameter of the kernel
+        case 1: band_cholesky_solve<1>(ctx, n, hb, AB, x, info, sm.data()); return 0;
+        case 4: band_cholesky_solve<4>(ctx, n, hb, AB, x, info, sm.data()); return 0;
+        case 7: band_cholesky_solve<7>(ctx, n, hb, AB, x, info, sm.data()); return 0;
+        case 8: band_cholesky_solve<8>(ctx, n, hb, AB, x, info, sm.data()); return 0;
+        case 16: band_cholesky_solve<16>(ctx, n, hb, AB, x, info, sm.data()); return 0;
+        case 32: band_cholesky_solve<32>(ctx, n, hb, AB, x, info, sm.data()); return 0;
+    }
+    return -1;
 }
 void skel_host_trial(int N, int P, int last_free, const double* x, const double* d, const double* lo, const double* hi, double* xt) {
     skel_trial(HostCtx(), N, P, last_free, x, d, lo, hi, xt);
