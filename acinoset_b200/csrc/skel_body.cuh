@@ -533,10 +533,22 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, double* AB
                         for (int j = 0; j <= i; ++j) acc[i][j] += la[i] * lb[j];
                 }
             }
+            // read-modify-write of the band: all loads first, then all stores (a store followed by a load of the same
+            // array is kept in order by the compiler: one L2 round trip per entry otherwise)
+            double old[4][4];
+#pragma unroll
             for (int i = 0; i < 4; ++i)
+#pragma unroll
                 for (int j = 0; j <= i; ++j) {
                     const int a = ta + i * nt, b = tb + j * nt;
-                    if (a < T && b <= a) AB[(j1 + a) * W + (a - b)] -= acc[i][j];
+                    old[i][j] = (a < T && b <= a) ? AB[(j1 + a) * W + (a - b)] : 0.0;
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    const int a = ta + i * nt, b = tb + j * nt;
+                    if (a < T && b <= a) AB[(j1 + a) * W + (a - b)] = old[i][j] - acc[i][j];
                 }
         }
         ctx.sync();
