@@ -16,10 +16,13 @@ namespace acino {
 struct CtaCtx {
     int tid, nthreads;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    // barrier among the first n threads of the CTA (n a multiple of 32), named barrier 1
+    __device__ __forceinline__ void sync_part(int n) const { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 };
 struct GridCtx {   // grid-stride phases without barriers
     long long tid, nthreads;
     __device__ __forceinline__ void sync() const {}
+    __device__ __forceinline__ void sync_part(int) const {}
 };
 
 __global__ void __launch_bounds__(128)

@@ -380,7 +380,7 @@ SKEL_HD void skel_assemble(const Ctx& ctx, int N, int P, const double* H, const 
 // the instructions in the panel step, 45 % in the trailing update, 32 warps waiting on one - profiles/r01_skel.md.)
 SKEL_HD size_t band_panel_doubles(int hb, int nb) {
     const size_t fwd = (size_t)(nb + hb) * (nb + 1), bwd = (size_t)nb * 32 + (size_t)nb * nb;
-    return (fwd > bwd ? fwd : bwd) + 2 * nb + 6;
+    return (fwd > bwd ? fwd : bwd) + 2 * nb + 8;
 }
 
 SKEL_HD double sk_rsqrt(double a) {
@@ -402,9 +402,10 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, double* AB
     constexpr int NBQ = NB <= 4 ? 4 : (NB <= 8 ? 8 : (NB <= 16 ? 16 : 32));   // power of two >= NB (NB <= 32)
     const int W = hb + 1;
     double* Lp = sm;                                   // [(NB + hb)][LD] panel rows, column c at Lp[r * LD + c]
-    double* yp = sm + band_panel_doubles(hb, NB) - 2 * NB - 6;   // [NB] right-hand side of the panel columns
+    double* yp = sm + band_panel_doubles(hb, NB) - 2 * NB - 8;   // [NB] right-hand side of the panel columns
     double* isd = yp + NB;                             // [NB] 1 / L_cc
-    double* scal = isd + NB;                           // 2 x {pivot, 1 / pivot, 1 / sqrt(pivot)}
+    double* scal = isd + NB;                           // 2 x {pivot, 1 / pivot, 1 / sqrt(pivot)}, [6] = failure flag
+    if (ctx.tid == 0) scal[6] = 0.0;
     const int tx = ctx.tid % NBQ, ty = ctx.tid / NBQ;
     const int sx = ctx.nthreads < NBQ ? ctx.nthreads : NBQ, sy = ctx.nthreads / NBQ > 0 ? ctx.nthreads / NBQ : 1;
     for (long long j0 = 0; j0 < n; j0 += NB) {
@@ -427,52 +428,61 @@ SKEL_HD void band_cholesky_solve(const Ctx& ctx, long long n, int hb, double* AB
             scal[2] = y;
         }
         ctx.sync();
-        // ---- B1: the nbp x nbp triangle and the right-hand side row (row index nbp here)
-        double inv_prev = 0;
-        for (int c = 0; c < nbp; ++c) {
-            const double* sc = scal + 3 * (c & 1);
-            double* sn = scal + 3 * ((c + 1) & 1);
-            const double piv = sc[0], ip = sc[1];
-            if (!(piv > 0)) {
-                if (ctx.tid == 0 && *info == 0) *info = (int)(j0 + c + 1);
-                return;                                // uniform: every thread reads the same pivot
-            }
-            const int nc = nbp - 1 - c;                // columns right of c
-            for (int rr = ty; rr <= nc; rr += sy) {    // triangle rows c+1 .. nbp-1, then the right-hand side (rr == nc)
-                const bool rhs = rr == nc;
-                const int r = c + 1 + rr;
-                const double lrc = rhs ? yp[c] : Lp[r * LD + c];
-                for (int q = tx; q < nc; q += sx) {
-                    const int cc = c + 1 + q;
-                    const double m = Lp[cc * LD + c] * ip;
-                    if (rhs) {
-                        yp[cc] -= lrc * m;
-                    } else if (r >= cc) {
-                        const double v = Lp[r * LD + cc] - lrc * m;
-                        Lp[r * LD + cc] = v;
-                        if (r == cc && q == 0) {       // the next pivot is final: prepare its scalars
-                            sn[0] = v;
-                            const double y = v > 0 ? sk_rsqrt(v) : 0.0;
-                            sn[1] = y * y;
-                            sn[2] = y;
+        // ---- B1: the nbp x nbp triangle and the right-hand side row (row index nbp here).  Only the first NPART threads
+        //      take part and synchronise among themselves (named barrier): 23 idle warps arriving at 16 CTA-wide
+        //      barriers per panel cost more than the triangle itself (ncu: 26 % of the kernel waiting there)
+        constexpr int NPART = ((NBQ * (NB + 1) + 31) / 32) * 32 < 1024 ? ((NBQ * (NB + 1) + 31) / 32) * 32 : 1024;   // the kernel runs 1024 threads
+        if (ctx.tid < NPART) {
+            double inv_prev = 0;
+            for (int c = 0; c < nbp; ++c) {
+                const double* sc = scal + 3 * (c & 1);
+                double* sn = scal + 3 * ((c + 1) & 1);
+                const double piv = sc[0], ip = sc[1];
+                if (!(piv > 0)) {                      // uniform among the participants: all read the same pivot
+                    if (ctx.tid == 0) {
+                        if (*info == 0) *info = (int)(j0 + c + 1);
+                        scal[6] = 1.0;
+                    }
+                    break;
+                }
+                const int nc = nbp - 1 - c;            // columns right of c
+                for (int rr = ty; rr <= nc; rr += sy) {    // triangle rows c+1 .. nbp-1, then the right-hand side (rr == nc)
+                    const bool rhs = rr == nc;
+                    const int r = c + 1 + rr;
+                    const double lrc = rhs ? yp[c] : Lp[r * LD + c];
+                    for (int q = tx; q < nc; q += sx) {
+                        const int cc = c + 1 + q;
+                        const double m = Lp[cc * LD + c] * ip;
+                        if (rhs) {
+                            yp[cc] -= lrc * m;
+                        } else if (r >= cc) {
+                            const double v = Lp[r * LD + cc] - lrc * m;
+                            Lp[r * LD + cc] = v;
+                            if (r == cc && q == 0) {   // the next pivot is final: prepare its scalars
+                                sn[0] = v;
+                                const double y = v > 0 ? sk_rsqrt(v) : 0.0;
+                                sn[1] = y * y;
+                                sn[2] = y;
+                            }
                         }
                     }
                 }
+                if (c > 0)
+                    for (int r = c - 1 + ctx.tid; r <= nbp; r += ctx.nthreads) {   // scale column c-1 (nobody reads it any more)
+                        if (r < nbp) Lp[r * LD + c - 1] *= inv_prev;
+                        else yp[c - 1] *= inv_prev;
+                    }
+                inv_prev = sc[2];
+                if (ctx.tid == 0) isd[c] = inv_prev;
+                ctx.sync_part(NPART);
             }
-            if (c > 0)
-                for (int r = c - 1 + ctx.tid; r <= nbp; r += ctx.nthreads) {   // scale column c-1 (nobody reads it any more)
-                    if (r < nbp) Lp[r * LD + c - 1] *= inv_prev;
-                    else yp[c - 1] *= inv_prev;
-                }
-            inv_prev = sc[2];
-            if (ctx.tid == 0) isd[c] = inv_prev;
-            ctx.sync();
-        }
-        for (int r = nbp - 1 + ctx.tid; r <= nbp; r += ctx.nthreads) {         // the last column
-            if (r < nbp) Lp[r * LD + nbp - 1] *= inv_prev;
-            else yp[nbp - 1] *= inv_prev;
+            for (int r = nbp - 1 + ctx.tid; r <= nbp; r += ctx.nthreads) {         // the last column
+                if (r < nbp) Lp[r * LD + nbp - 1] *= inv_prev;
+                else yp[nbp - 1] *= inv_prev;
+            }
         }
         ctx.sync();
+        if (scal[6] != 0.0) return;                    // non-positive pivot (info is set)
         // ---- B2: rows below the triangle: l[c] = (a[c] - sum_{k<c} l[k] L11[c][k]) / L11[c][c], one thread per row
         for (int r = nbp + ctx.tid; r < Rn; r += ctx.nthreads) {
             double l[NB];

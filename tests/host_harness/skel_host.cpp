@@ -11,6 +11,7 @@ using namespace acino;
 struct HostCtx {
     int tid = 0, nthreads = 1;
     void sync() const {}
+    void sync_part(int) const {}
 };
 
 extern "C" {
