@@ -4,9 +4,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "acino_common.cuh"
 #include "skel_body.cuh"
+#include "stereo_body.cuh"
 
 namespace acino {
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
@@ -43,6 +45,14 @@ cudaError_t launch_skel_trial(int N, int P, int last_free, const double* x, cons
                               const double* hi, double* xt, cudaStream_t s);
 cudaError_t launch_skel_pred(int N, int P, const double* x, const double* xt, const double* gtot, const double* H,
                              const double* sw, double* pred, double* step, cudaStream_t s);
+cudaError_t launch_stereo_init(const StereoCam& c1, const StereoCam& c2, int V, int M, const double* obj, const double* img1,
+                               const double* img2, double* pose_out, double* cost_out, cudaStream_t s);
+cudaError_t launch_stereo_blocks(const StereoCam& c1, const StereoCam& c2, int V, int M, const double* obj, const double* img1,
+                                 const double* img2, const double* rel, const double* poses, double lam, int blocks,
+                                 double* out_cost, double* out_S, double* out_back, int* out_info, cudaStream_t s);
+cudaError_t launch_stereo_solve(int V, const double* S_all, double* d_rel, int* info, cudaStream_t s);
+cudaError_t launch_stereo_update(int V, const double* rel, const double* poses, const double* back, const double* d_rel,
+                                 double* rel_t, double* poses_t, cudaStream_t s);
 cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, const double* x_ext, const float* g,
                               const double* sw, const double* lo, const double* hi, double* gtot, unsigned char* fixed,
                               double* cost_s, cudaStream_t s);
@@ -103,6 +113,13 @@ struct acino_handle {
     SkelDesc skel;
     SkelDesc* d_skel = nullptr;
     bool have_skel = false;
+    // pairwise extrinsic calibration (stereo) problem: device buffers owned by the handle
+    StereoCam st_c1, st_c2;
+    int st_V = 0, st_M = 0;
+    double* st_buf = nullptr;          // obj | img1 | img2 | rel | rel_t | poses | poses_t | cost | S | back | d_rel | info
+    double *st_obj = nullptr, *st_img1 = nullptr, *st_img2 = nullptr, *st_rel = nullptr, *st_rel_t = nullptr, *st_poses = nullptr,
+           *st_poses_t = nullptr, *st_cost = nullptr, *st_S = nullptr, *st_back = nullptr, *st_drel = nullptr;
+    int* st_info = nullptr;
 };
 
 static thread_local std::string g_err;
@@ -187,6 +204,7 @@ int acino_destroy(acino_handle* h) {
     if (h->ws) cudaFree(h->ws);
     if (h->red_ws) cudaFree(h->red_ws);
     if (h->d_skel) cudaFree(h->d_skel);
+    if (h->st_buf) cudaFree(h->st_buf);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->pipe_ready) {
         cudaStreamDestroy(h->s_h2d);
@@ -752,6 +770,108 @@ int acino_skel_pred_dev(acino_handle* h, int n_frames, const double* x, const do
     if (!x || !xt || !gtot || !H || !sw || !pred || !step) return fail(h, ACINO_ERR_ARG, "acino_skel_pred_dev: NULL pointer");
     CK(launch_skel_pred(n_frames, P, x, xt, gtot, H, sw, pred, step, (cudaStream_t)cuda_stream));
     h->launches += 1;
+    return ACINO_OK;
+}
+
+// ---- pairwise fisheye extrinsic calibration (calib.py:125-134), host pointers --------------------
+static StereoCam make_stcam(const double* K, const double* D) {
+    StereoCam c;
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    for (int i = 0; i < 4; ++i) c.D[i] = D[i];
+    return c;
+}
+
+int acino_stereo_set(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1, const double* img2,
+                     const double* K1, const double* D1, const double* K2, const double* D2) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_stereo_set: NULL handle");
+    if (n_views < 1 || n_points < 4 || !obj || !img1 || !img2 || !K1 || !D1 || !K2 || !D2)
+        return fail(h, ACINO_ERR_ARG, "acino_stereo_set: need >= 1 view, >= 4 points per view and non-NULL arrays");
+    CK(cudaSetDevice(h->device));
+    const size_t V = (size_t)n_views, M = (size_t)n_points;
+    const size_t n_obj = pad64(M * 3), n_img = pad64(V * M * 2), n_pose = pad64(V * 12 * 2), n_view = pad64(V * 42);
+    const size_t total = n_obj + 2 * n_img + 64 + 64 + 2 * n_pose + pad64(2 * V) + 2 * n_view + 64 + 64;
+    if (h->st_buf) cudaFree(h->st_buf);
+    h->st_buf = nullptr;
+    CK(cudaMalloc((void**)&h->st_buf, total * sizeof(double)));
+    double* p = h->st_buf;
+    h->st_obj = p; p += n_obj;
+    h->st_img1 = p; p += n_img;
+    h->st_img2 = p; p += n_img;
+    h->st_rel = p; p += 64;
+    h->st_rel_t = p; p += 64;
+    h->st_poses = p; p += n_pose;
+    h->st_poses_t = p; p += n_pose;
+    h->st_cost = p; p += pad64(2 * V);
+    h->st_S = p; p += n_view;
+    h->st_back = p; p += n_view;
+    h->st_drel = p; p += 64;
+    h->st_info = (int*)p;
+    CK(cudaMemcpy(h->st_obj, obj, M * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->st_img1, img1, V * M * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->st_img2, img2, V * M * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    h->st_c1 = make_stcam(K1, D1);
+    h->st_c2 = make_stcam(K2, D2);
+    h->st_V = n_views;
+    h->st_M = n_points;
+    return ACINO_OK;
+}
+
+int acino_stereo_init(acino_handle* h, double* poses, double* cost) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_stereo_init: NULL handle");
+    if (!h->st_V) return fail(h, ACINO_ERR_STATE, "acino_stereo_init: no problem set (acino_stereo_set first)");
+    if (!poses || !cost) return fail(h, ACINO_ERR_ARG, "acino_stereo_init: NULL output");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t V = (size_t)h->st_V;
+    CK(launch_stereo_init(h->st_c1, h->st_c2, h->st_V, h->st_M, h->st_obj, h->st_img1, h->st_img2, h->st_poses, h->st_cost, s));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(poses, h->st_poses, V * 2 * 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cost, h->st_cost, V * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ACINO_OK;
+}
+
+// lambda < 0: cost of (rel, poses) only.  Otherwise one damped Gauss-Newton step from (rel, poses): trial point
+// (rel_t, poses_t) and its cost.  cost = sum of squared pixel errors over both cameras, summed in view order.
+int acino_stereo_step(acino_handle* h, const double* rel, const double* poses, double lambda, double* rel_t, double* poses_t,
+                      double* cost, int32_t* info) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_stereo_step: NULL handle");
+    if (!h->st_V) return fail(h, ACINO_ERR_STATE, "acino_stereo_step: no problem set (acino_stereo_set first)");
+    if (!rel || !poses || !cost || !info || (lambda >= 0 && (!rel_t || !poses_t)))
+        return fail(h, ACINO_ERR_ARG, "acino_stereo_step: NULL pointer");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int V = h->st_V, M = h->st_M;
+    CK(cudaMemcpyAsync(h->st_rel, rel, 12 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_poses, poses, (size_t)V * 12 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->st_info, 0, 2 * sizeof(int), s));
+    const double* rel_eval = h->st_rel;
+    const double* poses_eval = h->st_poses;
+    if (lambda >= 0) {
+        CK(launch_stereo_blocks(h->st_c1, h->st_c2, V, M, h->st_obj, h->st_img1, h->st_img2, h->st_rel, h->st_poses, lambda, 1,
+                                h->st_cost, h->st_S, h->st_back, h->st_info, s));
+        CK(launch_stereo_solve(V, h->st_S, h->st_drel, h->st_info + 1, s));
+        CK(launch_stereo_update(V, h->st_rel, h->st_poses, h->st_back, h->st_drel, h->st_rel_t, h->st_poses_t, s));
+        h->launches += 3;
+        rel_eval = h->st_rel_t;
+        poses_eval = h->st_poses_t;
+    }
+    CK(launch_stereo_blocks(h->st_c1, h->st_c2, V, M, h->st_obj, h->st_img1, h->st_img2, rel_eval, poses_eval, 0.0, 0, h->st_cost,
+                            nullptr, nullptr, nullptr, s));
+    h->launches += 1;
+    std::vector<double> cv((size_t)V);
+    int inf[2] = {0, 0};
+    CK(cudaMemcpyAsync(cv.data(), h->st_cost, (size_t)V * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(inf, h->st_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (lambda >= 0) {
+        CK(cudaMemcpyAsync(rel_t, h->st_rel_t, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(poses_t, h->st_poses_t, (size_t)V * 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    double c = 0;
+    for (int v = 0; v < V; ++v) c += cv[v];
+    *cost = c;
+    *info = inf[0] ? inf[0] : inf[1];
     return ACINO_OK;
 }
 

@@ -186,6 +186,25 @@ int acino_skel_pred_dev(acino_handle* h, int n_frames, const double* x, const do
                         const double* gtot, const double* H, const double* sw, double* pred,
                         double* step, void* cuda_stream);
 
+/* ---- pairwise extrinsic calibration of two fisheye cameras, fp64, host pointers -------------------
+ * Replaces calibrate_pair_extrinsics_fisheye (calib.py:125-134: cv2.fisheye.stereoCalibrate, CALIB_FIX_INTRINSIC):
+ * relative pose (R, T) of camera 2 w.r.t. camera 1 from n_views checkerboard views seen by both, by minimising the
+ * reprojection error in both cameras over (R, T) and one board pose per view.  obj [M][3] board corners (z = 0),
+ * img1 / img2 [V][M][2] pixels, K [3][3], D [4].  Poses are 12 doubles: R (row-major 3 x 3) then t.
+ * acino_stereo_set    uploads the problem (device buffers owned by the handle);
+ * acino_stereo_init   per view and camera: board pose from the planar homography + damped Gauss-Newton refinement:
+ *                     poses [V][2][12], cost [V][2] (sum of squared pixel errors; < 0 = failed);
+ * acino_stereo_step   lambda < 0: cost of (rel [12], poses [V][12] = board poses in camera 1) only; lambda >= 0: one
+ *                     Levenberg-Marquardt step (per-view blocks eliminated, rotations updated as R exp([d]x)) ->
+ *                     trial point rel_t, poses_t and ITS cost.  info != 0: a block was not positive definite.
+ * The accept / reject loop is driven from acinoset_b200/stereo.py. */
+int acino_stereo_set(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1,
+                     const double* img2, const double* K1, const double* D1, const double* K2,
+                     const double* D2);
+int acino_stereo_init(acino_handle* h, double* poses, double* cost);
+int acino_stereo_step(acino_handle* h, const double* rel, const double* poses, double lambda,
+                      double* rel_t, double* poses_t, double* cost, int32_t* info);
+
 /* ---- FTE solve building blocks (device pointers, stream-ordered) ------------------------------
  * Together they replace `opt.solve(m)` (all_optimizations.py:503-524): a projected
  * Levenberg-Marquardt loop on  F(x) = sum rho(w r) + sum_{n>=3,p} q_p (third difference / Ts^2)^2

@@ -248,13 +248,47 @@ def gen_pinhole(calib, utils):
     np.savez_compressed(os.path.join(HERE, "pinhole.npz"), **out)
 
 
+def gen_stereo(calib, utils):
+    """Pairwise extrinsic calibration (calib.py:125-134): cv2.fisheye.stereoCalibrate called exactly as the reference
+    calls it (CALIB_FIX_INTRINSIC, 100 iterations, eps 1e-5) on the shipped checkerboard points of sunday_amelia -
+    the runs whose RMS the reference's notebook prints (calib_with_gui.ipynb:665,673: 0.32182 / 0.36876 px)."""
+    import cv2
+
+    base = os.path.join(REF, "data", "sunday_amelia", "extrinsic_calib")
+    out = {}
+    for tag, scene, cams in [("rot12", "4_cam_scene_rotating.json", (1, 2)), ("sta34", "4_cam_scene_static.json", (3, 4))]:
+        K, D, R, t, res = utils.load_scene(os.path.join(base, scene))
+        pts, fns = [], []
+        for c in cams:
+            d = json.load(open(os.path.join(base, "points", f"points_cam{c}.json")))
+            fns.append(list(d["points"].keys()))
+            pts.append(np.array(list(d["points"].values()), dtype=np.float32))
+            board_shape, bel = tuple(d["board_shape"]), d.get("board_edge_len", d.get("board_square_len"))
+        common = [f for f in fns[0] if f in fns[1]]
+        p1 = np.array([pts[0][fns[0].index(f)] for f in common], dtype=np.float32)
+        p2 = np.array([pts[1][fns[1].index(f)] for f in common], dtype=np.float32)
+        obj = utils.create_board_object_pts(board_shape, bel)
+        n = len(common)
+        ia, ib = (cams[0] - 1, cams[1] - 1) if len(K) == 4 else (0, 1)
+        objp = np.repeat(obj[np.newaxis], n, axis=0).reshape(n, 1, -1, 3)
+        res_cv = cv2.fisheye.stereoCalibrate(objp, p1.reshape(n, 1, -1, 2), p2.reshape(n, 1, -1, 2), K[ia].copy(), D[ia].copy(),
+                                             K[ib].copy(), D[ib].copy(), res, flags=cv2.fisheye.CALIB_FIX_INTRINSIC,
+                                             criteria=(cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 100, 1e-5))
+        out.update({f"{tag}_obj": obj, f"{tag}_img1": p1, f"{tag}_img2": p2, f"{tag}_K1": K[ia], f"{tag}_D1": D[ia],
+                    f"{tag}_K2": K[ib], f"{tag}_D2": D[ib], f"{tag}_rms": res_cv[0], f"{tag}_R": res_cv[5], f"{tag}_T": res_cv[6],
+                    f"{tag}_scene_R": R[[ia, ib]], f"{tag}_scene_t": t[[ia, ib]], f"{tag}_res": np.array(res)})
+        print("stereo", tag, "views", n, "rms", res_cv[0])
+    out["notebook_rms"] = np.array([0.32182, 0.36876])
+    np.savez_compressed(os.path.join(HERE, "stereo.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-sympy-jac", action="store_true")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     calib, utils = ref_shim.load_reference_calib()
-    todo = args.only.split(",") if args.only else ["fk", "fisheye", "loss", "tri", "generic", "sba", "pinhole"]
+    todo = args.only.split(",") if args.only else ["fk", "fisheye", "loss", "tri", "generic", "sba", "pinhole", "stereo"]
     if "fisheye" in todo:
         gen_fisheye(calib, utils)
     if "loss" in todo:
@@ -267,6 +301,8 @@ def main():
         gen_sba(calib, utils)
     if "pinhole" in todo:
         gen_pinhole(calib, utils)
+    if "stereo" in todo:
+        gen_stereo(calib, utils)
     if "fk" in todo:
         gen_cheetah_fk(args.skip_sympy_jac)
 
