@@ -91,6 +91,8 @@ def _load():
     lib.acino_skel_pred_dev.restype = ci
     lib.acino_stereo_set.argtypes = [vp, ci, ci] + [vp] * 7
     lib.acino_stereo_set.restype = ci
+    lib.acino_stereo_set_pinhole.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, ci, vp, vp, ci]
+    lib.acino_stereo_set_pinhole.restype = ci
     lib.acino_stereo_init.argtypes = [vp, vp, vp]
     lib.acino_stereo_init.restype = ci
     lib.acino_stereo_step.argtypes = [vp, vp, vp, cd, vp, vp, vp, vp]
@@ -139,7 +141,7 @@ EXPORTED = [
     "acino_project_points_pinhole", "acino_undistort_points_pinhole", "acino_triangulate_points_pinhole",
     "acino_skel_set", "acino_skel_eval_dev", "acino_skel_eval", "acino_skel_prepare_dev", "acino_skel_assemble_dev",
     "acino_band_solve_dev", "acino_skel_trial_dev", "acino_skel_pred_dev",
-    "acino_stereo_set", "acino_stereo_init", "acino_stereo_step",
+    "acino_stereo_set", "acino_stereo_set_pinhole", "acino_stereo_init", "acino_stereo_step",
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
     "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_eval_dev",

@@ -774,17 +774,36 @@ int acino_skel_pred_dev(acino_handle* h, int n_frames, const double* x, const do
 }
 
 // ---- pairwise fisheye extrinsic calibration (calib.py:125-134), host pointers --------------------
-static StereoCam make_stcam(const double* K, const double* D) {
+static StereoCam make_stcam(const double* K, const double* D, int nd, int model) {
     StereoCam c;
     c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
-    for (int i = 0; i < 4; ++i) c.D[i] = D[i];
+    for (int i = 0; i < 12; ++i) c.D[i] = i < nd ? D[i] : 0.0;
+    c.model = model;
     return c;
 }
+
+static int stereo_set_impl(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1, const double* img2,
+                           const double* K1, const double* D1, int nd1, const double* K2, const double* D2, int nd2, int model);
 
 int acino_stereo_set(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1, const double* img2,
                      const double* K1, const double* D1, const double* K2, const double* D2) {
     if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_stereo_set: NULL handle");
-    if (n_views < 1 || n_points < 4 || !obj || !img1 || !img2 || !K1 || !D1 || !K2 || !D2)
+    if (!D1 || !D2) return fail(h, ACINO_ERR_ARG, "acino_stereo_set: NULL distortion");
+    return stereo_set_impl(h, n_views, n_points, obj, img1, img2, K1, D1, 4, K2, D2, 4, 0);
+}
+
+int acino_stereo_set_pinhole(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1, const double* img2,
+                             const double* K1, const double* dist1, int n_dist1, const double* K2, const double* dist2, int n_dist2) {
+    if (!h) return fail(nullptr, ACINO_ERR_ARG, "acino_stereo_set_pinhole: NULL handle");
+    if (bad_dist(dist1, n_dist1) || bad_dist(dist2, n_dist2))
+        return fail(h, ACINO_ERR_ARG, "acino_stereo_set_pinhole: 0..12 distortion coefficients (tilt terms must be 0)");
+    return stereo_set_impl(h, n_views, n_points, obj, img1, img2, K1, dist1, n_dist1 < 12 ? n_dist1 : 12, K2, dist2,
+                           n_dist2 < 12 ? n_dist2 : 12, 1);
+}
+
+static int stereo_set_impl(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1, const double* img2,
+                           const double* K1, const double* D1, int nd1, const double* K2, const double* D2, int nd2, int model) {
+    if (n_views < 1 || n_points < 4 || !obj || !img1 || !img2 || !K1 || !K2)
         return fail(h, ACINO_ERR_ARG, "acino_stereo_set: need >= 1 view, >= 4 points per view and non-NULL arrays");
     CK(cudaSetDevice(h->device));
     const size_t V = (size_t)n_views, M = (size_t)n_points;
@@ -809,8 +828,8 @@ int acino_stereo_set(acino_handle* h, int n_views, int n_points, const double* o
     CK(cudaMemcpy(h->st_obj, obj, M * 3 * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->st_img1, img1, V * M * 2 * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->st_img2, img2, V * M * 2 * sizeof(double), cudaMemcpyHostToDevice));
-    h->st_c1 = make_stcam(K1, D1);
-    h->st_c2 = make_stcam(K2, D2);
+    h->st_c1 = make_stcam(K1, D1, nd1, model);
+    h->st_c2 = make_stcam(K2, D2, nd2, model);
     h->st_V = n_views;
     h->st_M = n_points;
     return ACINO_OK;

@@ -24,7 +24,9 @@
 namespace acino {
 
 struct StereoCam {
-    double fx, fy, cx, cy, D[4];
+    double fx, fy, cx, cy;
+    double D[12];        // model 0 (fisheye): k1..k4;  model 1 (pinhole): k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 (OpenCV order)
+    int model;
 };
 
 // per-view record sizes (doubles)
@@ -53,8 +55,37 @@ ST_HD void st_exp(const double* w, double* R) {
     R[6] = -a * y + b * x * z;      R[7] = a * x + b * y * z;        R[8] = 1 - b * (x * x + y * y);
 }
 
+// cv2.projectPoints model (plumb-bob / rational / thin-prism, calib.py:64-66) and its 2 x 3 Jacobian
+ST_HD void st_project_pinhole(const StereoCam& cam, const double* Xc, double* uv, double* J) {
+    const double* k = cam.D;
+    const double iz = 1.0 / Xc[2], x = Xc[0] * iz, y = Xc[1] * iz;
+    const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const double Nn = 1 + k[0] * r2 + k[1] * r4 + k[4] * r6, Dn = 1 + k[5] * r2 + k[6] * r4 + k[7] * r6;
+    const double cd = Nn / Dn;
+    const double xd = x * cd + 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r4;
+    const double yd = y * cd + k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r4;
+    uv[0] = cam.fx * xd + cam.cx;
+    uv[1] = cam.fy * yd + cam.cy;
+    if (J) {
+        const double dN = k[0] + 2 * k[1] * r2 + 3 * k[4] * r4, dD = k[5] + 2 * k[6] * r2 + 3 * k[7] * r4;
+        const double dcd = (dN * Dn - Nn * dD) / (Dn * Dn);            // d cd / d r2
+        const double sx = k[8] + 2 * k[9] * r2, sy = k[10] + 2 * k[11] * r2;
+        const double xx = cd + 2 * x * x * dcd + 2 * k[2] * y + 6 * k[3] * x + 2 * x * sx;   // d xd / d x
+        const double xy = 2 * x * y * dcd + 2 * k[2] * x + 2 * k[3] * y + 2 * y * sx;        // d xd / d y
+        const double yx = 2 * x * y * dcd + 2 * k[2] * x + 2 * k[3] * y + 2 * x * sy;        // d yd / d x
+        const double yy = cd + 2 * y * y * dcd + 6 * k[2] * y + 2 * k[3] * x + 2 * y * sy;   // d yd / d y
+        const double fxi = cam.fx * iz, fyi = cam.fy * iz;
+        J[0] = fxi * xx; J[1] = fxi * xy; J[2] = -fxi * (xx * x + xy * y);
+        J[3] = fyi * yx; J[4] = fyi * yy; J[5] = -fyi * (yx * x + yy * y);
+    }
+}
+
 // Kannala-Brandt projection of a camera-frame point and its 2 x 3 Jacobian (same model as acino_common.cuh)
 ST_HD void st_project(const StereoCam& cam, const double* Xc, double* uv, double* J) {
+    if (cam.model == 1) {
+        st_project_pinhole(cam, Xc, uv, J);
+        return;
+    }
     const double iz = 1.0 / Xc[2], a = Xc[0] * iz, b = Xc[1] * iz;
     const double r2 = a * a + b * b + 1e-12, r = sqrt(r2), ir = 1.0 / r;
     const double th = atan(r), th2 = th * th;
@@ -75,6 +106,22 @@ ST_HD void st_project(const StereoCam& cam, const double* Xc, double* uv, double
 // cv2.fisheye.undistortPoints (pixel -> normalised coordinates), Newton on theta_d(theta); returns false when it fails
 ST_HD bool st_undistort(const StereoCam& cam, double u, double v, double* xy) {
     const double px = (u - cam.cx) / cam.fx, py = (v - cam.cy) / cam.fy;
+    if (cam.model == 1) {            // fixed-point inversion of the pinhole distortion (initialisation only: 20 rounds)
+        const double* k = cam.D;
+        double x = px, y = py;
+        for (int j = 0; j < 20; ++j) {
+            const double r2 = x * x + y * y;
+            const double icd = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icd < 0) return false;
+            const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (px - dx) * icd;
+            y = (py - dy) * icd;
+        }
+        xy[0] = x;
+        xy[1] = y;
+        return true;
+    }
     double thd = sqrt(px * px + py * py);
     if (thd > 1.5707963267948966) thd = 1.5707963267948966;
     if (thd < 1e-8) { xy[0] = px; xy[1] = py; return true; }

@@ -2,6 +2,7 @@
 (/root/reference/src/calib/calib.py:125-134,141-194; src/calib/app.py:84-124):
 
     calibrate_pair_extrinsics_fisheye(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, camera_resolution) -> (rms, r, t)
+    calibrate_pair_extrinsics(...)  - the standard-camera-model twin (calib.py:41-49, cv2.stereoCalibrate)
     calibrate_pairwise_extrinsics(calib_func, img_pts_arr, fnames_arr, k_arr, d_arr, camera_resolution, board_shape,
                                   board_edge_len) -> (r_arr, t_arr)
     calibrate_fisheye_extrinsics_pairwise(camera_fpaths, points_fpaths, out_fpath)
@@ -27,11 +28,15 @@ class _GpuBackend:
     def __init__(self, device=0):
         self.h = _fte.get_handle(device)
 
-    def set(self, obj, img1, img2, K1, D1, K2, D2):
+    def set(self, obj, img1, img2, K1, D1, K2, D2, pinhole=False):
         self.V, self.M = img1.shape[0], img1.shape[1]
         p = _lib._np_ptr
-        self.h._check(_lib.lib.acino_stereo_set(self.h._h, self.V, self.M, p(obj), p(img1), p(img2), p(K1), p(D1), p(K2), p(D2)),
-                      "acino_stereo_set")
+        if pinhole:
+            self.h._check(_lib.lib.acino_stereo_set_pinhole(self.h._h, self.V, self.M, p(obj), p(img1), p(img2), p(K1), p(D1), D1.size,
+                                                            p(K2), p(D2), D2.size), "acino_stereo_set_pinhole")
+        else:
+            self.h._check(_lib.lib.acino_stereo_set(self.h._h, self.V, self.M, p(obj), p(img1), p(img2), p(K1), p(D1), p(K2), p(D2)),
+                          "acino_stereo_set")
 
     def init(self):
         poses = np.empty((self.V, 2, 12))
@@ -60,8 +65,9 @@ def _median_relative_pose(poses):
 
 
 def solve_pair(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, max_iter=100, eps=1e-10, backend=None, device=0,
-               return_info=False):
-    """-> (rms, R (3,3), T (3,1)) [, info].  img_pts_* (V, M, 2) pixels of the same V views, obj_pts (M, 3)."""
+               return_info=False, pinhole=False):
+    """-> (rms, R (3,3), T (3,1)) [, info].  img_pts_* (V, M, 2) pixels of the same V views, obj_pts (M, 3).
+    pinhole=True: d_* are OpenCV's standard-model coefficients (up to 12) instead of the 4 fisheye ones."""
     obj = np.ascontiguousarray(obj_pts, dtype=np.float64).reshape(-1, 3)
     M = obj.shape[0]
     img1 = np.ascontiguousarray(img_pts_1, dtype=np.float64).reshape(-1, M, 2)
@@ -70,9 +76,10 @@ def solve_pair(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, max_iter=100, 
         raise ValueError("img_pts_1 and img_pts_2 must hold the same (>= 1) views of the same board")
     V = img1.shape[0]
     K1, K2 = (np.ascontiguousarray(k, dtype=np.float64).reshape(3, 3) for k in (k_1, k_2))
-    D1, D2 = (np.ascontiguousarray(np.asarray(d, dtype=np.float64).reshape(-1)[:4]) for d in (d_1, d_2))
+    nd = 14 if pinhole else 4
+    D1, D2 = (np.ascontiguousarray(np.zeros(0) if d is None else np.asarray(d, dtype=np.float64).reshape(-1)[:nd]) for d in (d_1, d_2))
     be = _GpuBackend(device) if backend is None else backend
-    be.set(obj, img1, img2, K1, D1, K2, D2)
+    be.set(obj, img1, img2, K1, D1, K2, D2, pinhole=pinhole)
     poses2, cost0 = be.init()
     if np.any(cost0 < 0):
         raise _lib.AcinoError(f"board pose initialisation failed for views {np.nonzero((cost0 < 0).any(axis=1))[0].tolist()}")
@@ -109,6 +116,24 @@ def calibrate_pair_extrinsics_fisheye(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k
                       d_2, device=device)
 
 
+def calibrate_pair_extrinsics(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, camera_resolution=None, device=0,
+                              rational_model=False, backend=None):
+    """calib.py:41-49 (cv2.stereoCalibrate, flags = CALIB_FIX_INTRINSIC only): the standard-camera-model twin.
+
+    Reference behaviour kept by default: without CALIB_RATIONAL_MODEL / CALIB_THIN_PRISM_MODEL in the flags OpenCV drops
+    k4..k6 and s1..s4 of the distortion vectors it is given, so the reference's pair calibration runs on the 5-coefficient
+    model even though its intrinsics were calibrated with 8 (calib.py:18) - verified against cv2 4.13.0 to 1e-8
+    (tests/golden/stereo.npz).  ``rational_model=True`` uses every coefficient."""
+    n = np.asarray(img_pts_1).shape[0]
+
+    def coeffs(d):
+        d = np.zeros(0) if d is None else np.asarray(d, dtype=np.float64).reshape(-1)
+        return d if rational_model else d[:5]
+
+    return solve_pair(obj_pts, np.asarray(img_pts_1).reshape(n, -1, 2), np.asarray(img_pts_2).reshape(n, -1, 2), k_1, coeffs(d_1),
+                      k_2, coeffs(d_2), device=device, pinhole=True, backend=backend)
+
+
 def calibrate_pairwise_extrinsics(calib_func, img_pts_arr, fnames_arr, k_arr, d_arr, camera_resolution, board_shape,
                                   board_edge_len):
     """calib.py:141-194: camera 1 at R1 = [[1,0,0],[0,0,-1],[0,1,0]], T1 = 0 (world z up), every next camera placed by
@@ -134,7 +159,13 @@ def calibrate_pairwise_extrinsics(calib_func, img_pts_arr, fnames_arr, k_arr, d_
     return r_arr, t_arr
 
 
-def calibrate_fisheye_extrinsics_pairwise(camera_fpaths, points_fpaths, out_fpath, device=0):
+def calibrate_standard_extrinsics_pairwise(camera_fpaths, points_fpaths, out_fpath, device=0):
+    """app.py:119-120"""
+    return calibrate_fisheye_extrinsics_pairwise(camera_fpaths, points_fpaths, out_fpath, device=device,
+                                                 _pair_func=calibrate_pair_extrinsics)
+
+
+def calibrate_fisheye_extrinsics_pairwise(camera_fpaths, points_fpaths, out_fpath, device=0, _pair_func=None):
     """app.py:84-124: camera files + point files -> scene file with the chained pairwise extrinsics."""
     from . import utils
 
@@ -153,7 +184,8 @@ def calibrate_fisheye_extrinsics_pairwise(camera_fpaths, points_fpaths, out_fpat
         assert board_shape is None or tuple(board_shape) == tuple(bs)
         board_shape, board_edge_len = bs, bel
     print("camera pair\tcommon frames\tRMS reprojection error")
-    r_arr, t_arr = calibrate_pairwise_extrinsics(lambda *a: calibrate_pair_extrinsics_fisheye(*a, device=device), img_pts_arr,
+    pair = calibrate_pair_extrinsics_fisheye if _pair_func is None else _pair_func
+    r_arr, t_arr = calibrate_pairwise_extrinsics(lambda *a: pair(*a, device=device), img_pts_arr,
                                                  fnames_arr, k_arr, d_arr, cam_res, board_shape, board_edge_len)
     utils.save_scene(out_fpath, np.array(k_arr), np.array(d_arr), np.array(r_arr), np.array(t_arr), cam_res)
     return r_arr, t_arr

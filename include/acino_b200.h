@@ -201,6 +201,12 @@ int acino_skel_pred_dev(acino_handle* h, int n_frames, const double* x, const do
 int acino_stereo_set(acino_handle* h, int n_views, int n_points, const double* obj, const double* img1,
                      const double* img2, const double* K1, const double* D1, const double* K2,
                      const double* D2);
+/* the same problem for the standard camera model (calibrate_pair_extrinsics, calib.py:41-49: cv2.stereoCalibrate with
+ * CALIB_FIX_INTRINSIC); dist as in acino_project_points_pinhole */
+int acino_stereo_set_pinhole(acino_handle* h, int n_views, int n_points, const double* obj,
+                             const double* img1, const double* img2, const double* K1,
+                             const double* dist1, int n_dist1, const double* K2, const double* dist2,
+                             int n_dist2);
 int acino_stereo_init(acino_handle* h, double* poses, double* cost);
 int acino_stereo_step(acino_handle* h, const double* rel, const double* poses, double lambda,
                       double* rel_t, double* poses_t, double* cost, int32_t* info);

@@ -278,6 +278,29 @@ def gen_stereo(calib, utils):
                     f"{tag}_K2": K[ib], f"{tag}_D2": D[ib], f"{tag}_rms": res_cv[0], f"{tag}_R": res_cv[5], f"{tag}_T": res_cv[6],
                     f"{tag}_scene_R": R[[ia, ib]], f"{tag}_scene_t": t[[ia, ib]], f"{tag}_res": np.array(res)})
         print("stereo", tag, "views", n, "rms", res_cv[0])
+    # standard camera model: the reference's calibrate_pair_extrinsics (calib.py:41-49), run unmodified, on synthetic boards
+    rng = np.random.default_rng(17)
+    PIN_NOISE = 0.0      # cv2.stereoCalibrate stops early (30 iterations, eps 1e-5): with noise it ends far from the minimum
+    K1 = np.array([[1210.0, 0, 960.0], [0, 1198.0, 540.0], [0, 0, 1]])
+    K2 = np.array([[1180.0, 0, 950.0], [0, 1185.0, 545.0], [0, 0, 1]])
+    d1 = np.array([0.11, -0.05, 0.001, -0.002, 0.01, 0.02, -0.01, 0.003])
+    d2 = np.array([-0.08, 0.03, -0.0007, 0.0012, 0.004, 0.015, -0.006, 0.001])
+    obj = utils.create_board_object_pts((9, 6), 0.05).astype(np.float32)
+    R_true = cv2.Rodrigues(np.array([0.04, -0.35, 0.02]))[0]
+    T_true = np.array([-0.55, 0.02, 0.08])
+    V = 14
+    i1, i2 = np.empty((V, 54, 2), np.float32), np.empty((V, 54, 2), np.float32)
+    for v in range(V):
+        Rv = cv2.Rodrigues(rng.normal(0, 0.25, 3))[0]
+        tv = np.array([rng.uniform(-0.25, 0.25), rng.uniform(-0.15, 0.15), rng.uniform(0.9, 1.5)])
+        u1 = calib.project_points(obj.astype(np.float64), K1, d1, Rv, tv)
+        u2 = calib.project_points(obj.astype(np.float64), K2, d2, R_true @ Rv, R_true @ tv + T_true)
+        i1[v] = u1 + rng.normal(0, PIN_NOISE, u1.shape)
+        i2[v] = u2 + rng.normal(0, PIN_NOISE, u2.shape)
+    rms_p, r_p, t_p = calib.calibrate_pair_extrinsics(obj, i1.reshape(V, 9, 6, 2), i2.reshape(V, 9, 6, 2), K1, d1, K2, d2, (1920, 1080))
+    out.update(pin_obj=obj, pin_img1=i1, pin_img2=i2, pin_K1=K1, pin_D1=d1, pin_K2=K2, pin_D2=d2, pin_rms=rms_p, pin_R=r_p,
+               pin_T=t_p, pin_R_true=R_true, pin_T_true=T_true)
+    print("stereo pinhole: rms", rms_p, "dR", np.abs(r_p - R_true).max(), "dT", np.abs(t_p.ravel() - T_true).max())
     out["notebook_rms"] = np.array([0.32182, 0.36876])
     np.savez_compressed(os.path.join(HERE, "stereo.npz"), **out)
 

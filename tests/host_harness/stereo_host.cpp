@@ -15,23 +15,24 @@ static StereoCam g_c1, g_c2;
 static int g_V = 0, g_M = 0;
 static std::vector<double> g_obj, g_img1, g_img2;
 
-static StereoCam make_cam(const double* K, const double* D) {
+static StereoCam make_cam(const double* K, const double* D, int nd, int model) {
     StereoCam c;
     c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
-    for (int i = 0; i < 4; ++i) c.D[i] = D[i];
+    for (int i = 0; i < 12; ++i) c.D[i] = i < nd ? D[i] : 0.0;
+    c.model = model;
     return c;
 }
 
 extern "C" {
 
 int stereo_host_set(int V, int M, const double* obj, const double* img1, const double* img2, const double* K1, const double* D1,
-                    const double* K2, const double* D2) {
+                    int nd1, const double* K2, const double* D2, int nd2, int model) {
     g_V = V; g_M = M;
     g_obj.assign(obj, obj + (size_t)M * 3);
     g_img1.assign(img1, img1 + (size_t)V * M * 2);
     g_img2.assign(img2, img2 + (size_t)V * M * 2);
-    g_c1 = make_cam(K1, D1);
-    g_c2 = make_cam(K2, D2);
+    g_c1 = make_cam(K1, D1, nd1, model);
+    g_c2 = make_cam(K2, D2, nd2, model);
     return 0;
 }
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import golden
-from test_stereo_host import check_against_reference
+from test_stereo_host import check_against_reference, check_pinhole_against_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -50,3 +50,10 @@ def test_calibrate_fisheye_extrinsics_pairwise_writes_the_scene(tmp_path):
     assert np.allclose(r_s[0], R1) and np.allclose(t_s[0], 0)
     assert np.abs(r_s[1] - g["sta34_R"] @ R1).max() < 1e-5 and np.abs(t_s[1].ravel() - g["sta34_T"].ravel()).max() < 1e-5
     assert tuple(res_s) == res and np.allclose(k_arr[1], g["sta34_K2"])
+
+
+def test_pinhole_pair_calibration_matches_reference():
+    """calibrate_pair_extrinsics (calib.py:41-49) by name, incl. the reference's dropped rational coefficients."""
+    from acinoset_b200 import stereo
+
+    check_pinhole_against_reference(stereo.calibrate_pair_extrinsics)

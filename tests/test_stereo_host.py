@@ -23,9 +23,10 @@ class HostBackend:
     def __init__(self, lib):
         self.lib = lib
 
-    def set(self, obj, img1, img2, K1, D1, K2, D2):
+    def set(self, obj, img1, img2, K1, D1, K2, D2, pinhole=False):
         self.V, self.M = img1.shape[0], img1.shape[1]
-        self.lib.stereo_host_set(self.V, self.M, _p(obj), _p(img1), _p(img2), _p(K1), _p(D1), _p(K2), _p(D2))
+        self.lib.stereo_host_set(self.V, self.M, _p(obj), _p(img1), _p(img2), _p(K1), _p(D1), min(D1.size, 12), _p(K2), _p(D2),
+                                 min(D2.size, 12), 1 if pinhole else 0)
 
     def init(self):
         poses, cost = np.empty((self.V, 2, 12)), np.empty((self.V, 2))
@@ -138,3 +139,25 @@ def test_pairwise_chain_with_injected_calib_func():
     assert np.allclose(r_arr[2], rel[1][0] @ rel[0][0] @ R1) and np.allclose(t_arr[2], rel[1][0] @ rel[0][1] + rel[1][1])
     with pytest.raises(AssertionError):
         stereo.calibrate_pairwise_extrinsics(fake, pts[:2], [["a"], ["b"]], [np.eye(3)] * 2, [np.zeros(4)] * 2, (10, 10), (9, 6), 0.03)
+
+
+def check_pinhole_against_reference(pair_func):
+    """Shared with the GPU test: the reference's calibrate_pair_extrinsics (cv2.stereoCalibrate, run unmodified) on
+    noise-free synthetic boards seen through the 8-coefficient rational model of calib.py:18.
+    pair_func(obj, img1, img2, k1, d1, k2, d2, resolution, rational_model=...) -> (rms, r, t)."""
+    g = golden("stereo.npz")
+    a = (g["pin_obj"], g["pin_img1"].reshape(-1, 9, 6, 2), g["pin_img2"].reshape(-1, 9, 6, 2), g["pin_K1"], g["pin_D1"], g["pin_K2"],
+         g["pin_D2"], (1920, 1080))
+    # default = the reference's behaviour: OpenCV ignores k4..k6 without CALIB_RATIONAL_MODEL -> a 0.49 px model error
+    rms, R, T = pair_func(*a, rational_model=False)
+    assert abs(rms - float(g["pin_rms"])) < 1e-6
+    assert np.abs(R - g["pin_R"]).max() < 1e-6 and np.abs(T - g["pin_T"]).max() < 1e-6 and T.shape == (3, 1)
+    # every coefficient used: the noise-free ground truth comes back (pixels were rounded to float32)
+    rms_f, R_f, T_f = pair_func(*a, rational_model=True)
+    assert rms_f < 1e-4 and np.abs(R_f - g["pin_R_true"]).max() < 1e-7 and np.abs(T_f.ravel() - g["pin_T_true"]).max() < 1e-6
+
+
+def test_pinhole_pair_calibration_matches_reference(backend):
+    from acinoset_b200 import stereo
+
+    check_pinhole_against_reference(lambda *a, **k: stereo.calibrate_pair_extrinsics(*a, backend=backend, **k))
