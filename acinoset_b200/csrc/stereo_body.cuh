@@ -29,9 +29,7 @@ struct StereoCam {
     int model;
 };
 
-// per-view record sizes (doubles)
-constexpr int ST_POSE = 12;          // R (9, row-major) + t (3)
-constexpr int ST_BLK = 6 + 36 + 36;  // per view: (V + lam diag V)^-1 gv (6), (V + lam diag V)^-1 W^T (6 x 6), Schur term (6 x 6) ... see stereo_view_blocks
+constexpr int ST_POSE = 12;          // a pose record: R (9, row-major) + t (3)
 
 ST_HD void st_mm(const double* a, const double* b, double* c) {
     for (int i = 0; i < 3; ++i)

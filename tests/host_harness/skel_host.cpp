@@ -1,7 +1,11 @@
 // TEST HARNESS (not part of the library): compiles acinoset_b200/csrc/skel_body.cuh - the exact source of the
 // generic-skeleton CUDA kernels - for the host with a one-thread context, so that `pytest -m "not gpu"` can check the
 // kernel arithmetic against the NumPy oracle in a container without a GPU.  Built by tests/test_skel_host.py with g++.
+#include <pthread.h>
+
 #include <cstring>
+#include <map>
+#include <thread>
 #include <vector>
 
 #include "../../acinoset_b200/csrc/skel_body.cuh"
@@ -13,6 +17,40 @@ struct HostCtx {
     void sync() const {}
     void sync_part(int) const {}
 };
+
+// Multi-threaded context: T real threads and real barriers, so that the kernels' thread mappings (strides, 2-D
+// decompositions, the participants-only barrier of the panel step) are exercised on the CPU as well - a CTA in slow motion.
+struct MtShared {
+    int nthreads;
+    pthread_barrier_t all;
+    std::map<int, pthread_barrier_t*> part;
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    explicit MtShared(int n) : nthreads(n) { pthread_barrier_init(&all, nullptr, n); }
+    pthread_barrier_t* part_barrier(int n) {
+        if (n > nthreads) n = nthreads;
+        pthread_mutex_lock(&mu);
+        pthread_barrier_t*& b = part[n];
+        if (!b) {
+            b = new pthread_barrier_t;
+            pthread_barrier_init(b, nullptr, n);
+        }
+        pthread_mutex_unlock(&mu);
+        return b;
+    }
+};
+struct MtCtx {
+    int tid, nthreads;
+    MtShared* sh;
+    void sync() const { pthread_barrier_wait(&sh->all); }
+    void sync_part(int n) const { pthread_barrier_wait(sh->part_barrier(n)); }
+};
+template <typename F>
+static void run_mt(int nthreads, F f) {
+    MtShared sh(nthreads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t] { f(MtCtx{t, nthreads, &sh}); });
+    for (auto& t : th) t.join();
+}
 
 extern "C" {
 
@@ -57,6 +95,27 @@ void skel_host_eval(const SkelDesc* S, int n_frames, const double* x, const doub
     for (int n = 0; n < n_frames; ++n)
         skel_eval_frame(*S, ctx, x + (size_t)n * P, meas + n * mo * 2, w + n * mo, cost ? cost + n : nullptr,
                         g ? g + (size_t)n * P : nullptr, H ? H + (size_t)n * (P * (P + 1) / 2) : nullptr, sm.data());
+}
+
+// the same, ONE frame at a time on `nthreads` real threads with real barriers
+void skel_host_eval_mt(const SkelDesc* S, int n_frames, const double* x, const double* meas, const double* w, double* cost,
+                       double* g, double* H, int nthreads) {
+    const int P = 3 + 3 * S->n_parts;
+    const size_t mo = (size_t)S->n_cams * S->n_out;
+    std::vector<double> sm(SkelSmemLayout(S->n_links, S->n_out).total);
+    for (int n = 0; n < n_frames; ++n)
+        run_mt(nthreads, [&](const MtCtx& ctx) {
+            skel_eval_frame(*S, ctx, x + (size_t)n * P, meas + n * mo * 2, w + n * mo, cost ? cost + n : nullptr,
+                            g ? g + (size_t)n * P : nullptr, H ? H + (size_t)n * (P * (P + 1) / 2) : nullptr, sm.data());
+        });
+}
+
+int skel_host_band_solve_mt(long long n, int hb, int nb, double* AB, double* x, int* info, int nthreads) {
+    std::vector<double> sm(band_panel_doubles(hb, nb));
+    if (nb == 16) run_mt(nthreads, [&](const MtCtx& ctx) { band_cholesky_solve<16>(ctx, n, hb, AB, x, info, sm.data()); });
+    else if (nb == 8) run_mt(nthreads, [&](const MtCtx& ctx) { band_cholesky_solve<8>(ctx, n, hb, AB, x, info, sm.data()); });
+    else return -1;
+    return 0;
 }
 
 void skel_host_prepare(int N, int P, int last_free, const double* x, const double* g, const double* sw, const double* lo,

@@ -16,7 +16,7 @@ from oracle import skel_fte
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     out = tmp_path_factory.mktemp("skel_host") / "skel_host.so"
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out),
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", str(out),
                            os.path.join(ROOT, "tests", "host_harness", "skel_host.cpp")])
     return ctypes.CDLL(str(out))
 
@@ -178,3 +178,47 @@ def test_band_cholesky_random_systems(harness):
         assert info[0] == 0
         ref = np.linalg.solve(A, b)
         assert np.abs(x - ref).max() < 1e-10 * max(1.0, np.abs(ref).max()), (n, hb, nb)
+
+
+def test_kernel_thread_mappings_with_real_threads(harness, dummy_cams):
+    """The same bodies on T real threads with real barriers (a CTA in slow motion): the strided / 2-D thread mappings and
+    the participants-only barrier of the panel step give the one-thread results."""
+    rng = np.random.default_rng(9)
+    for n, hb, nb, T in [(131, 20, 16, 64), (200, 45, 8, 128), (97, 30, 16, 48), (40, 39, 8, 128)]:
+        A = np.zeros((n, n))
+        for i in range(n):
+            for k in range(1, min(i, hb) + 1):
+                A[i, i - k] = A[i - k, i] = rng.normal()
+        A += np.diag(np.abs(A).sum(1) + rng.uniform(0.5, 2.0, n))
+        AB = np.zeros((n, hb + 1))
+        for i in range(n):
+            for k in range(min(i, hb) + 1):
+                AB[i, k] = A[i, i - k]
+        b = rng.normal(size=n)
+        AB1, x1, AB2, x2 = AB.copy(), b.copy(), AB.copy(), b.copy()
+        info = np.zeros(1, dtype=np.int32)
+        harness.skel_host_band_solve(ctypes.c_longlong(n), hb, nb, _ptr(AB1), _ptr(x1), _ptr(info))
+        assert harness.skel_host_band_solve_mt(ctypes.c_longlong(n), hb, nb, _ptr(AB2), _ptr(x2), _ptr(info), T) == 0
+        assert info[0] == 0
+        assert np.array_equal(x1, x2) and np.array_equal(AB1, AB2), (n, hb, nb, T)      # same operations, same order per entry
+        assert np.abs(x2 - np.linalg.solve(A, b)).max() < 1e-10
+    # a non-positive pivot stops every thread (participants and bystanders) without a deadlock
+    bad = np.zeros((40, 9))
+    bad[:, 0] = 1.0
+    bad[17, 0] = -1.0
+    xb = np.ones(40)
+    info[:] = 0
+    assert harness.skel_host_band_solve_mt(ctypes.c_longlong(40), 8, 8, _ptr(bad), _ptr(xb), _ptr(info), 128) == 0
+    assert info[0] == 18
+    # skel_eval with 96 real threads per frame
+    skel, flat, x, meas, w = make_problem("K1", dummy_cams, 2, seed=13)
+    N, P = x.shape
+    desc = make_desc(harness, flat, dummy_cams, 1)
+    out = []
+    for mt in (0, 96):
+        cost, g, Hu = np.zeros(N), np.zeros((N, P)), np.zeros((N, P * (P + 1) // 2))
+        args = (_ptr(desc), N, _ptr(x), _ptr(np.ascontiguousarray(meas)), _ptr(np.ascontiguousarray(w)), _ptr(cost), _ptr(g), _ptr(Hu))
+        harness.skel_host_eval_mt(*args, mt) if mt else harness.skel_host_eval(*args)
+        out.append((cost, g, Hu))
+    for a, b2 in zip(out[0], out[1]):
+        assert np.array_equal(a, b2)
