@@ -80,3 +80,33 @@ def test_redescending_loss_name_matches_reference_vectors():
 
     g = golden("loss.npz")
     assert np.abs(build.redescending_loss(g["e"], 3, 10, 20) - g["rho_3_10_20"]).max() < 1e-12
+
+
+def test_reference_module_names_are_importable():
+    """A user of the reference finds the names its scripts call (no GPU needed to import)."""
+    from acinoset_b200 import all_optimizations, app, build, calib, misc, sba, stereo, utils
+
+    for mod, names in [
+        (calib, ["project_points_fisheye", "triangulate_points_fisheye", "get_pairwise_3d_points_from_df", "project_points",
+                 "triangulate_points", "create_undistort_point_function", "bundle_adjust_points_and_extrinsics",
+                 "bundle_adjust_points_only", "bundle_adjust_board_points_and_extrinsics",
+                 "create_bundle_adjustment_jacobian_sparsity_matrix", "prepare_calib_board_data_for_bundle_adjustment",
+                 "cost_func_points_extrinsics", "params_to_points_extrinsics"]),
+        (stereo, ["calibrate_pair_extrinsics_fisheye", "calibrate_pair_extrinsics", "calibrate_pairwise_extrinsics"]),
+        (app, ["calibrate_fisheye_extrinsics_pairwise", "calibrate_standard_extrinsics_pairwise", "sba_board_points_fisheye",
+               "sba_points_fisheye", "save_tri", "save_sba", "save_ekf", "save_fte", "save_optimised_cheetah", "save_3d_cheetah_as_2d"]),
+        (misc, ["get_markers", "get_pose_params", "get_3d_marker_coords", "redescending_loss", "rot_x", "rot_y", "rot_z"]),
+        (all_optimizations, ["fte", "ekf", "sba", "tri", "pt3d_to_2d", "pt3d_to_x2d", "pt3d_to_y2d"]),
+        (build, ["load_skeleton", "build_model", "solve_optimisation", "save_data", "convert_to_dict", "redescending_loss",
+                 "pt3d_to_2d", "np_rot_x"]),
+        (utils, ["load_scene", "save_scene", "load_camera", "save_camera", "load_points", "save_points", "find_scene_file",
+                 "load_dlc_points_as_df", "create_dlc_points_2d_file", "create_board_object_pts"]),
+        (sba, ["sba_board_points_fisheye", "sba_points_fisheye", "jac_points_extrinsics"]),
+    ]:
+        for n in names:
+            assert callable(getattr(mod, n)), (mod.__name__, n)
+    assert len(misc.get_markers()) == 20 and misc.get_markers()[2] == "nose"
+    assert misc.get_pose_params()["psi_0"] == 5
+    import numpy as np
+
+    assert np.allclose(misc.rot_x(0.3) @ misc.rot_x(0.3).T, np.eye(3))
