@@ -67,7 +67,9 @@ def _median_relative_pose(poses):
 def solve_pair(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, max_iter=100, eps=1e-10, backend=None, device=0,
                return_info=False, pinhole=False):
     """-> (rms, R (3,3), T (3,1)) [, info].  img_pts_* (V, M, 2) pixels of the same V views, obj_pts (M, 3).
-    pinhole=True: d_* are OpenCV's standard-model coefficients (up to 12) instead of the 4 fisheye ones."""
+    pinhole=True: d_* are OpenCV's standard-model coefficients (up to 12) instead of the 4 fisheye ones.
+    ``backend`` is a test hook (tests/host_harness runs the kernel source on the host to check it without a GPU); the
+    library itself has no CPU path: with the default backend a missing GPU raises AcinoError."""
     obj = np.ascontiguousarray(obj_pts, dtype=np.float64).reshape(-1, 3)
     M = obj.shape[0]
     img1 = np.ascontiguousarray(img_pts_1, dtype=np.float64).reshape(-1, M, 2)

@@ -47,6 +47,29 @@ def test_no_gpu_fails_loudly(built):
         ab.Handle(0)
 
 
+def test_new_entry_points_have_no_cpu_fallback(built):
+    """The generic-skeleton solve and the pair calibration need the GPU like everything else."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import json
+
+    import acinoset_b200 as ab
+    from acinoset_b200 import build, stereo
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "stereo.npz"))
+    with pytest.raises(ab.AcinoError):
+        stereo.calibrate_pair_extrinsics_fisheye(g["rot12_obj"], g["rot12_img1"], g["rot12_img2"], g["rot12_K1"], g["rot12_D1"],
+                                                 g["rot12_K2"], g["rot12_D2"], (1920, 1080))
+    gk = np.load(os.path.join(ROOT, "tests", "golden", "generic_fk.npz"))
+    skel = json.loads(str(gk["K1_skeleton_json"]))
+    K = np.tile(np.eye(3), (2, 1, 1))
+    model = build.model_from_arrays(skel, (K, np.zeros((2, 4)), K.copy(), np.zeros((2, 3))), np.zeros((4, 2, 15, 2)), np.ones((4, 2, 15)))
+    with pytest.raises(ab.AcinoError):
+        build.solve_optimisation(model)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "acinoset_b200")
     for dirpath, _, files in os.walk(pkg):
