@@ -47,6 +47,8 @@ def _load():
     lib.acino_fte_eval_dev.restype = ci
     lib.acino_fte_eval.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
     lib.acino_fte_eval.restype = ci
+    lib.acino_fte_eval_kernel_name.argtypes = [ci]
+    lib.acino_fte_eval_kernel_name.restype = ctypes.c_char_p
     lib.acino_fk_project_dev.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.acino_fk_project_dev.restype = ci
     lib.acino_fk_project.argtypes = [vp, ci, vp, vp, vp]
@@ -135,7 +137,7 @@ lib = _load()
 # every symbol include/acino_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED = [
     "acino_create", "acino_destroy", "acino_last_error", "acino_version", "acino_launch_count",
-    "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval",
+    "acino_set_cameras", "acino_set_redescending", "acino_fte_eval_dev", "acino_fte_eval", "acino_fte_eval_kernel_name",
     "acino_fk_project_dev", "acino_fk_project", "acino_fte_jac_dev", "acino_fte_jac", "acino_project_points", "acino_undistort_points",
     "acino_triangulate_points", "acino_triangulate_pairwise", "acino_generic_fk",
     "acino_project_points_pinhole", "acino_undistort_points_pinhole", "acino_triangulate_points_pinhole",
@@ -189,6 +191,10 @@ class Handle:
     @property
     def launch_count(self):
         return int(lib.acino_launch_count(self._h))
+
+    @staticmethod
+    def fte_kernel_name(n_frames=1 << 20):
+        return lib.acino_fte_eval_kernel_name(int(n_frames)).decode()
 
     # ---- scene
     def set_cameras(self, K, D, R, t):

@@ -13,6 +13,7 @@
 namespace acino {
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
                             const float* w, float* cost, float* g, float* H, cudaStream_t stream);
+const char* fte_eval_kernel_name(int n_frames);
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream);
 cudaError_t launch_fte_jac(const SceneF& scene, int n_frames, const float* x, float* uv, float* J, cudaStream_t stream);
@@ -270,6 +271,8 @@ int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const floa
     h->launches += 1;
     return ACINO_OK;
 }
+
+const char* acino_fte_eval_kernel_name(int n_frames) { return fte_eval_kernel_name(n_frames); }
 
 static int ensure_pipe(acino_handle* h) {
     if (h->pipe_ready) return ACINO_OK;

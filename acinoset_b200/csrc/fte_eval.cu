@@ -739,6 +739,8 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
     return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
 }
 
+const char* fte_eval_kernel_name(int) { return "fte_eval_kernel<8, 1, 4, 0, 0>"; }
+
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;

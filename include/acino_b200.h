@@ -74,6 +74,9 @@ int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const floa
                        const float* w, float* cost, float* g, float* H, void* cuda_stream);
 int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* meas,
                    const float* w, float* cost, float* g, float* H);
+/* Name (as ncu / the launch list shows it) of the kernel acino_fte_eval[_dev] launches for a batch of
+ * n_frames frames: bench.py's roofline.kernel. */
+const char* acino_fte_eval_kernel_name(int n_frames);
 
 /* Reprojection only: pose_to_3d (all_optimizations.py:186) + project_points_fisheye for every
  * camera (calib.py:132-136; save_3d_cheetah_as_2d at all_optimizations.py:560).
