@@ -145,6 +145,7 @@ EXPORTED = [
     "acino_band_solve_dev", "acino_skel_trial_dev", "acino_skel_pred_dev",
     "acino_stereo_set", "acino_stereo_set_pinhole", "acino_stereo_init", "acino_stereo_step",
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
+    "acino_lm_desc_size", "acino_lm_plan_create", "acino_lm_plan_destroy", "acino_lm_enqueue",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
     "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_eval_dev",
     "acino_sba_schur_dev", "acino_sba_dense_solve_dev", "acino_sba_backsub_dev", "acino_sba_pred_dev",

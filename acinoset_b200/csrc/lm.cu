@@ -8,26 +8,9 @@
 // B + lam diag(B), couplings, right-hand side), lm_step (projected trial point, model reduction),
 // lm_reduce (fixed-order fp64 sums).  Frame indices are GLOBAL (frame0 + local) so that a rank
 // holding a contiguous shard with 3-frame halos builds exactly its rows of the global system.
-#include "acino_common.cuh"
+#include "lm_common.cuh"
 
 namespace acino {
-
-constexpr int SBF = 3;            // frames per super-block
-constexpr int SBN = SBF * NA;     // 75
-
-// coefficient of D3^T D3 between global frames a and a+k (0 <= k <= 3), D3 rows m = 3..ng-1 with
-// stencil (-1, 3, -3, 1) on columns m-3..m
-__device__ __forceinline__ double band_coef(long long a, int k, long long ng) {
-    const double st[4] = {-1.0, 3.0, -3.0, 1.0};
-    if (a < 0 || a + k >= ng) return 0.0;
-    long long m0 = a + k;
-    if (m0 < 3) m0 = 3;
-    long long m1 = a + 3;
-    if (m1 > ng - 1) m1 = ng - 1;
-    double s = 0.0;
-    for (long long m = m0; m <= m1; ++m) s += st[a - m + 3] * st[a + k - m + 3];
-    return s;
-}
 
 // thread per (frame, parameter).  x_ext has 3 halo frames on each side: row (n + 3) is local frame n.
 __global__ void lm_prepare_kernel(const int n_frames, const long long frame0, const long long ng,

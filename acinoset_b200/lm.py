@@ -6,16 +6,27 @@ Replaces the reference's `opt.solve(m)` (Pyomo -> IPOPT subprocess,
     F(x) = sum_{n,c,l,d} rho(w (proj - meas))  +  sum_{n>=3,p} (1/Q_p) (third difference / Ts^2)^2
 
 (measurement term :394-399,494-497; dynamics :369-391; weights :245-252,310-315) under the 21 pose
-bounds (:403-483).  Per attempt: lm_assemble -> block cyclic reduction (csrc/bcr.cu) -> lm_step ->
-fte_eval at the trial point -> lm_prepare -> lm_reduce; the host only reads 5 scalars back.
+bounds (:403-483).
+
+One attempt = the phases of csrc/lm_plan.cu, all enqueued on one stream with no host decision in
+between: REDUCE (structured level 0 fused with the assembly, csrc/lm_l0.cu, then the dense block
+cyclic reduction levels, csrc/bcr.cu) -> BACKSUB -> TRIAL (projected step, fte_eval at the trial
+point, gradient / frozen set, fixed-order sums) -> DECIDE (gain ratio, lambda update, commit,
+convergence test - on the device).  After one eager attempt the sequence is captured into a CUDA
+graph and replayed; the host stays one attempt ahead of the GPU and only looks at the pinned mirror
+of the device control block to learn that the solve has finished.
 
 Multi-GPU: frames are sharded in contiguous blocks (multiples of 3 frames); every rank reduces its
-shard onto its two end super-blocks (pinned BCR), ONE all_gather moves the interface blocks
-(2 x (75x75 + 75x75 + 75) doubles per rank), every rank solves the 2G-block interface chain
-redundantly (bit-identical, no broadcast needed) and back-substitutes locally.  The interface
-solution of the neighbouring rank is exactly the step of the halo frames, so no separate halo
-exchange is needed.  A second, 5-scalar all_reduce carries the objective / model-reduction sums.
+shard onto its two end super-blocks (pinned BCR), one all_gather moves the interface blocks
+(22 800 doubles per rank), every rank solves the 2G-block interface chain redundantly
+(bit-identical, no broadcast needed) and back-substitutes locally; the interface solution of the
+neighbouring rank is exactly the step of the halo frames.  A second all_gather of 8 doubles per
+rank carries the objective / model-reduction partials of the trial point: the accept / reject
+decision of attempt k needs the evaluation that FOLLOWS the interface exchange of attempt k, and
+the assembly of attempt k+1 needs that decision, so two exchange points per attempt are inherent
+(both are captured in the graph; every rank sums the partials in rank order => identical bits).
 """
+import ctypes
 import numpy as np
 
 from . import bcr as _bcr
@@ -148,11 +159,73 @@ class ChainSolver:
         self.backsub(D, rhs, x)
 
 
+
+
+# ---- device control block (csrc/lm_common.cuh enum LmCtl) and phases (include/acino_b200.h) ------
+(CTL_LAM, CTL_F, CTL_FT, CTL_PRED, CTL_STEP, CTL_RHO, CTL_REL, CTL_ACCEPT, CTL_DONE, CTL_N_ATTEMPT, CTL_N_ACCEPT,
+ CTL_FAIL_STREAK, CTL_STATUS, CTL_MAX_ITER, CTL_MAX_ATTEMPTS, CTL_TOL_STEP, CTL_TOL_REL, CTL_ITERS, CTL_HIST_CAP,
+ CTL_TOL_NOISE, CTL_NOISE_STREAK, CTL_N_ENQ, CTL_DONE_AT) = range(23)
+CTL_SIZE, N_SUMS, N_HIST = 32, 8, 8
+PH_INIT_EVAL, PH_INIT_FINISH, PH_REDUCE, PH_BACKSUB, PH_TRIAL, PH_DECIDE = range(6)
+STATUS = {0: "running", 1: "converged", 2: "no acceptable step", 3: "iteration limit"}
+
+
+def level0_split(M, pinned):
+    """(elim0, surv0, dense levels): the first elimination level is done by the structured kernels of
+    csrc/lm_l0.cu, which also ASSEMBLE every block that survives it - so surv0 lists every block that is not
+    eliminated at level 0 with its eliminated neighbours (or -1), not only the ones that receive an update."""
+    levels, left = _bcr.make_schedule(M, pin_first=pinned, pin_last=pinned)
+    elim0 = levels[0]["elim"] if levels else np.zeros((0, 3), np.int32)
+    gone = set(int(e) for e in elim0[:, 0])
+    surv0 = np.array([(j, j - 1 if (j - 1) in gone else -1, j + 1 if (j + 1) in gone else -1)
+                      for j in range(M) if j not in gone], dtype=np.int32).reshape(-1, 3)
+    return elim0, surv0, levels[1:], left
+
+
+def flatten_levels(levels):
+    """-> (counts (L,2) int32 host array, sched (sum(ne+ns),3) int32: per level the elim rows, then the surv rows)."""
+    counts = np.array([(lv["elim"].shape[0], lv["surv"].shape[0]) for lv in levels], dtype=np.int32).reshape(-1, 2)
+    rows = [r for lv in levels for r in (lv["elim"], lv["surv"])]
+    sched = np.concatenate(rows).astype(np.int32) if rows else np.zeros((0, 3), np.int32)
+    return np.ascontiguousarray(counts), np.ascontiguousarray(sched.reshape(-1, 3))
+
+
+_vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+
+
+class LmDesc(ctypes.Structure):
+    """acino_lm_desc (include/acino_b200.h)."""
+    _fields_ = ([("n_frames", _i32), ("n_blocks", _i32), ("rank", _i32), ("world", _i32), ("frame0", _i64), ("n_global", _i64)]
+                + [(k, _vp) for k in ("meas", "w", "sw", "lo", "hi")]
+                + [(k, _vp * 2) for k in ("x_ext", "x32", "cost", "g", "H", "gtot", "fixed", "cost_s")]
+                + [(k, _vp) for k in ("pred", "step", "D", "Lc", "P", "Q", "rhs", "dx", "dhalo", "info")]
+                + [("n_elim0", _i32), ("n_surv0", _i32), ("elim0", _vp), ("surv0", _vp),
+                   ("n_levels", _i32), ("level_counts", _vp), ("sched", _vp)]
+                + [(k, _vp) for k in ("payload", "gathered", "cD", "cLc", "cP", "cQ", "crhs", "cx")]
+                + [("n_clevels", _i32), ("clevel_counts", _vp), ("csched", _vp)]
+                + [(k, _vp) for k in ("sums_local", "sums_all", "ctl", "ctl_host", "hist")]
+                + [("hist_cap", _i32)])
+
+
+_lib.lib.acino_lm_desc_size.argtypes = []
+_lib.lib.acino_lm_desc_size.restype = ctypes.c_int
+if _lib.lib.acino_lm_desc_size() != ctypes.sizeof(LmDesc):
+    raise ImportError("acino_lm_desc layout mismatch between include/acino_b200.h and acinoset_b200/lm.py")
+_lib.lib.acino_lm_plan_create.argtypes = [ctypes.c_void_p, ctypes.POINTER(LmDesc), ctypes.POINTER(ctypes.c_void_p)]
+_lib.lib.acino_lm_plan_create.restype = ctypes.c_int
+_lib.lib.acino_lm_plan_destroy.argtypes = [ctypes.c_void_p]
+_lib.lib.acino_lm_plan_destroy.restype = ctypes.c_int
+_lib.lib.acino_lm_enqueue.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+_lib.lib.acino_lm_enqueue.restype = ctypes.c_int
+
+
 class FTESolver:
     """LM solver for one shard of frames on one GPU (world = 1: the whole problem)."""
 
+    HIST_CAP = 4096
+
     def __init__(self, handle, meas, w, Ts, frame0=0, n_global=None, q=None, bounds=None, rank=0, world=1,
-                 group=None):
+                 group=None, use_graph=True):
         import torch
 
         self.h = handle
@@ -161,13 +234,16 @@ class FTESolver:
         self.N = int(meas.shape[0])
         self.frame0 = int(frame0)
         self.ng = int(n_global if n_global is not None else self.N)
-        self.rank, self.world, self.group = rank, world, group
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.use_graph = bool(use_graph)
         if world > 1 and (self.N % 3 != 0 and rank < world - 1):
             raise ValueError("shards must be multiples of 3 frames (use shard_frames)")
         if world > 1 and self.N < 6:
             raise ValueError("need at least 6 frames per rank")
+        if self.N < 1:
+            raise ValueError("need at least one frame")
         self.M = -(-self.N // 3)
-        f64, f32 = torch.float64, torch.float32
+        f64, f32, i32 = torch.float64, torch.float32, torch.int32
         dev = self.dev
         self.meas = torch.as_tensor(np.ascontiguousarray(meas, dtype=np.float32)).to(dev)
         self.w = torch.as_tensor(np.ascontiguousarray(w, dtype=np.float32)).to(dev)
@@ -181,20 +257,74 @@ class FTESolver:
         def buf(*shape, dtype=f64):
             return torch.zeros(*shape, dtype=dtype, device=dev)
 
-        # two states (accepted / trial), swapped on acceptance
+        # two states: [0] accepted, [1] trial (DECIDE copies trial -> accepted on the device when a step is accepted)
         self.st = [dict(x_ext=buf(N + 6, NA), x32=buf(N, NA, dtype=f32), cost=buf(N, dtype=f32),
                         g=buf(N, NA, dtype=f32), H=buf(N, _lib.N_UPPER, dtype=f32), gtot=buf(N, NA),
                         fixed=buf(N, NA, dtype=torch.uint8), cost_s=buf(N)) for _ in range(2)]
-        self.d_ext = buf(N + 6, NA)
         self.pred, self.step = buf(N), buf(N)
-        self.D, self.Lc = buf(M, SB, SB), buf(M, SB, SB)
+        self.D, self.Lc, self.P, self.Q = (buf(M, SB, SB) for _ in range(4))
         self.rhs, self.dx = buf(M, SB), buf(M, SB)
-        self.out5 = buf(5)
-        self.local = ChainSolver(handle, M, pinned=world > 1)
-        self.iface = ChainSolver(handle, 2 * world, pinned=False) if world > 1 else None
+        self.dhalo = buf(2, SB)
+        self.info = torch.zeros(1, dtype=i32, device=dev)
+        self.sums_local = buf(N_SUMS)
+        self.sums_all = buf(world, N_SUMS) if world > 1 else self.sums_local
+        self.ctl = buf(CTL_SIZE)
+        self.ctl_host = torch.zeros(CTL_SIZE, dtype=f64).pin_memory()
+        self.hist = buf(self.HIST_CAP, N_HIST)
+        # schedules
+        elim0, surv0, levels, _ = level0_split(M, pinned=world > 1)
+        self._counts, sched = flatten_levels(levels)
+        self.elim0 = torch.from_numpy(np.ascontiguousarray(elim0)).to(dev)
+        self.surv0 = torch.from_numpy(np.ascontiguousarray(surv0)).to(dev)
+        self.sched = torch.from_numpy(sched).to(dev)
         self.n_launch0 = handle.launch_count
+        d = LmDesc()
+        d.n_frames, d.n_blocks, d.rank, d.world, d.frame0, d.n_global = N, M, self.rank, self.world, self.frame0, self.ng
+        for k, t in (("meas", self.meas), ("w", self.w), ("sw", self.sw), ("lo", self.lo), ("hi", self.hi),
+                     ("pred", self.pred), ("step", self.step), ("D", self.D), ("Lc", self.Lc), ("P", self.P), ("Q", self.Q),
+                     ("rhs", self.rhs), ("dx", self.dx), ("dhalo", self.dhalo), ("info", self.info),
+                     ("elim0", self.elim0), ("surv0", self.surv0), ("sched", self.sched),
+                     ("sums_local", self.sums_local), ("sums_all", self.sums_all), ("ctl", self.ctl),
+                     ("ctl_host", self.ctl_host), ("hist", self.hist)):
+            setattr(d, k, t.data_ptr())
+        for k in ("x_ext", "x32", "cost", "g", "H", "gtot", "fixed", "cost_s"):
+            setattr(d, k, (ctypes.c_void_p * 2)(self.st[0][k].data_ptr(), self.st[1][k].data_ptr()))
+        d.n_elim0, d.n_surv0, d.n_levels = int(elim0.shape[0]), int(surv0.shape[0]), int(self._counts.shape[0])
+        d.level_counts = self._counts.ctypes.data
+        d.hist_cap = self.HIST_CAP
+        if world > 1:
+            self.payload = buf(PAYLOAD)
+            self.gathered = buf(world, PAYLOAD)
+            G2 = 2 * world
+            self.cD, self.cLc, self.cP, self.cQ = (buf(G2, SB, SB) for _ in range(4))
+            self.crhs, self.cx = buf(G2, SB), buf(G2, SB)
+            clevels, _ = _bcr.make_schedule(G2)
+            self._ccounts, csched = flatten_levels(clevels)
+            self.csched = torch.from_numpy(csched).to(dev)
+            for k in ("payload", "gathered", "cD", "cLc", "cP", "cQ", "crhs", "cx", "csched"):
+                setattr(d, k, getattr(self, k).data_ptr())
+            d.n_clevels = int(self._ccounts.shape[0])
+            d.clevel_counts = self._ccounts.ctypes.data
+        self._plan = ctypes.c_void_p()
+        handle._check(_lib.lib.acino_lm_plan_create(handle._h, ctypes.byref(d), ctypes.byref(self._plan)),
+                      "acino_lm_plan_create")
+        self._graph = None
 
-    # -- pieces ---------------------------------------------------------------------------------
+    def close(self):
+        """Release the captured CUDA graph and the plan.  With world > 1 the graph holds NCCL work: close every solver
+        BEFORE torch.distributed.destroy_process_group() (destroying a communicator that a live graph references blocks)."""
+        self._graph = None
+        if getattr(self, "_plan", None) is not None and self._plan.value:
+            _lib.lib.acino_lm_plan_destroy(self._plan)
+            self._plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- pieces (also used by the tests) ------------------------------------------------------------
     def _eval(self, s):
         self.h.fte_eval_dev(s["x32"], self.meas, self.w, s["cost"], s["g"], s["H"])
 
@@ -202,57 +332,37 @@ class FTESolver:
         self.h.call_dev("acino_lm_prepare_dev", self.N, self.frame0, self.ng, s["x_ext"], s["g"], self.sw, self.lo,
                         self.hi, s["gtot"], s["fixed"], s["cost_s"])
 
-    def _sums(self, s, with_step):
-        """Global (F, pred, step_inf): fixed-order local sums + one 5-scalar all_reduce."""
-        torch = self.torch
-        self.h.call_dev("acino_lm_reduce_dev", self.N, s["cost"], s["cost_s"], self.pred if with_step else None, None,
-                        self.step if with_step else None, self.out5)
+    def _enq(self, phase):
+        st = self.torch.cuda.current_stream(self.dev).cuda_stream
+        self.h._check(_lib.lib.acino_lm_enqueue(self.h._h, self._plan, int(phase), ctypes.c_void_p(st)), "acino_lm_enqueue")
+
+    def _gather(self, out, inp):
         if self.world > 1:
             import torch.distributed as dist
 
-            dist.all_reduce(self.out5[:4], op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(self.out5[4:], op=dist.ReduceOp.MAX, group=self.group)
-        o = self.out5.cpu().numpy()
-        return float(o[0] + o[1]), float(o[2]), float(o[4])
+            dist.all_gather_into_tensor(out.view(-1), inp.view(-1), group=self.group)
 
-    def _solve_step(self, s, lam):
-        """(B + lam diag B) dx = -g on the accepted state -> self.d_ext (with halos)."""
-        torch = self.torch
-        N, M = self.N, self.M
-        self.h.call_dev("acino_lm_assemble_dev", N, self.frame0, self.ng, M, s["H"], s["gtot"], s["fixed"], self.sw,
-                        float(lam), self.D, self.Lc, self.rhs)
-        self.d_ext.zero_()
-        if self.world == 1:
-            self.local.solve(self.D, self.Lc, self.rhs, self.dx)
-        else:
-            self.local.reduce(self.D, self.Lc, self.rhs)
-            fixed_blocks = torch.zeros(M * 3, NA, dtype=torch.uint8, device=self.dev)
-            fixed_blocks[:N] = s["fixed"]
-            payload = pack_interface(self.D, self.Lc, self.rhs, fixed_blocks.view(M, SB))
-            Dc, Lcc, rc = gather_interface_chain(payload, self.world, self.group)
-            xc = torch.zeros(2 * self.world, SB, dtype=torch.float64, device=self.dev)
-            self.iface.solve(Dc, Lcc, rc, xc)
-            xf, xl, hl, hr = split_interface_solution(xc, self.rank, self.world)
-            self.dx[0], self.dx[M - 1] = xf, xl
-            self.local.backsub(self.D, self.rhs, self.dx)
-            if hl is not None:
-                self.d_ext[0:3] = hl.view(3, NA)
-            if hr is not None:
-                self.d_ext[N + 3:N + 6] = hr.view(3, NA)
-        self.d_ext[3:3 + N] = self.dx.view(-1, NA)[:N]
+    def _attempt(self):
+        """Enqueue one LM attempt (no host decision anywhere in it)."""
+        self._enq(PH_REDUCE)
+        if self.world > 1:
+            self._gather(self.gathered, self.payload)
+        self._enq(PH_BACKSUB)
+        self._enq(PH_TRIAL)
+        if self.world > 1:
+            self._gather(self.sums_all, self.sums_local)
+        self._enq(PH_DECIDE)
 
-    def _trial(self, s, t):
-        torch = self.torch
-        N = self.N
-        self.h.call_dev("acino_lm_step_dev", N, self.frame0, self.ng, s["x_ext"], self.d_ext, s["gtot"], s["H"], self.sw,
-                        self.lo, self.hi, t["x_ext"], t["x32"], self.pred, self.step)
-        # halo rows of the trial state: the neighbour applies the same clamp to the same numbers
-        t["x_ext"][0:3] = torch.minimum(torch.maximum(s["x_ext"][0:3] + self.d_ext[0:3], self.lo), self.hi)
-        t["x_ext"][N + 3:] = torch.minimum(torch.maximum(s["x_ext"][N + 3:] + self.d_ext[N + 3:], self.lo), self.hi)
-        self._eval(t)
-        self._prepare(t)
+    def linear_solve(self, lam):
+        """(test hook) REDUCE + BACKSUB on the accepted state with the given lambda -> dx (M,75), dhalo (2,75)."""
+        self.ctl[CTL_LAM] = float(lam)
+        self._enq(PH_REDUCE)
+        if self.world > 1:
+            self._gather(self.gathered, self.payload)
+        self._enq(PH_BACKSUB)
+        return self.dx, self.dhalo
 
-    def _exchange_halo_init(self, s, x0):
+    def _exchange_halo_init(self, s):
         """One-time halo fill of the initial iterate (all_gather of the 3 first / last frames)."""
         torch = self.torch
         if self.world == 1:
@@ -269,54 +379,109 @@ class FTESolver:
         if self.rank < self.world - 1:
             s["x_ext"][N + 3:N + 6] = allb[self.rank + 1, 0]
 
+    def exchange_us(self, reps=50):
+        """Device time of the two per-attempt exchanges (CUDA events around all_gather x 2), microseconds."""
+        torch = self.torch
+        if self.world == 1:
+            return 0.0
+        for _ in range(5):
+            self._gather(self.gathered, self.payload)
+            self._gather(self.sums_all, self.sums_local)
+        torch.cuda.synchronize(self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            self._gather(self.gathered, self.payload)
+            self._gather(self.sums_all, self.sums_local)
+        e1.record()
+        torch.cuda.synchronize(self.dev)
+        return 1e3 * e0.elapsed_time(e1) / reps
+
     # -- the loop -------------------------------------------------------------------------------
-    def solve(self, x0, max_iter=60, lam0=1e-3, tol_step=1e-6, tol_rel=1e-8, max_attempts=12, verbose=False):
+    def solve(self, x0, max_iter=60, lam0=1e-3, tol_step=1e-6, tol_rel=1e-7, max_attempts=12, verbose=False,
+              tol_noise=5e-8):
+        """Stops when an accepted step moves no variable by more than tol_step, or lowers F by less than tol_rel * F,
+        or when two consecutive REJECTED trial points differ from F by less than tol_noise * F (the measurement term
+        is evaluated in fp32: ~6e-8 relative resolution per frame), or after max_attempts rejections in a row, or
+        after max_iter accepted iterations.  (The reference stops IPOPT at tol = 1e-1, all_optimizations.py:511.)"""
         torch = self.torch
         N = self.N
-        s, t = self.st
+        s = self.st[0]
         x0 = np.clip(np.asarray(x0, dtype=np.float64), self.lo.cpu().numpy(), self.hi.cpu().numpy())
         s["x_ext"].zero_()
         s["x_ext"][3:3 + N] = torch.as_tensor(x0).to(self.dev)
         s["x32"].copy_(s["x_ext"][3:3 + N].to(torch.float32))
-        self._exchange_halo_init(s, x0)
-        self._eval(s)
-        self._prepare(s)
-        F, _, _ = self._sums(s, with_step=False)
-        lam = lam0
-        hist = [F]
-        n_eval, n_solve, it = 1, 0, 0
-        converged = False
-        for it in range(max_iter):
-            accepted = False
-            for _ in range(max_attempts):
-                self._solve_step(s, lam)
-                n_solve += 1
-                self._trial(s, t)
-                n_eval += 1
-                Ft, pred, step = self._sums(t, with_step=True)
-                rho = (F - Ft) / pred if pred > 0 else -1.0
-                if verbose and self.rank == 0:
-                    print(f"it {it:3d} lam {lam:9.3e} F {F:16.6f} Ft {Ft:16.6f} pred {pred:10.3e} rho {rho:7.3f} |dx|inf {step:.2e}")
-                if Ft < F and rho > 1e-4:
-                    accepted = True
-                    rel = (F - Ft) / max(abs(F), 1e-30)
-                    F = Ft
-                    s, t = t, s
-                    if rho > 0.75:
-                        lam = max(lam / 3, 1e-12)
-                    elif rho < 0.25:
-                        lam *= 2
-                    break
-                lam *= 4
-            hist.append(F)
-            if not accepted:
-                break
-            if step < tol_step or rel < tol_rel:
-                converged = True
-                break
-        self.st = [s, t]
+        self._exchange_halo_init(s)
+        ctl0 = np.zeros(CTL_SIZE)
+        ctl0[CTL_LAM], ctl0[CTL_MAX_ITER], ctl0[CTL_MAX_ATTEMPTS] = lam0, max_iter, max_attempts
+        ctl0[CTL_TOL_STEP], ctl0[CTL_TOL_REL], ctl0[CTL_HIST_CAP] = tol_step, tol_rel, self.HIST_CAP
+        ctl0[CTL_TOL_NOISE], ctl0[CTL_DONE_AT] = tol_noise, -1.0
+        if max_iter <= 0:
+            ctl0[CTL_DONE], ctl0[CTL_STATUS] = 1, 3
+        self.ctl.copy_(torch.from_numpy(ctl0))
+        self.info.zero_()
+        self._enq(PH_INIT_EVAL)
+        if self.world > 1:
+            self._gather(self.sums_all, self.sums_local)
+        self._enq(PH_INIT_FINISH)
         torch.cuda.synchronize(self.dev)
+        F0 = float(self.ctl_host[CTL_F])
+        launches0 = self.h.launch_count
+        cap = max_iter * max_attempts + 2
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def enqueue(k):
+            if self._graph is not None and k > 0:
+                self._graph.replay()
+                return
+            self._attempt()                           # eager: the first attempt of every solve (= warm-up of the capture)
+            if self.use_graph and self._graph is None and k == 0:
+                torch.cuda.synchronize(self.dev)
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._attempt()
+                    self._graph = g
+                except Exception as e:                # capture is an optimisation, never a different code path
+                    self._graph = None
+                    self.use_graph = False
+                    self._graph_error = repr(e)
+                    torch.cuda.synchronize(self.dev)
+
+        # The host stays ONE attempt ahead of the GPU: it enqueues attempt k, then waits for attempt k-1 only and looks
+        # at the pinned mirror of the control block.  `done` is raised by the device at the same attempt index j on every
+        # rank; every rank then makes sure it has enqueued exactly j + 2 attempts (an attempt contains collectives, so the
+        # counts must match whatever each host happened to observe) - the surplus attempts are idle on the device.
+        k = 0
+        while k < cap and max_iter > 0:
+            enqueue(k)
+            evs[k & 1].record()
+            k += 1
+            if k >= 2:
+                evs[k & 1].synchronize()              # attempt k-2 has finished
+                done_at = int(self.ctl_host[CTL_DONE_AT])
+                if done_at >= 0:
+                    while k < done_at + 2:
+                        enqueue(k)
+                        k += 1
+                    break
+        torch.cuda.synchronize(self.dev)
+        ctl = self.ctl.cpu().numpy()
+        n_att = int(ctl[CTL_N_ATTEMPT])
+        hist = self.hist[:min(n_att, self.HIST_CAP)].cpu().numpy()
+        if verbose and self.rank == 0:
+            it = 0
+            for r in hist:
+                print(f"it {it:3d} lam {r[2]:9.3e} F {r[0]:16.6f} Ft {r[1]:16.6f} pred {r[6]:10.3e} rho {r[3]:7.3f} "
+                      f"|dx|inf {r[4]:.2e}{' *' if r[5] else ''}")
+                it += int(r[5])
         x = s["x_ext"][3:3 + N].cpu().numpy()
-        info = dict(F=F, iters=it + 1, n_eval=n_eval, n_solve=n_solve, history=hist, lam=lam, converged=converged,
-                    bcr_info=int(self.local.info.item()), launches=self.h.launch_count - self.n_launch0)
+        history = [F0] + [float(r[1]) for r in hist if r[5]]
+        status = int(ctl[CTL_STATUS])
+        info = dict(F=float(ctl[CTL_F]), iters=int(ctl[CTL_ITERS]), n_eval=n_att + 1, n_solve=n_att, history=history,
+                    lam=float(ctl[CTL_LAM]), converged=status == 1, status=STATUS.get(status, str(status)),
+                    bcr_info=int(self.info.item()), launches=self.h.launch_count - self.n_launch0,
+                    graph=self._graph is not None, attempts_enqueued=k,
+                    collectives_per_attempt=0 if self.world == 1 else 2, host_syncs_per_attempt=0,
+                    step=float(ctl[CTL_STEP]))
         return x, info

@@ -253,6 +253,82 @@ int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, cons
                           const double* P, const double* Q, const double* rhs, double* x,
                           void* cuda_stream);
 
+/* ---- FTE solve: the whole Levenberg-Marquardt attempt as stream-ordered phases --------------------
+ * Replaces `results = opt.solve(m, tee=True)` (all_optimizations.py:503-524) without a host in the loop:
+ * lambda, the objective, the accept / reject decision and the convergence test live in a device-resident
+ * control block; a caller enqueues the phases of one attempt (or replays a CUDA graph of them) and reads
+ * the pinned mirror of the control block when it wants to know whether the solve has finished.
+ * Multi-GPU (frames sharded over ranks): the caller performs the two exchanges between the phases -
+ * all_gather(payload -> gathered) after REDUCE and all_gather(sums_local -> sums_all) after TRIAL; with
+ * world == 1 pass gathered = payload and sums_all = sums_local (no exchange).
+ * All pointers are DEVICE pointers unless stated; the caller owns every buffer for the plan's lifetime. */
+#define ACINO_LM_PAYLOAD   22800   /* doubles: D_first, D_last, Lc_first, Lc_last (75x75 each), rhs_first, rhs_last,
+                                      frozen_first, frozen_last (75 each) */
+#define ACINO_LM_SUMS      8       /* doubles per rank: sum cost, sum smoothness cost, sum model reduction, -, max |step|, - */
+#define ACINO_LM_CTL       32      /* doubles: see acinoset_b200/lm.py CTL_* (lambda, F, ..., done, status) */
+#define ACINO_LM_HIST      8       /* doubles per logged attempt: F, F_trial, lambda, rho, |step|inf, accepted, pred, - */
+typedef struct acino_lm_desc {
+    int32_t n_frames;              /* N: frames of this rank's shard */
+    int32_t n_blocks;              /* M = ceil(N / 3) super-blocks of 3 frames x 25 parameters */
+    int32_t rank, world;
+    int64_t frame0, n_global;      /* first global frame of the shard, global frame count */
+    const float* meas;             /* [N][C][20][2] */
+    const float* w;                /* [N][C][20] */
+    const double* sw;              /* [25] 2 q_p / Ts^4 (all_optimizations.py:245-252, 369-391) */
+    const double* lo;              /* [25] pose bounds (:403-483), +-inf where free */
+    const double* hi;
+    double* x_ext[2];              /* [N + 6][25] accepted / trial state, 3 halo frames per side */
+    float* x32[2];                 /* [N][25] fp32 copy the evaluation consumes */
+    float* cost[2];                /* [N]      outputs of fte_eval */
+    float* g[2];                   /* [N][25] */
+    float* H[2];                   /* [N][325] */
+    double* gtot[2];               /* [N][25] total gradient (measurement + smoothness) */
+    uint8_t* fixed[2];             /* [N][25] frozen (bound-active) variables */
+    double* cost_s[2];             /* [N] smoothness cost per frame */
+    double* pred;                  /* [N] model reduction per frame */
+    double* step;                  /* [N] max |step| per frame */
+    double* D;                     /* [M][75][75] */
+    double* Lc;                    /* [M][75][75] */
+    double* P;                     /* [M][75][75] */
+    double* Q;                     /* [M][75][75] */
+    double* rhs;                   /* [M][75] */
+    double* dx;                    /* [M][75] the step */
+    double* dhalo;                 /* [2][75] step of the neighbouring ranks' interface blocks (0 at the global ends) */
+    int32_t* info;                 /* [1] != 0: non-positive pivot (block index + 1) */
+    int32_t n_elim0, n_surv0;      /* structured level 0 (csrc/lm_l0.cu): eliminated / surviving blocks */
+    const int32_t* elim0;          /* [n_elim0][3] (block, left, right) */
+    const int32_t* surv0;          /* [n_surv0][3] (block, eliminated left or -1, eliminated right or -1) */
+    int32_t n_levels;              /* dense levels below (csrc/bcr.cu) */
+    const int32_t* level_counts;   /* HOST [n_levels][2] (n_elim, n_surv) */
+    const int32_t* sched;          /* per level: n_elim elim rows then n_surv surv rows, [.][3] each */
+    double* payload;               /* [ACINO_LM_PAYLOAD] this rank's reduced end blocks (world > 1) */
+    const double* gathered;        /* [world][ACINO_LM_PAYLOAD] */
+    double* cD; double* cLc; double* cP; double* cQ;      /* interface chain [2 world][75][75] */
+    double* crhs; double* cx;      /* [2 world][75] */
+    int32_t n_clevels;
+    const int32_t* clevel_counts;  /* HOST */
+    const int32_t* csched;
+    double* sums_local;            /* [ACINO_LM_SUMS] */
+    const double* sums_all;        /* [world][ACINO_LM_SUMS] */
+    double* ctl;                   /* [ACINO_LM_CTL] */
+    double* ctl_host;              /* HOST, pinned: mirror written at the end of INIT_FINISH and DECIDE */
+    double* hist;                  /* [hist_cap][ACINO_LM_HIST] */
+    int32_t hist_cap;
+} acino_lm_desc;
+typedef struct acino_lm_plan acino_lm_plan;
+enum {
+    ACINO_LM_INIT_EVAL = 0,        /* evaluate the accepted state: fte_eval, gradient / frozen set, local sums */
+    ACINO_LM_INIT_FINISH = 1,      /* F <- sum over ranks */
+    ACINO_LM_REDUCE = 2,           /* assemble (B + lam diag B), eliminate down to the end blocks (world > 1: payload) */
+    ACINO_LM_BACKSUB = 3,          /* world > 1: interface chain from `gathered`; back-substitution -> dx, dhalo */
+    ACINO_LM_TRIAL = 4,            /* projected trial point, fte_eval there, gradient / frozen set, local sums */
+    ACINO_LM_DECIDE = 5            /* gain ratio, lambda update, commit trial -> accepted, convergence test */
+};
+int acino_lm_desc_size(void);      /* sizeof(acino_lm_desc): lets a foreign-language binding check its struct layout */
+int acino_lm_plan_create(acino_handle* h, const acino_lm_desc* desc, acino_lm_plan** out);
+int acino_lm_plan_destroy(acino_lm_plan* plan);
+int acino_lm_enqueue(acino_handle* h, acino_lm_plan* plan, int phase, void* cuda_stream);
+
 /* ---- sparse bundle adjustment building blocks (fp64, device pointers, stream-ordered) ---------
  * Replace cost_func_points_extrinsics / cost_func_points_only (calib.py:312-316,355-359) and the
  * finite-difference Jacobian + TRF step SciPy's least_squares performs on them (calib.py:335,381).

@@ -45,4 +45,5 @@ if rank == 0:
                       "seconds": float(dt.item()), "lm_iters_per_sec": info["n_solve"] / float(dt.item()),
                       "ms_per_attempt": 1e3 * float(dt.item()) / info["n_solve"], "F": info["F"], "converged": info["converged"],
                       "marker_rms_m": float(np.sqrt(se[0].item() / se[1].item())), "bcr_info": info["bcr_info"]}))
+sol.close()
 if world > 1: dist.destroy_process_group()

@@ -11,6 +11,9 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(float(os.environ.get("ACINO_TEST_HANG_DUMP_S", "240")), exit=True)   # a hang prints where
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -43,6 +46,8 @@ def main():
         ok = dF < 1e-6 and dx < 1e-3 and info["bcr_info"] == 0
     flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    sol.close()                      # the captured graph references the NCCL communicator: release it first
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 

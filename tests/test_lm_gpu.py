@@ -120,6 +120,107 @@ def test_lm_assemble_matches_oracle_system(handle, dummy_cams):
     assert abs(cs - fte.smooth_cost(x0, p["Ts"], q)) < 1e-9 * max(1.0, cs)
 
 
+def _state_on_bounds(sol, p, N, seed=0):
+    """Put an iterate with some whole columns on their bounds into the accepted state and evaluate it."""
+    import torch
+    from oracle import skeleton
+
+    lo, hi = skeleton.active_bounds()
+    x0 = p["x0"].copy()
+    for pp in range(12, 20):
+        x0[:, pp] = hi[pp] if pp % 2 else lo[pp]
+    x0 = np.clip(x0, lo, hi)
+    s = sol.st[0]
+    s["x_ext"].zero_()
+    s["x_ext"][3:3 + N] = torch.from_numpy(x0).cuda()
+    s["x32"].copy_(s["x_ext"][3:3 + N].float())
+    sol._eval(s)
+    sol._prepare(s)
+    return s
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 6, 7, 31, 100, 302])
+def test_structured_level0_matches_dense_route(handle, dummy_cams, N):
+    """REDUCE + BACKSUB of the plan (structured level 0 fused with the assembly, csrc/lm_l0.cu) give the same step as
+    lm_assemble + the dense block cyclic reduction on every level."""
+    import synth
+    import torch
+    from acinoset_b200 import lm
+    from oracle import fisheye, skeleton
+
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=31 + N, cams=dummy_cams)
+    sol = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"])
+    s = _state_on_bounds(sol, p, N)
+    lam = 0.05
+    D, Lc, rhs = (torch.zeros_like(t) for t in (sol.D, sol.Lc, sol.rhs))
+    sol.h.call_dev("acino_lm_assemble_dev", N, 0, N, sol.M, s["H"], s["gtot"], s["fixed"], sol.sw, lam, D, Lc, rhs)
+    x_ref = torch.zeros_like(rhs)
+    cs = lm.ChainSolver(handle, sol.M)
+    cs.solve(D, Lc, rhs, x_ref)
+    dx, dhalo = sol.linear_solve(lam)
+    torch.cuda.synchronize()
+    assert int(cs.info.item()) == 0 and int(sol.info.item()) == 0
+    xr, xn = x_ref.cpu().numpy(), dx.cpu().numpy()
+    assert np.abs(xr).max() > 1e-6
+    assert np.abs(xn - xr).max() < 1e-8 * np.abs(xr).max()
+    assert np.abs(dhalo.cpu().numpy()).max() == 0.0
+
+
+@pytest.mark.parametrize("N,frame0,ng", [(6, 0, 1000), (150, 300, 1000), (151, 849, 1000), (9, 3, 12)])
+def test_structured_level0_pinned_payload_matches_dense_route(handle, dummy_cams, N, frame0, ng):
+    """A rank's shard (pinned end blocks, global frame offset): the interface payload of the plan equals the
+    end blocks of lm_assemble + pinned dense reduction."""
+    import synth
+    import torch
+    from acinoset_b200 import lm
+    from oracle import fisheye, skeleton
+
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=77 + N, cams=dummy_cams, start=frame0)
+    last = frame0 + N == ng
+    sol = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"], frame0=frame0, n_global=ng, rank=1 if frame0 else 0,
+                       world=3 if not last else 2)
+    s = _state_on_bounds(sol, p, N)
+    lam = 0.2
+    M = sol.M
+    D, Lc, rhs = (torch.zeros_like(t) for t in (sol.D, sol.Lc, sol.rhs))
+    sol.h.call_dev("acino_lm_assemble_dev", N, frame0, ng, M, s["H"], s["gtot"], s["fixed"], sol.sw, lam, D, Lc, rhs)
+    cs = lm.ChainSolver(handle, M, pinned=True)
+    cs.reduce(D, Lc, rhs)
+    fixed_blocks = torch.zeros(M * 3, 25, dtype=torch.uint8, device="cuda")
+    fixed_blocks[:N] = s["fixed"]
+    ref = lm.pack_interface(D, Lc, rhs, fixed_blocks.view(M, 75)).cpu().numpy()
+    sol.ctl[lm.CTL_LAM] = lam
+    sol._enq(lm.PH_REDUCE)
+    torch.cuda.synchronize()
+    got = sol.payload.cpu().numpy()
+    assert int(sol.info.item()) == 0
+    n2 = 75 * 75
+    for k, name in enumerate(("D_first", "D_last", "Lc_first", "Lc_last")):
+        a, b = got[k * n2:(k + 1) * n2], ref[k * n2:(k + 1) * n2]
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(b).max(), 1e-300), name
+    assert np.abs(got[4 * n2:4 * n2 + 150] - ref[4 * n2:4 * n2 + 150]).max() <= 1e-9 * np.abs(ref[4 * n2:4 * n2 + 150]).max()
+    assert np.array_equal(got[4 * n2 + 150:], ref[4 * n2 + 150:])
+    if frame0 > 0:
+        assert np.abs(ref[2 * n2:3 * n2]).max() > 0      # the coupling to the previous rank's last block is there
+
+
+def test_fte_solve_graph_equals_eager(handle, dummy_cams):
+    """The CUDA-graph replay of an attempt and the eager enqueue are the same kernels on the same data: identical bits."""
+    import synth
+    from acinoset_b200 import lm
+    from oracle import fisheye, skeleton
+
+    N = 120
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=9, cams=dummy_cams)
+    xa, ia = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"], use_graph=True).solve(p["x0"], max_iter=30)
+    xb, ib = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"], use_graph=False).solve(p["x0"], max_iter=30)
+    assert ia["graph"] and not ib["graph"]
+    assert ia["n_solve"] == ib["n_solve"] and ia["iters"] == ib["iters"]
+    assert ia["F"] == ib["F"] and np.array_equal(xa, xb)
+    assert ia["converged"] and ia["history"][-1] == ia["F"]
+    assert all(b <= a for a, b in zip(ia["history"], ia["history"][1:]))
+
+
 @pytest.mark.parametrize("N", [48, 200])
 def test_fte_solve_matches_cpu_restatement(handle, dummy_cams, N):
     """Solve parity: final objective within 1e-4 relative and marker positions within
