@@ -548,15 +548,15 @@ bcr_update2_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict_
 }
 
 // x_e = R^-T (z - P x_a - Q x_c), R = L Delta^1/2 stored by bcr_factor in D_e.  256 threads.
-//   1. v = z - [P | Q] [x_a ; x_c]: thread (row, third) reads 50 contiguous doubles of the row's 150 - all loads
-//      independent and issued at once; L is staged in shared memory meanwhile
+//   1. v = z - [P | Q] [x_a ; x_c]: warp per row, lanes across the row (coalesced), 30 independent loads in flight per
+//      thread; L is staged in shared memory meanwhile
 //   2. backward substitution L^T x = Delta^-1/2 v by ONE warp, no barriers: lane holds rows lane, lane+32,
 //      lane+64; once x_k is final it is broadcast by shuffle and u_i -= L_ki x_k for i < k (row k of L).
 __global__ void __launch_bounds__(256)
 bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*factor*/, const double* __restrict__ P,
                    const double* __restrict__ Q, const double* __restrict__ rhs, double* __restrict__ x) {
     __shared__ __align__(16) double sxx[2 * SB + 2];       // [x_a ; x_c]
-    __shared__ double spart[3][SB];
+    __shared__ double spart[1][SB];
     __shared__ double sL[SB * LD];
     const int e = elim[3 * blockIdx.x], a = elim[3 * blockIdx.x + 1], c = elim[3 * blockIdx.x + 2];
     const int tid = threadIdx.x;
@@ -567,21 +567,41 @@ bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*
         cp_async8(&sL[r * LD + (i - r * SB)], D + (size_t)e * SB2 + i);
     }
     __syncthreads();
-    if (tid < 3 * SB) {
-        const int r = tid / 3, part = tid - 3 * r;          // columns [50 part, 50 part + 50) of [P | Q]
-        double s0 = 0.0, s1 = 0.0;
+    {
+        // v_r = sum_c P[r][c] x_a[c] + Q[r][c] x_c[c]: warp per row, lanes across the row (coalesced 600-byte rows, all
+        // loads of a warp's 9-10 rows independent), fixed-order butterfly sum.  spart[0] holds the result.
+        const int warp = tid >> 5, lane = tid & 31;
+        const double* Pe = P + (size_t)e * SB2;
+        const double* Qe = Q + (size_t)e * SB2;
+        // rows r = warp + 8 i, i = 0..9 in two batches of five: 30 independent loads in flight per thread
 #pragma unroll
-        for (int k = 0; k < 50; k += 2) {
-            const int cc = 50 * part + k;                    // even; a pair never straddles P | Q (75 is odd: handle per element)
-            const int c0 = cc, c1 = cc + 1;
-            const double m0 = c0 < SB ? (a >= 0 ? P[(size_t)e * SB2 + r * SB + c0] : 0.0)
-                                      : (c >= 0 ? Q[(size_t)e * SB2 + r * SB + c0 - SB] : 0.0);
-            const double m1 = c1 < SB ? (a >= 0 ? P[(size_t)e * SB2 + r * SB + c1] : 0.0)
-                                      : (c >= 0 ? Q[(size_t)e * SB2 + r * SB + c1 - SB] : 0.0);
-            s0 = fma(m0, sxx[c0], s0);
-            s1 = fma(m1, sxx[c1], s1);
+        for (int batch = 0; batch < 2; ++batch) {
+            double pv[5][3], qv[5][3];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int r = warp + 8 * (5 * batch + i);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int cc = lane + 32 * k;
+                    const bool ok = r < SB && cc < SB;
+                    pv[i][k] = (ok && a >= 0) ? Pe[r * SB + cc] : 0.0;
+                    qv[i][k] = (ok && c >= 0) ? Qe[r * SB + cc] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int r = warp + 8 * (5 * batch + i);
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int cc = lane + 32 * k;
+                    if (cc < SB) s = fma(qv[i][k], sxx[SB + cc], fma(pv[i][k], sxx[cc], s));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && r < SB) spart[0][r] = s;
+            }
         }
-        spart[part][r] = s0 + s1;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -591,7 +611,7 @@ bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int i = lane + 32 * j;
-            u[j] = i < SB ? (rhs[(size_t)e * SB + i] - ((spart[0][i] + spart[1][i]) + spart[2][i])) * sL[i * LD + i] : 0.0;
+            u[j] = i < SB ? (rhs[(size_t)e * SB + i] - spart[0][i]) * sL[i * LD + i] : 0.0;
         }
 #pragma unroll
         for (int j = 2; j >= 0; --j) {
