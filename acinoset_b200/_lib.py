@@ -107,7 +107,7 @@ def _load():
     lib.acino_lm_step_dev.restype = ci
     lib.acino_lm_reduce_dev.argtypes = [vp, ci] + [vp] * 7
     lib.acino_lm_reduce_dev.restype = ci
-    lib.acino_bcr_factor_dev.argtypes = [vp, ci] + [vp] * 8
+    lib.acino_bcr_factor_dev.argtypes = [vp, ci] + [vp] * 9
     lib.acino_bcr_factor_dev.restype = ci
     lib.acino_bcr_update_dev.argtypes = [vp, ci] + [vp] * 7
     lib.acino_bcr_update_dev.restype = ci

@@ -12,8 +12,6 @@
 //   bcr_backsub  (reverse order)   x_e = R^-T (z - P x_a - Q x_c)
 // fp64 throughout: the smoothness weights (2 q / Ts^4 ~ 1e7..1e9) against data blocks (~1e5) make
 // the system too ill-conditioned for fp32 factorisation; B200 runs fp64 FMA at half the fp32 rate.
-#include <cstdlib>
-
 #include "acino_common.cuh"
 
 namespace acino {
@@ -124,13 +122,22 @@ __device__ __forceinline__ void bcr_diag_block(double* __restrict__ sm, double* 
 
 template <bool TWO_PASS>
 __global__ void __launch_bounds__(FACTOR_THREADS, TWO_PASS ? 2 : 1)
-bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__ D, const double* __restrict__ Lc,
-                  double* __restrict__ P, double* __restrict__ Q, double* __restrict__ rhs, int* __restrict__ info) {
+bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, const double* __restrict__ D, const double* __restrict__ Lc,
+                  double* __restrict__ P, double* __restrict__ Q, double* __restrict__ R, double* __restrict__ rhs,
+                  int* __restrict__ info, const int split) {
     constexpr int NCOLS = TWO_PASS ? FCOLS_2P : FCOLS;      // panel columns of the (first) pass
     constexpr int ZCOL = NCOLS - 1;                          // the right-hand-side vector b is the last column
     extern __shared__ __align__(16) double sm[];             // [NCOLS][FCS]
     __shared__ double sinv[SB], sdi[SB], scpq_all[TWO_PASS ? SB / FB : 1][FB][FB];
-    const int e = elim[3 * blockIdx.x], a = elim[3 * blockIdx.x + 1], c = elim[3 * blockIdx.x + 2];
+    const int e = elim[3 * blockIdx.x], c = elim[3 * blockIdx.x + 2];
+    // Split mode (small levels, two CTAs per block, TWO_PASS layout): slice 0 eliminates [D | Lc_e | b] and writes R, P, z;
+    // slice 1 eliminates [D | Lc_c^T] and writes Q.  Both factor D redundantly - the SMs are idle at these levels - and each
+    // streams a 151-column panel instead of 226 columns through shared memory (the kernel's bound).  The factor goes to R,
+    // not back into D: the other slice may still be reading D_e.
+    const int slice = (TWO_PASS && split) ? (int)blockIdx.y : 0;
+    if (slice == 1 && c < 0) return;
+    // neighbour whose coupling fills columns 75..149: the left one (Lc_e), or in slice 1 the right one (Lc_c^T)
+    const int a = slice == 1 ? c : elim[3 * blockIdx.x + 1];
     const int tid = threadIdx.x;
 #ifdef ACINO_BCR_TIMING
     long long _tprev = clock64();
@@ -138,22 +145,26 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
     // ---- load the panel (column-major) with 8-byte async copies, all in flight at once
     {
         const double* gD = D + (size_t)e * SB2;
-        const double* gA = Lc + (size_t)e * SB2;
+        const double* gA = Lc + (size_t)(slice == 1 ? c : e) * SB2;
         const double* gC = Lc + (size_t)(c >= 0 ? c : 0) * SB2;
         for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
             const int r = i / SB, cc = i - r * SB;
             cp_async8(&sm[r * FCS + cc], gD + i);                              // symmetric: (r,cc) == (cc,r)
-            if (a >= 0) cp_async8(&sm[(SB + cc) * FCS + r], gA + i);           // Lc_e (r, cc)
+            if (a >= 0) {
+                if (slice == 1) cp_async8(&sm[(SB + r) * FCS + cc], gA + i);   // Lc_c^T (cc, r) = Lc_c (r, cc)
+                else cp_async8(&sm[(SB + cc) * FCS + r], gA + i);              // Lc_e (r, cc)
+            }
             if (!TWO_PASS && c >= 0) cp_async8(&sm[(2 * SB + r) * FCS + cc], gC + i);   // Lc_c^T (cc, r) = Lc_c (r, cc)
         }
-        if (tid < SB) sm[ZCOL * FCS + tid] = rhs[(size_t)e * SB + tid];
+        if (tid < SB) sm[ZCOL * FCS + tid] = slice == 1 ? 0.0 : rhs[(size_t)e * SB + tid];
         if (tid < NCOLS) sm[tid * FCS + SB] = 0.0;                             // row 75: zero padding
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
     const int col = tid >> 1, half = tid & 1;
     const bool is_d = col < SB;
-    const bool rhs_on = (tid >= SB && tid < NCOLS) && (tid == ZCOL || (tid < 2 * SB ? a >= 0 : c >= 0));     // phase (b)
-    const bool active_col = col < NCOLS && (is_d || col == ZCOL || (col < 2 * SB ? a >= 0 : c >= 0));         // phase (c)
+    const bool z_on = slice == 0;
+    const bool rhs_on = (tid >= SB && tid < NCOLS) && (tid == ZCOL ? z_on : (tid < 2 * SB ? a >= 0 : c >= 0));     // phase (b)
+    const bool active_col = col < NCOLS && (is_d || (col == ZCOL ? z_on : (col < 2 * SB ? a >= 0 : c >= 0)));       // phase (c)
     double* cj = sm + col * FCS;
     __syncthreads();
     // (a) by thread FACTOR_THREADS - 1 (its column slot is beyond the panel, so it is otherwise idle)
@@ -233,13 +244,13 @@ bcr_factor_kernel(const int* __restrict__ elim /*[ne][3]*/, double* __restrict__
     // ---- write-out: factor in place of D_e, P, z (and Q in the one-pass kernel)
     for (int i = tid; i < SB * SB; i += FACTOR_THREADS) {
         const int r = i / SB, cc = i - r * SB;
-        D[(size_t)e * SB2 + i] = r > cc ? sm[cc * FCS + r] * sinv[cc] : (r == cc ? sdi[r] : 0.0);
-        if (a >= 0) P[(size_t)e * SB2 + i] = sm[(SB + cc) * FCS + r] * sdi[r];
+        if (slice == 0) R[(size_t)e * SB2 + i] = r > cc ? sm[cc * FCS + r] * sinv[cc] : (r == cc ? sdi[r] : 0.0);
+        if (a >= 0) (slice == 1 ? Q : P)[(size_t)e * SB2 + i] = sm[(SB + cc) * FCS + r] * sdi[r];
         if (!TWO_PASS && c >= 0) Q[(size_t)e * SB2 + i] = sm[(2 * SB + cc) * FCS + r] * sdi[r];
     }
-    if (tid < SB) rhs[(size_t)e * SB + tid] = sm[ZCOL * FCS + tid] * sdi[tid];
+    if (slice == 0 && tid < SB) rhs[(size_t)e * SB + tid] = sm[ZCOL * FCS + tid] * sdi[tid];
     BCR_MARK(4);
-    if (!TWO_PASS || c < 0) return;
+    if (!TWO_PASS || c < 0 || split) return;
 
     // ---- pass 2: Q = R^-1 Lc_c^T.  The right-hand buffer is reloaded with Lc_c^T; every column replays the
     //      elimination on its own (multipliers c_pq, 1/a_pp and the final panel columns are all in shared
@@ -483,7 +494,7 @@ __device__ __forceinline__ void rmw_tile(double* __restrict__ Dj, const int ty, 
 
 __global__ void __launch_bounds__(UPDATE2_THREADS, 2)
 bcr_update2_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict__ D, double* __restrict__ Lc,
-                   const double* __restrict__ P, const double* __restrict__ Q, double* __restrict__ rhs) {
+                   const double* __restrict__ P, const double* __restrict__ Q, double* __restrict__ rhs, const int split) {
     extern __shared__ __align__(16) double sm[];
     double* b0 = sm;                       // Q_el
     double* b1 = sm + SB * LD;             // P_er, then P_el
@@ -491,6 +502,29 @@ bcr_update2_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict_
     double* szr = szl + SB;                // z_er
     const int j = surv[3 * blockIdx.x], el = surv[3 * blockIdx.x + 1], er = surv[3 * blockIdx.x + 2];
     const int tid = threadIdx.x;
+    // Split mode (small levels): CTA (., 0) does stage 1 (the SYRKs onto D_j and b_j), CTA (., 1) stage 2 (the GEMM that
+    // gives Lc_j) - disjoint outputs, so the two halves of a block's update run on two SMs at once.
+    const int part = split ? (int)blockIdx.y : -1;
+    if (part == 1) {
+        if (el < 0) return;
+        for (int i = tid; i < SB * SB; i += UPDATE2_THREADS) {
+            const int r = i / SB, c = i - r * SB;
+            cp_async8(&b0[r * LD + c], Q + (size_t)el * SB2 + i);
+            cp_async8(&b1[r * LD + c], P + (size_t)el * SB2 + i);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        const int gy = tid >> 4, gx = tid & 15;
+        if (gy < 15 && gx < 15) {
+            double acc[5][5];
+            tile_atb(b0, b1, 5 * gy, 5 * gx, acc);
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) Lc[(size_t)j * SB2 + (5 * gy + r) * SB + 5 * gx + c] = -acc[r][c];
+        }
+        return;
+    }
     for (int i = tid; i < SB * SB; i += UPDATE2_THREADS) {
         const int r = i / SB, c = i - r * SB;
         if (el >= 0) cp_async8(&b0[r * LD + c], Q + (size_t)el * SB2 + i);
@@ -529,7 +563,7 @@ bcr_update2_kernel(const int* __restrict__ surv /*[ns][3]*/, double* __restrict_
     }
     __syncthreads();                       // group B's update of D_j is visible; P_er no longer needed
     if (have && !grpB) rmw_tile(Dj, ty, tx, acc);
-    if (el < 0) return;
+    if (el < 0 || part == 0) return;
     // ---- stage 2: Lc_j = -Q_el^T P_el
     for (int i = tid; i < SB * SB; i += UPDATE2_THREADS) {
         const int r = i / SB, c = i - r * SB;
@@ -636,54 +670,61 @@ bcr_backsub_kernel(const int* __restrict__ elim, const double* __restrict__ D /*
 }
 
 
-cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const double* Lc, double* P, double* Q,
-                              double* rhs, int* info, cudaStream_t s) {
+// Levels with at most SPLIT_MAX blocks run two CTAs per block (split kernels above): the GPU has 148 SMs and these levels
+// are bound by the latency of one block.  Levels with more blocks than SMs use the two-pass / two-stage kernels (two CTAs
+// per SM); in between, the one-pass kernels.
+constexpr int SPLIT_MAX = 74;
+constexpr int TWO_PASS_FROM = 149;
+
+static cudaError_t bcr_configure() {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || configured[dev]) return cudaSuccess;        // the attribute is per device
+    cudaError_t e = cudaFuncSetAttribute(bcr_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(bcr_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(bcr_update2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE2_SMEM);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_bcr_factor(int n_elim, const int* elim, const double* D, const double* Lc, double* P, double* Q,
+                              double* R, double* rhs, int* info, cudaStream_t s) {
     if (n_elim <= 0) return cudaSuccess;
-    static bool set = false;
-    static int two_pass_from = 149;      // ACINO_BCR_TWO_PASS_FROM: levels with at least this many blocks use the two-pass kernel
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(bcr_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR_SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(bcr_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_FACTOR2_SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE_SMEM);
-        if (e != cudaSuccess) return e;
-        const char* env = getenv("ACINO_BCR_TWO_PASS_FROM");
-        if (env) two_pass_from = atoi(env);
-        set = true;
-    }
-    if (n_elim >= two_pass_from)
-        bcr_factor_kernel<true><<<n_elim, FACTOR_THREADS, BCR_FACTOR2_SMEM, s>>>(elim, D, Lc, P, Q, rhs, info);
+    cudaError_t e = bcr_configure();
+    if (e != cudaSuccess) return e;
+    if (n_elim <= SPLIT_MAX)
+        bcr_factor_kernel<true><<<dim3(n_elim, 2), FACTOR_THREADS, BCR_FACTOR2_SMEM, s>>>(elim, D, Lc, P, Q, R, rhs, info, 1);
+    else if (n_elim >= TWO_PASS_FROM)
+        bcr_factor_kernel<true><<<n_elim, FACTOR_THREADS, BCR_FACTOR2_SMEM, s>>>(elim, D, Lc, P, Q, R, rhs, info, 0);
     else
-        bcr_factor_kernel<false><<<n_elim, FACTOR_THREADS, BCR_FACTOR_SMEM, s>>>(elim, D, Lc, P, Q, rhs, info);
+        bcr_factor_kernel<false><<<n_elim, FACTOR_THREADS, BCR_FACTOR_SMEM, s>>>(elim, D, Lc, P, Q, R, rhs, info, 0);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
                               double* rhs, cudaStream_t s) {
     if (n_surv <= 0) return cudaSuccess;
-    static bool set = false;
-    static int two_stage_from = 149;     // ACINO_BCR_TWO_PASS_FROM: levels with at least this many blocks use the two-stage kernel
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE_SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(bcr_update2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BCR_UPDATE2_SMEM);
-        if (e != cudaSuccess) return e;
-        const char* env = getenv("ACINO_BCR_TWO_PASS_FROM");
-        if (env) two_stage_from = atoi(env);
-        set = true;
-    }
-    if (n_surv >= two_stage_from)
-        bcr_update2_kernel<<<n_surv, UPDATE2_THREADS, BCR_UPDATE2_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
+    cudaError_t e = bcr_configure();
+    if (e != cudaSuccess) return e;
+    if (n_surv <= SPLIT_MAX)
+        bcr_update2_kernel<<<dim3(n_surv, 2), UPDATE2_THREADS, BCR_UPDATE2_SMEM, s>>>(surv, D, Lc, P, Q, rhs, 1);
+    else if (n_surv >= TWO_PASS_FROM)
+        bcr_update2_kernel<<<n_surv, UPDATE2_THREADS, BCR_UPDATE2_SMEM, s>>>(surv, D, Lc, P, Q, rhs, 0);
     else
         bcr_update_kernel<<<n_surv, UPDATE_THREADS, BCR_UPDATE_SMEM, s>>>(surv, D, Lc, P, Q, rhs);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* D, const double* P, const double* Q,
+cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* R, const double* P, const double* Q,
                                const double* rhs, double* x, cudaStream_t s) {
     if (n_elim <= 0) return cudaSuccess;
-    bcr_backsub_kernel<<<n_elim, 256, 0, s>>>(elim, D, P, Q, rhs, x);
+    bcr_backsub_kernel<<<n_elim, 256, 0, s>>>(elim, R, P, Q, rhs, x);
     return cudaGetLastError();
 }
 

@@ -64,11 +64,11 @@ cudaError_t launch_lm_step(int n_frames, long long frame0, long long ng, const d
 cudaError_t launch_lm_reduce(int n, const float* a0, const double* a1, const double* a2, const double* a3,
                              const double* m, double* out, double* ws, cudaStream_t s);
 size_t lm_reduce_ws_bytes();
-cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const double* Lc, double* P, double* Q,
-                              double* rhs, int* info, cudaStream_t s);
+cudaError_t launch_bcr_factor(int n_elim, const int* elim, const double* D, const double* Lc, double* P, double* Q,
+                              double* R, double* rhs, int* info, cudaStream_t s);
 cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
                               double* rhs, cudaStream_t s);
-cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* D, const double* P, const double* Q,
+cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* R, const double* P, const double* Q,
                                const double* rhs, double* x, cudaStream_t s);
 cudaError_t launch_sba_cams(int C, const double* params, const double* R, const double* t, const double* K,
                             const double* D, void* cams, cudaStream_t s);
@@ -895,12 +895,12 @@ int acino_lm_reduce_dev(acino_handle* h, int n, const float* a0, const double* a
     return ACINO_OK;
 }
 
-int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, double* D, const double* Lc, double* P,
-                         double* Q, double* rhs, int32_t* info, void* cuda_stream) {
+int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* D, const double* Lc, double* P,
+                         double* Q, double* R, double* rhs, int32_t* info, void* cuda_stream) {
     DEV_ENTER("acino_bcr_factor_dev");
-    if (n_elim < 0 || (n_elim > 0 && (!elim || !D || !Lc || !P || !Q || !rhs || !info)))
+    if (n_elim < 0 || (n_elim > 0 && (!elim || !D || !Lc || !P || !Q || !R || !rhs || !info)))
         return fail(h, ACINO_ERR_ARG, "acino_bcr_factor_dev: bad arguments");
-    CK(launch_bcr_factor(n_elim, elim, D, Lc, P, Q, rhs, info, s));
+    CK(launch_bcr_factor(n_elim, elim, D, Lc, P, Q, R, rhs, info, s));
     h->launches += n_elim > 0;
     return ACINO_OK;
 }
@@ -915,12 +915,12 @@ int acino_bcr_update_dev(acino_handle* h, int n_surv, const int32_t* surv, doubl
     return ACINO_OK;
 }
 
-int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* D, const double* P,
+int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* R, const double* P,
                           const double* Q, const double* rhs, double* x, void* cuda_stream) {
     DEV_ENTER("acino_bcr_backsub_dev");
-    if (n_elim < 0 || (n_elim > 0 && (!elim || !D || !P || !Q || !rhs || !x)))
+    if (n_elim < 0 || (n_elim > 0 && (!elim || !R || !P || !Q || !rhs || !x)))
         return fail(h, ACINO_ERR_ARG, "acino_bcr_backsub_dev: bad arguments");
-    CK(launch_bcr_backsub(n_elim, elim, D, P, Q, rhs, x, s));
+    CK(launch_bcr_backsub(n_elim, elim, R, P, Q, rhs, x, s));
     h->launches += n_elim > 0;
     return ACINO_OK;
 }

@@ -19,11 +19,11 @@ cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, cons
 cudaError_t launch_lm_reduce(int n, const float* a0, const double* a1, const double* a2, const double* a3,
                              const double* m, double* out, double* ws, cudaStream_t s);
 size_t lm_reduce_ws_bytes();
-cudaError_t launch_bcr_factor(int n_elim, const int* elim, double* D, const double* Lc, double* P, double* Q,
-                              double* rhs, int* info, cudaStream_t s);
+cudaError_t launch_bcr_factor(int n_elim, const int* elim, const double* D, const double* Lc, double* P, double* Q,
+                              double* R, double* rhs, int* info, cudaStream_t s);
 cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc, const double* P, const double* Q,
                               double* rhs, cudaStream_t s);
-cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* D, const double* P, const double* Q,
+cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* R, const double* P, const double* Q,
                                const double* rhs, double* x, cudaStream_t s);
 cudaError_t launch_l0_invert(const LmShard& sh, int n_elim, const int* elim, const float* H, const double* gtot,
                              const unsigned char* fixed, const double* sw, const double* ctl, double* W, double* rhs,
@@ -277,7 +277,7 @@ int acino_lm_plan_create(acino_handle* h, const acino_lm_desc* desc, acino_lm_pl
     if (d.n_frames < 1 || d.n_blocks * 3 < d.n_frames || d.world < 1 || d.rank < 0 || d.rank >= d.world)
         return fail(h, ACINO_ERR_ARG, "acino_lm_plan_create: bad shard description");
     if (d.world > 1 && d.n_blocks < 2) return fail(h, ACINO_ERR_ARG, "acino_lm_plan_create: a rank needs at least 2 super-blocks");
-    if (!d.meas || !d.w || !d.sw || !d.lo || !d.hi || !d.pred || !d.step || !d.D || !d.Lc || !d.P || !d.Q || !d.rhs || !d.dx ||
+    if (!d.meas || !d.w || !d.sw || !d.lo || !d.hi || !d.pred || !d.step || !d.D || !d.Lc || !d.P || !d.Q || !d.R || !d.rhs || !d.dx ||
         !d.dhalo || !d.info || !d.sums_local || !d.sums_all || !d.ctl || !d.ctl_host || !d.hist)
         return fail(h, ACINO_ERR_ARG, "acino_lm_plan_create: NULL buffer");
     for (int i = 0; i < 2; ++i)
@@ -285,7 +285,7 @@ int acino_lm_plan_create(acino_handle* h, const acino_lm_desc* desc, acino_lm_pl
             return fail(h, ACINO_ERR_ARG, "acino_lm_plan_create: NULL state buffer");
     if ((d.n_elim0 > 0 && !d.elim0) || (d.n_surv0 > 0 && !d.surv0) || (d.n_levels > 0 && (!d.level_counts || !d.sched)))
         return fail(h, ACINO_ERR_ARG, "acino_lm_plan_create: NULL schedule");
-    if (d.world > 1 && (!d.payload || !d.gathered || !d.cD || !d.cLc || !d.cP || !d.cQ || !d.crhs || !d.cx ||
+    if (d.world > 1 && (!d.payload || !d.gathered || !d.cD || !d.cLc || !d.cP || !d.cQ || !d.cR || !d.crhs || !d.cx ||
                         d.n_clevels < 1 || !d.clevel_counts || !d.csched))
         return fail(h, ACINO_ERR_ARG, "acino_lm_plan_create: NULL interface-chain buffer");
     if (!h->have_cams) return fail(h, ACINO_ERR_STATE, "acino_lm_plan_create: cameras not set");
@@ -312,18 +312,18 @@ int acino_lm_plan_destroy(acino_lm_plan* plan) {
 
 // forward elimination / back-substitution of the dense levels of a chain
 static int chain_reduce(acino_handle* h, const std::vector<int>& lvl, const int32_t* sched, double* D, double* Lc, double* P,
-                        double* Q, double* rhs, int32_t* info, cudaStream_t s) {
+                        double* Q, double* R, double* rhs, int32_t* info, cudaStream_t s) {
     const int32_t* ptr = sched;
     for (size_t l = 0; l < lvl.size() / 2; ++l) {
         const int ne = lvl[2 * l], ns = lvl[2 * l + 1];
-        CK(launch_bcr_factor(ne, ptr, D, Lc, P, Q, rhs, info, s));
+        CK(launch_bcr_factor(ne, ptr, D, Lc, P, Q, R, rhs, info, s));
         CK(launch_bcr_update(ns, ptr + 3 * (size_t)ne, D, Lc, P, Q, rhs, s));
         h->launches += (ne > 0) + (ns > 0);
         ptr += 3 * (size_t)(ne + ns);
     }
     return ACINO_OK;
 }
-static int chain_backsub(acino_handle* h, const std::vector<int>& lvl, const int32_t* sched, const double* D, const double* P,
+static int chain_backsub(acino_handle* h, const std::vector<int>& lvl, const int32_t* sched, const double* R, const double* P,
                          const double* Q, const double* rhs, double* x, cudaStream_t s) {
     std::vector<const int32_t*> ptrs(lvl.size() / 2);
     const int32_t* ptr = sched;
@@ -332,7 +332,7 @@ static int chain_backsub(acino_handle* h, const std::vector<int>& lvl, const int
         ptr += 3 * (size_t)(lvl[2 * l] + lvl[2 * l + 1]);
     }
     for (size_t l = lvl.size() / 2; l-- > 0;) {
-        CK(launch_bcr_backsub(lvl[2 * l], ptrs[l], D, P, Q, rhs, x, s));
+        CK(launch_bcr_backsub(lvl[2 * l], ptrs[l], R, P, Q, rhs, x, s));
         h->launches += lvl[2 * l] > 0;
     }
     return ACINO_OK;
@@ -370,7 +370,7 @@ int acino_lm_enqueue(acino_handle* h, acino_lm_plan* plan, int phase, void* cuda
         CK(launch_l0_invert(sh, d.n_elim0, d.elim0, d.H[0], d.gtot[0], d.fixed[0], d.sw, d.ctl, d.P, d.rhs, d.info, s));
         CK(launch_l0_update(sh, d.n_surv0, d.surv0, d.H[0], d.gtot[0], d.fixed[0], d.sw, d.ctl, d.P, d.D, d.Lc, d.rhs, s));
         h->launches += (d.n_elim0 > 0) + (d.n_surv0 > 0);
-        rc = chain_reduce(h, plan->lvl, d.sched, d.D, d.Lc, d.P, d.Q, d.rhs, d.info, s);
+        rc = chain_reduce(h, plan->lvl, d.sched, d.D, d.Lc, d.P, d.Q, d.R, d.rhs, d.info, s);
         if (rc) return rc;
         if (d.world > 1) {
             lm_iface_pack_kernel<<<(ACINO_LM_PAYLOAD + 255) / 256, 256, 0, s>>>(N, M, d.D, d.Lc, d.rhs, d.fixed[0], d.payload);
@@ -383,15 +383,15 @@ int acino_lm_enqueue(acino_handle* h, acino_lm_plan* plan, int phase, void* cuda
             lm_iface_build_kernel<<<2 * d.world, 256, 0, s>>>(d.world, d.gathered, d.cD, d.cLc, d.crhs);
             CK(cudaGetLastError());
             h->launches += 1;
-            rc = chain_reduce(h, plan->clvl, d.csched, d.cD, d.cLc, d.cP, d.cQ, d.crhs, d.info, s);
+            rc = chain_reduce(h, plan->clvl, d.csched, d.cD, d.cLc, d.cP, d.cQ, d.cR, d.crhs, d.info, s);
             if (rc) return rc;
-            rc = chain_backsub(h, plan->clvl, d.csched, d.cD, d.cP, d.cQ, d.crhs, d.cx, s);
+            rc = chain_backsub(h, plan->clvl, d.csched, d.cR, d.cP, d.cQ, d.crhs, d.cx, s);
             if (rc) return rc;
             lm_iface_scatter_kernel<<<1, 96, 0, s>>>(d.rank, d.world, M, d.cx, d.dx, d.dhalo);
             CK(cudaGetLastError());
             h->launches += 1;
         }
-        rc = chain_backsub(h, plan->lvl, d.sched, d.D, d.P, d.Q, d.rhs, d.dx, s);
+        rc = chain_backsub(h, plan->lvl, d.sched, d.R, d.P, d.Q, d.rhs, d.dx, s);
         if (rc) return rc;
         CK(launch_l0_backsub(sh, d.n_elim0, d.elim0, d.fixed[0], d.sw, d.P, d.rhs, d.dx, s));
         h->launches += d.n_elim0 > 0;

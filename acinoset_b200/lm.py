@@ -140,18 +140,19 @@ class ChainSolver:
         self.left = left
         self.P = torch.zeros(M, SB, SB, dtype=torch.float64, device=dev)
         self.Q = torch.zeros(M, SB, SB, dtype=torch.float64, device=dev)
+        self.R = torch.zeros(M, SB, SB, dtype=torch.float64, device=dev)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def reduce(self, D, Lc, rhs):
         for lv in self.levels:
             ne, ns = lv["elim"].shape[0], lv["surv"].shape[0]
-            self.h.call_dev("acino_bcr_factor_dev", ne, lv["elim"], D, Lc, self.P, self.Q, rhs, self.info)
+            self.h.call_dev("acino_bcr_factor_dev", ne, lv["elim"], D, Lc, self.P, self.Q, self.R, rhs, self.info)
             if ns:
                 self.h.call_dev("acino_bcr_update_dev", ns, lv["surv"], D, Lc, self.P, self.Q, rhs)
 
     def backsub(self, D, rhs, x):
         for lv in reversed(self.levels):
-            self.h.call_dev("acino_bcr_backsub_dev", lv["elim"].shape[0], lv["elim"], D, self.P, self.Q, rhs, x)
+            self.h.call_dev("acino_bcr_backsub_dev", lv["elim"].shape[0], lv["elim"], self.R, self.P, self.Q, rhs, x)
 
     def solve(self, D, Lc, rhs, x):
         """Unpinned chain: full solve (D, Lc, rhs are overwritten)."""
@@ -198,10 +199,10 @@ class LmDesc(ctypes.Structure):
     _fields_ = ([("n_frames", _i32), ("n_blocks", _i32), ("rank", _i32), ("world", _i32), ("frame0", _i64), ("n_global", _i64)]
                 + [(k, _vp) for k in ("meas", "w", "sw", "lo", "hi")]
                 + [(k, _vp * 2) for k in ("x_ext", "x32", "cost", "g", "H", "gtot", "fixed", "cost_s")]
-                + [(k, _vp) for k in ("pred", "step", "D", "Lc", "P", "Q", "rhs", "dx", "dhalo", "info")]
+                + [(k, _vp) for k in ("pred", "step", "D", "Lc", "P", "Q", "R", "rhs", "dx", "dhalo", "info")]
                 + [("n_elim0", _i32), ("n_surv0", _i32), ("elim0", _vp), ("surv0", _vp),
                    ("n_levels", _i32), ("level_counts", _vp), ("sched", _vp)]
-                + [(k, _vp) for k in ("payload", "gathered", "cD", "cLc", "cP", "cQ", "crhs", "cx")]
+                + [(k, _vp) for k in ("payload", "gathered", "cD", "cLc", "cP", "cQ", "cR", "crhs", "cx")]
                 + [("n_clevels", _i32), ("clevel_counts", _vp), ("csched", _vp)]
                 + [(k, _vp) for k in ("sums_local", "sums_all", "ctl", "ctl_host", "hist")]
                 + [("hist_cap", _i32)])
@@ -262,7 +263,7 @@ class FTESolver:
                         g=buf(N, NA, dtype=f32), H=buf(N, _lib.N_UPPER, dtype=f32), gtot=buf(N, NA),
                         fixed=buf(N, NA, dtype=torch.uint8), cost_s=buf(N)) for _ in range(2)]
         self.pred, self.step = buf(N), buf(N)
-        self.D, self.Lc, self.P, self.Q = (buf(M, SB, SB) for _ in range(4))
+        self.D, self.Lc, self.P, self.Q, self.R = (buf(M, SB, SB) for _ in range(5))
         self.rhs, self.dx = buf(M, SB), buf(M, SB)
         self.dhalo = buf(2, SB)
         self.info = torch.zeros(1, dtype=i32, device=dev)
@@ -281,7 +282,7 @@ class FTESolver:
         d = LmDesc()
         d.n_frames, d.n_blocks, d.rank, d.world, d.frame0, d.n_global = N, M, self.rank, self.world, self.frame0, self.ng
         for k, t in (("meas", self.meas), ("w", self.w), ("sw", self.sw), ("lo", self.lo), ("hi", self.hi),
-                     ("pred", self.pred), ("step", self.step), ("D", self.D), ("Lc", self.Lc), ("P", self.P), ("Q", self.Q),
+                     ("pred", self.pred), ("step", self.step), ("D", self.D), ("Lc", self.Lc), ("P", self.P), ("Q", self.Q), ("R", self.R),
                      ("rhs", self.rhs), ("dx", self.dx), ("dhalo", self.dhalo), ("info", self.info),
                      ("elim0", self.elim0), ("surv0", self.surv0), ("sched", self.sched),
                      ("sums_local", self.sums_local), ("sums_all", self.sums_all), ("ctl", self.ctl),
@@ -296,12 +297,12 @@ class FTESolver:
             self.payload = buf(PAYLOAD)
             self.gathered = buf(world, PAYLOAD)
             G2 = 2 * world
-            self.cD, self.cLc, self.cP, self.cQ = (buf(G2, SB, SB) for _ in range(4))
+            self.cD, self.cLc, self.cP, self.cQ, self.cR = (buf(G2, SB, SB) for _ in range(5))
             self.crhs, self.cx = buf(G2, SB), buf(G2, SB)
             clevels, _ = _bcr.make_schedule(G2)
             self._ccounts, csched = flatten_levels(clevels)
             self.csched = torch.from_numpy(csched).to(dev)
-            for k in ("payload", "gathered", "cD", "cLc", "cP", "cQ", "crhs", "cx", "csched"):
+            for k in ("payload", "gathered", "cD", "cLc", "cP", "cQ", "cR", "crhs", "cx", "csched"):
                 setattr(d, k, getattr(self, k).data_ptr())
             d.n_clevels = int(self._ccounts.shape[0])
             d.clevel_counts = self._ccounts.ctypes.data

@@ -243,13 +243,14 @@ int acino_lm_reduce_dev(acino_handle* h, int n, const float* a0, const double* a
 
 /* Block cyclic reduction of a block-tridiagonal SPD chain (schedule: acinoset_b200/bcr.py).
  * elim / surv are [n][3] int32 rows (block, left, right) / (block, eliminated-left, eliminated-right),
- * -1 = none.  factor overwrites D_e with its factor R = L Delta^1/2 (strict lower triangle L, diagonal
- * Delta^-1/2) and rhs_e with z = R^-1 b; info != 0 flags a non-positive pivot (block index + 1). */
-int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, double* D, const double* Lc,
-                         double* P, double* Q, double* rhs, int32_t* info, void* cuda_stream);
+ * -1 = none.  factor writes the factor of D_e, R = L Delta^1/2 (strict lower triangle L, diagonal Delta^-1/2), to
+ * R[e] (D_e itself is left alone: small levels run two CTAs per block and the other one may still be reading it)
+ * and overwrites rhs_e with z = R^-1 b; info != 0 flags a non-positive pivot (block index + 1). */
+int acino_bcr_factor_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* D, const double* Lc,
+                         double* P, double* Q, double* R, double* rhs, int32_t* info, void* cuda_stream);
 int acino_bcr_update_dev(acino_handle* h, int n_surv, const int32_t* surv, double* D, double* Lc,
                          const double* P, const double* Q, double* rhs, void* cuda_stream);
-int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* D,
+int acino_bcr_backsub_dev(acino_handle* h, int n_elim, const int32_t* elim, const double* R,
                           const double* P, const double* Q, const double* rhs, double* x,
                           void* cuda_stream);
 
@@ -291,6 +292,7 @@ typedef struct acino_lm_desc {
     double* Lc;                    /* [M][75][75] */
     double* P;                     /* [M][75][75] */
     double* Q;                     /* [M][75][75] */
+    double* R;                     /* [M][75][75] factors of the blocks the dense levels eliminate */
     double* rhs;                   /* [M][75] */
     double* dx;                    /* [M][75] the step */
     double* dhalo;                 /* [2][75] step of the neighbouring ranks' interface blocks (0 at the global ends) */
@@ -303,7 +305,7 @@ typedef struct acino_lm_desc {
     const int32_t* sched;          /* per level: n_elim elim rows then n_surv surv rows, [.][3] each */
     double* payload;               /* [ACINO_LM_PAYLOAD] this rank's reduced end blocks (world > 1) */
     const double* gathered;        /* [world][ACINO_LM_PAYLOAD] */
-    double* cD; double* cLc; double* cP; double* cQ;      /* interface chain [2 world][75][75] */
+    double* cD; double* cLc; double* cP; double* cQ; double* cR;   /* interface chain [2 world][75][75] */
     double* crhs; double* cx;      /* [2 world][75] */
     int32_t n_clevels;
     const int32_t* clevel_counts;  /* HOST */

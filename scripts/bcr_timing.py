@@ -25,7 +25,7 @@ for rep in range(3):
     torch.cuda.synchronize()
     L.lib.acino_debug_bcr_reset()
     lv = cs.levels[0]      # level 0: eliminate block 1 (two neighbours)
-    h.call_dev("acino_bcr_factor_dev", lv["elim"].shape[0], lv["elim"], Dd, Ld, cs.P, cs.Q, rd, cs.info)
+    h.call_dev("acino_bcr_factor_dev", lv["elim"].shape[0], lv["elim"], Dd, Ld, cs.P, cs.Q, cs.R, rd, cs.info)
     torch.cuda.synchronize()
     out = (ctypes.c_longlong * 8)()
     L.lib.acino_debug_bcr_cycles(out)
