@@ -119,6 +119,8 @@ def _load():
     lib.acino_sba_schur_partial_size.restype = i64
     lib.acino_sba_cams_dev.argtypes = [vp, ci] + [vp] * 7
     lib.acino_sba_cams_dev.restype = ci
+    lib.acino_sba_cams_model_dev.argtypes = [vp, ci, ci, ci] + [vp] * 7
+    lib.acino_sba_cams_model_dev.restype = ci
     lib.acino_sba_eval_dev.argtypes = [vp, ci, vp, vp, vp, vp, vp, cd, vp, vp, vp, vp, vp, vp]
     lib.acino_sba_eval_dev.restype = ci
     lib.acino_sba_schur_dev.argtypes = [vp, ci, ci] + [vp] * 7 + [cd, vp, vp, vp, vp]
@@ -147,7 +149,7 @@ EXPORTED = [
     "acino_lm_prepare_dev", "acino_lm_assemble_dev", "acino_lm_step_dev", "acino_lm_reduce_dev",
     "acino_lm_desc_size", "acino_lm_plan_create", "acino_lm_plan_destroy", "acino_lm_enqueue",
     "acino_bcr_factor_dev", "acino_bcr_update_dev", "acino_bcr_backsub_dev",
-    "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_eval_dev",
+    "acino_sba_cam_bytes", "acino_sba_schur_partial_size", "acino_sba_cams_dev", "acino_sba_cams_model_dev", "acino_sba_eval_dev",
     "acino_sba_schur_dev", "acino_sba_dense_solve_dev", "acino_sba_backsub_dev", "acino_sba_pred_dev",
 ]
 

@@ -61,7 +61,7 @@ def _save_positions(positions, out_dir, name, scene_fpath, start_frame, device):
     with open(out_fpath, "wb") as f:
         pickle.dump(dict(positions=positions, start_frame=start_frame), f)
     print(f"Saved {out_fpath}")
-    _fte.save_3d_cheetah_as_2d(np.nan_to_num(positions), out_dir, scene_fpath, MARKERS, None, start_frame, out_fname=name,
+    _fte.save_3d_cheetah_as_2d(positions, out_dir, scene_fpath, MARKERS, None, start_frame, out_fname=name,
                                device=device)
     return out_fpath
 

@@ -33,9 +33,7 @@ def _save_stage(name, positions, out_dir, scene_fpath, start_frame, dlc_thresh, 
     if states is not None:
         extra.update(states)
     save_optimised_cheetah(positions, out_fpath, extra_data=extra)
-    import numpy as np
-
-    save_3d_cheetah_as_2d(np.nan_to_num(positions), out_dir, scene_fpath, MARKERS, None, start_frame, out_fname=name, device=device)
+    save_3d_cheetah_as_2d(positions, out_dir, scene_fpath, MARKERS, None, start_frame, out_fname=name, device=device)
     return out_fpath
 
 

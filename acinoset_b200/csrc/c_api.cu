@@ -70,8 +70,8 @@ cudaError_t launch_bcr_update(int n_surv, const int* surv, double* D, double* Lc
                               double* rhs, cudaStream_t s);
 cudaError_t launch_bcr_backsub(int n_elim, const int* elim, const double* R, const double* P, const double* Q,
                                const double* rhs, double* x, cudaStream_t s);
-cudaError_t launch_sba_cams(int C, const double* params, const double* R, const double* t, const double* K,
-                            const double* D, void* cams, cudaStream_t s);
+cudaError_t launch_sba_cams(int C, int model, int n_dist, const double* params, const double* R, const double* t,
+                            const double* K, const double* D, void* cams, cudaStream_t s);
 size_t sba_cam_bytes();
 cudaError_t launch_sba_eval(int n_obs, const void* cams, const double* pts, const float* uv, const int* cam_idx,
                             const int* pt_idx, double f_scale, double* res, double* Jc, double* Jp, double* wgt,
@@ -262,13 +262,14 @@ int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* m
     float* dg = dc + ac;
     float* dH = dg + ag;
     // chunk size: a multiple of 64 frames (keeps every chunk's tiles 16-byte aligned), <= kMaxChunks chunks
-    static size_t chunk0 = 0;
-    if (!chunk0) {
+    size_t chunk = 16384;        // measured best of 4096..65536 on B200 (scripts/bench_e2e_chunks.sh)
+#ifdef ACINO_EXPERIMENTS
+    {
         const char* e = getenv("ACINO_E2E_CHUNK");      // A/B knob (frames per chunk, multiple of 64)
-        chunk0 = e ? (size_t)atol(e) : 16384;
-        if (chunk0 < 64 || chunk0 % 64) chunk0 = 16384;
+        const size_t c = e ? (size_t)atol(e) : 0;
+        if (c >= 64 && c % 64 == 0) chunk = c;
     }
-    size_t chunk = chunk0;
+#endif
     while ((N + chunk - 1) / chunk > (size_t)acino_handle::kMaxChunks) chunk *= 2;
     const int n_chunks = (int)((N + chunk - 1) / chunk);
     for (int i = 0; i < n_chunks; ++i) {
@@ -937,7 +938,19 @@ int acino_sba_cams_dev(acino_handle* h, int n_cams, const double* params, const 
     DEV_ENTER("acino_sba_cams_dev");
     if (n_cams < 1 || n_cams > 10 || !K || !D || !cams || (!params && (!R || !t)))
         return fail(h, ACINO_ERR_ARG, "acino_sba_cams_dev: need 1..10 cameras, K, D and params or (R, t)");
-    CK(launch_sba_cams(n_cams, params, R, t, K, D, cams, s));
+    CK(launch_sba_cams(n_cams, 0, 4, params, R, t, K, D, cams, s));
+    h->launches += 1;
+    return ACINO_OK;
+}
+
+int acino_sba_cams_model_dev(acino_handle* h, int n_cams, int model, int n_dist, const double* params, const double* R,
+                             const double* t, const double* K, const double* D, void* cams, void* cuda_stream) {
+    DEV_ENTER("acino_sba_cams_model_dev");
+    if (n_cams < 1 || n_cams > 10 || !K || !D || !cams || (!params && (!R || !t)))
+        return fail(h, ACINO_ERR_ARG, "acino_sba_cams_model_dev: need 1..10 cameras, K, D and params or (R, t)");
+    if ((model != 0 && model != 1) || n_dist < 0 || n_dist > 12 || (model == 0 && n_dist != 4))
+        return fail(h, ACINO_ERR_ARG, "acino_sba_cams_model_dev: model 0 (fisheye, 4 coefficients) or 1 (standard, <= 12)");
+    CK(launch_sba_cams(n_cams, model, n_dist, params, R, t, K, D, cams, s));
     h->launches += 1;
     return ACINO_OK;
 }

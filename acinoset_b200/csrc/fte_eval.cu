@@ -583,6 +583,7 @@ fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const 
                 float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
     fte_eval_body<FT, WANT_H, NPAIR, PERSIST>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
 }
+#ifdef ACINO_EXPERIMENTS
 // ... or by an explicit register cap (5 CTAs x 160 threads x 80 registers = 64 000 of the SM's 65 536)
 template <int FT, bool WANT_H, int MAXREG, int NPAIR, bool PERSIST>
 __global__ void __launch_bounds__(FT * NL) __maxnreg__(MAXREG)
@@ -591,6 +592,7 @@ fte_eval_kernel_r(const __grid_constant__ SceneF scene, const int n_frames, cons
                   float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
     fte_eval_body<FT, WANT_H, NPAIR, PERSIST>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
 }
+#endif
 
 #ifdef ACINO_PHASE_TIMING
 extern "C" void acino_debug_phase_cycles(long long* out16) { cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(long long) * 16); }
@@ -652,52 +654,45 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 }
 
 // ------------------------------------------------------------------------------------------
-static int g_variant = -1;   // ACINO_FTE_VARIANT: experiment selector (frames/CTA, min CTAs/SM, unrolled camera pairs)
-
 using FteKernel = void (*)(const SceneF, int, int, const float*, const float*, const float*, float*, float*, float*);
+
+// per-device launch configuration (cudaFuncSetAttribute is per device; a process may drive several GPUs)
+struct FteDeviceCfg {
+    FteKernel configured[16];
+    int n_configured;
+    int n_sm;
+};
+static FteDeviceCfg g_dev_cfg[64];
 
 template <int FT, bool PERSIST>
 static cudaError_t launch_fte_eval_k(FteKernel kH, FteKernel kN, int ctas_per_sm, const SceneF& scene, int n_frames,
                                      const float* x, const float* meas, const float* w, float* cost, float* g, float* H,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, int exp_bits, size_t smem_pad) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
     // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
-    static int g_exp = -1;               // ACINO_FTE_EXP: bit 0 L2 prefetch of a later tile, bit 1 MUFU sin / cos
-    if (g_exp < 0) {
-        const char* e = getenv("ACINO_FTE_EXP");
-        g_exp = e ? atoi(e) : 0;
-    }
     int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
                    (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
-    if ((g_exp & 1) && (use_bulk & 1)) use_bulk |= 4;
-    if (g_exp & 2) use_bulk |= 8;
+    if ((exp_bits & 1) && (use_bulk & 1)) use_bulk |= 4;      // experiment: L2 prefetch of a later tile
+    if (exp_bits & 2) use_bulk |= 8;                          // experiment: MUFU sin / cos
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    FteDeviceCfg& cfg = g_dev_cfg[dev];
     const int n_tiles = (n_frames + FT - 1) / FT;
     int grid = n_tiles;
     if (PERSIST) {       // one wave of resident CTAs, each walking tiles blockIdx.x, blockIdx.x + grid, ...
-        static int n_sm = 0;
-        if (!n_sm) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        }
-        grid = n_tiles < n_sm * ctas_per_sm ? n_tiles : n_sm * ctas_per_sm;
-    }
-    static size_t smem_pad = (size_t)-1;    // ACINO_FTE_SMEM_PAD: residency experiment (extra dynamic smem per CTA)
-    if (smem_pad == (size_t)-1) {
-        const char* e = getenv("ACINO_FTE_SMEM_PAD");
-        smem_pad = e ? (size_t)atol(e) : 0;
+        if (!cfg.n_sm) cudaDeviceGetAttribute(&cfg.n_sm, cudaDevAttrMultiProcessorCount, dev);
+        grid = n_tiles < cfg.n_sm * ctas_per_sm ? n_tiles : cfg.n_sm * ctas_per_sm;
     }
     const size_t smem = sizeof(Smem<FT, PERSIST>) + smem_pad;
-    static FteKernel configured[16];
-    static int n_configured = 0;
     FteKernel k = H ? kH : kN;
     bool done = false;
-    for (int i = 0; i < n_configured; ++i) done |= configured[i] == k;
+    for (int i = 0; i < cfg.n_configured; ++i) done |= cfg.configured[i] == k;
     if (!done) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (n_configured < 16) configured[n_configured++] = k;
+        if (cfg.n_configured < 16) cfg.configured[cfg.n_configured++] = k;
     }
     k<<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     return cudaGetLastError();
@@ -705,38 +700,53 @@ static cudaError_t launch_fte_eval_k(FteKernel kH, FteKernel kN, int ctas_per_sm
 
 template <int FT, int MINB, int NPAIR, bool PERSIST>
 static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream, int exp_bits = 0,
+                                     size_t smem_pad = 0) {
     return launch_fte_eval_k<FT, PERSIST>(fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST>, fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST>,
-                                          MINB, scene, n_frames, x, meas, w, cost, g, H, stream);
+                                          MINB, scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, smem_pad);
 }
+#ifdef ACINO_EXPERIMENTS
 template <int FT, int MAXREG, int CTAS, int NPAIR, bool PERSIST>
 static cudaError_t launch_fte_eval_r(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream, int exp_bits,
+                                     size_t smem_pad) {
     return launch_fte_eval_k<FT, PERSIST>(fte_eval_kernel_r<FT, true, MAXREG, NPAIR, PERSIST>, fte_eval_kernel_r<FT, false, MAXREG, NPAIR, PERSIST>,
-                                          CTAS, scene, n_frames, x, meas, w, cost, g, H, stream);
+                                          CTAS, scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, smem_pad);
 }
+#endif
 
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
                             const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    if (g_variant < 0) {
-        const char* e = getenv("ACINO_FTE_VARIANT");
-        g_variant = e ? atoi(e) : 0;
-    }
-    // Default: 8 frames per CTA, 4 CTAs per SM (96 registers, no spills), runtime camera-pair loop.
-    // A/B variants kept for scripts/bench_variants.sh (B200, 256 000 frames, profiles/r01_fte_eval.md):
+#ifdef ACINO_EXPERIMENTS
+    // A/B variants of scripts/bench_variants.sh (B200, 256 000 frames, profiles/r01_fte_eval.md); build with
+    // -DACINO_EXPERIMENTS to get the ACINO_FTE_VARIANT / ACINO_FTE_EXP / ACINO_FTE_SMEM_PAD switches:
     //   0 default 6.45e8 frames/s | 1: 5 CTAs/SM, 72 regs 6.2e8 | 4: 16 frames/CTA 4.8e8 | 5/6: 4 frames/CTA 5.7e8 / 5.4e8
-    //   8: camera-pair loop unrolled 6.4e8 | 9: unrolled, 3 CTAs/SM, 128 regs 5.6e8
-    if (g_variant == 1) return launch_fte_eval_v<8, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 4) return launch_fte_eval_v<16, 2, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 5) return launch_fte_eval_v<4, 9, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 6) return launch_fte_eval_v<4, 10, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 10) return launch_fte_eval_v<8, 4, 0, true>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 11) return launch_fte_eval_r<8, 80, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
-    if (g_variant == 12) return launch_fte_eval_r<8, 88, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    //   8: camera-pair loop unrolled 6.4e8 | 9: unrolled, 3 CTAs/SM, 128 regs 5.6e8 | 10: persistent 5.9e8
+    static int variant = -1, exp_bits = 0;
+    static size_t pad = 0;
+    if (variant < 0) {
+        const char* e = getenv("ACINO_FTE_VARIANT");
+        variant = e ? atoi(e) : 0;
+        e = getenv("ACINO_FTE_EXP");
+        exp_bits = e ? atoi(e) : 0;
+        e = getenv("ACINO_FTE_SMEM_PAD");
+        pad = e ? (size_t)atol(e) : 0;
+    }
+    if (variant == 1) return launch_fte_eval_v<8, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 4) return launch_fte_eval_v<16, 2, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 5) return launch_fte_eval_v<4, 9, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 6) return launch_fte_eval_v<4, 10, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 10) return launch_fte_eval_v<8, 4, 0, true>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 11) return launch_fte_eval_r<8, 80, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 12) return launch_fte_eval_r<8, 88, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+#else
+    // 8 frames per CTA, 4 CTAs per SM (96 registers, no spills), runtime camera-pair loop
     return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+#endif
 }
 
 const char* fte_eval_kernel_name(int) { return "fte_eval_kernel<8, 1, 4, 0, 0>"; }

@@ -11,6 +11,7 @@
 // reductions (warp shuffles in fixed order -> per-CTA partials -> fixed-order final sum).
 // Parameter layout = the reference's: [rvec_0..rvec_{C-1} | t_0..t_{C-1} | X_0..X_{n-1}].
 #include "acino_common.cuh"
+#include "stereo_body.cuh"
 
 namespace acino {
 
@@ -18,12 +19,21 @@ struct SbaCam {           // per camera, refreshed from the parameter vector eac
     double R[9];
     double dR[27];        // dR[i][j][k] = d R_ij / d rvec_k  at [ (i*3+j)*3 + k ]
     double t[3];
-    double fx, fy, cx, cy, D[4];
+    // intrinsics + distortion: model 0 = Kannala-Brandt fisheye (k1..k4, cv2.fisheye.projectPoints, calib.py:132-136),
+    // model 1 = OpenCV's standard model, up to 12 coefficients (cv2.projectPoints, calib.py:64-66)
+    StereoCam in;
 };
 
+__device__ __forceinline__ void sba_set_intrinsics(SbaCam& cam, const int c, const int model, const int nd,
+                                                   const double* __restrict__ K, const double* __restrict__ Dd) {
+    cam.in.fx = K[9 * c]; cam.in.fy = K[9 * c + 4]; cam.in.cx = K[9 * c + 2]; cam.in.cy = K[9 * c + 5];
+    for (int i = 0; i < 12; ++i) cam.in.D[i] = i < nd ? Dd[nd * c + i] : 0.0;
+    cam.in.model = model;
+}
+
 // Rodrigues rotation and its derivative (closed form; generators at theta -> 0), thread per camera
-__global__ void sba_cams_kernel(const int C, const double* __restrict__ params, const double* __restrict__ K,
-                                const double* __restrict__ Dd, SbaCam* __restrict__ cams) {
+__global__ void sba_cams_kernel(const int C, const int model, const int nd, const double* __restrict__ params,
+                                const double* __restrict__ K, const double* __restrict__ Dd, SbaCam* __restrict__ cams) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double r[3] = {params[3 * c], params[3 * c + 1], params[3 * c + 2]};
@@ -62,22 +72,21 @@ __global__ void sba_cams_kernel(const int C, const double* __restrict__ params, 
     }
     for (int i = 0; i < 9; ++i) cam.R[i] = Rm[i];
     for (int i = 0; i < 3; ++i) cam.t[i] = params[3 * C + 3 * c + i];
-    cam.fx = K[9 * c]; cam.fy = K[9 * c + 4]; cam.cx = K[9 * c + 2]; cam.cy = K[9 * c + 5];
-    for (int i = 0; i < 4; ++i) cam.D[i] = Dd[4 * c + i];
+    sba_set_intrinsics(cam, c, model, nd, K, Dd);
     cams[c] = cam;
 }
 
 // cameras given as fixed matrices (points-only mode): R, t straight from the scene
-__global__ void sba_cams_fixed_kernel(const int C, const double* __restrict__ R, const double* __restrict__ t,
-                                      const double* __restrict__ K, const double* __restrict__ Dd, SbaCam* __restrict__ cams) {
+__global__ void sba_cams_fixed_kernel(const int C, const int model, const int nd, const double* __restrict__ R,
+                                      const double* __restrict__ t, const double* __restrict__ K,
+                                      const double* __restrict__ Dd, SbaCam* __restrict__ cams) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     SbaCam cam;
     for (int i = 0; i < 9; ++i) cam.R[i] = R[9 * c + i];
     for (int i = 0; i < 27; ++i) cam.dR[i] = 0.0;
     for (int i = 0; i < 3; ++i) cam.t[i] = t[3 * c + i];
-    cam.fx = K[9 * c]; cam.fy = K[9 * c + 4]; cam.cx = K[9 * c + 2]; cam.cy = K[9 * c + 5];
-    for (int i = 0; i < 4; ++i) cam.D[i] = Dd[4 * c + i];
+    sba_set_intrinsics(cam, c, model, nd, K, Dd);
     cams[c] = cam;
 }
 
@@ -115,8 +124,24 @@ sba_eval_kernel(const int n_obs, const int bulk_ok, const SbaCam* __restrict__ c
         const double yc = cam.R[3] * x + cam.R[4] * y + cam.R[5] * z + cam.t[1];
         const double zc = cam.R[6] * x + cam.R[7] * y + cam.R[8] * z + cam.t[2];
         ProjOut<double> pr;
-        fisheye_cam<double, WANT_J>(xc, yc, zc, cam.fx, cam.fy, cam.D[0], cam.D[1], cam.D[2], cam.D[3], pr);
-        const double ru = pr.u + cam.cx - (double)uv[2 * i], rv = pr.v + cam.cy - (double)uv[2 * i + 1];
+        double ru, rv;
+        if (cam.in.model == 1) {
+            const double Xc[3] = {xc, yc, zc};
+            double p2[2], J6[6];
+            st_project_pinhole(cam.in, Xc, p2, WANT_J ? J6 : nullptr);
+            ru = p2[0] - (double)uv[2 * i];
+            rv = p2[1] - (double)uv[2 * i + 1];
+            if (WANT_J) {
+                for (int k = 0; k < 3; ++k) {
+                    pr.ju[k] = J6[k];
+                    pr.jv[k] = J6[3 + k];
+                }
+            }
+        } else {
+            fisheye_cam<double, WANT_J>(xc, yc, zc, cam.in.fx, cam.in.fy, cam.in.D[0], cam.in.D[1], cam.in.D[2], cam.in.D[3], pr);
+            ru = pr.u + cam.in.cx - (double)uv[2 * i];
+            rv = pr.v + cam.in.cy - (double)uv[2 * i + 1];
+        }
         double* o_res = staged ? S.res + 2 * tid : res + 2 * (size_t)i;
         o_res[0] = ru;
         o_res[1] = rv;
@@ -423,10 +448,10 @@ __global__ void sba_pred_kernel(const int n_obs, const int* __restrict__ cam_idx
 // ---- launchers --------------------------------------------------------------------------------
 static inline int nb(int n, int b) { return (n + b - 1) / b; }
 
-cudaError_t launch_sba_cams(int C, const double* params, const double* R, const double* t, const double* K,
-                            const double* D, void* cams, cudaStream_t s) {
-    if (params) sba_cams_kernel<<<1, 32, 0, s>>>(C, params, K, D, (SbaCam*)cams);
-    else sba_cams_fixed_kernel<<<1, 32, 0, s>>>(C, R, t, K, D, (SbaCam*)cams);
+cudaError_t launch_sba_cams(int C, int model, int n_dist, const double* params, const double* R, const double* t,
+                            const double* K, const double* D, void* cams, cudaStream_t s) {
+    if (params) sba_cams_kernel<<<1, 32, 0, s>>>(C, model, n_dist, params, K, D, (SbaCam*)cams);
+    else sba_cams_fixed_kernel<<<1, 32, 0, s>>>(C, model, n_dist, R, t, K, D, (SbaCam*)cams);
     return cudaGetLastError();
 }
 size_t sba_cam_bytes() { return sizeof(SbaCam); }

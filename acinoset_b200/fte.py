@@ -188,7 +188,8 @@ def save_3d_cheetah_as_2d(positions_3d_arr, out_dir, scene_fpath, bodyparts, pro
     (``app.save_3d_cheetah_as_2d(positions, OUT_DIR, scene_fpath, markers, project_points_fisheye,
     start_frame)``; the callee lives in the reference's missing ``lib`` package, so the file format is the
     DLC layout its own loader reads back, utils.py:105-120: columns (scorer, bodyparts, x|y|likelihood),
-    index = frame number).  All N x L points of a camera are projected by ONE kernel launch.
+    index = frame number).  All N x L points of a camera are projected by ONE kernel launch.  Markers whose 3-D
+    position is not finite are written as NaN pixels with likelihood 0.
     Returns the list of per-camera DataFrames; files ``cam{i+1}_{out_fname}.h5`` (and ``.csv``)."""
     import os
 
@@ -208,7 +209,11 @@ def save_3d_cheetah_as_2d(positions_3d_arr, out_dir, scene_fpath, bodyparts, pro
     dfs = []
     for i in range(len(k_arr)):
         uv = np.asarray(project(P.reshape(-1, 3), k_arr[i], d_arr[i], r_arr[i], t_arr[i])).reshape(N, L, 2)
-        data = np.concatenate([uv, np.ones((N, L, 1))], axis=2).reshape(N, L * 3)
+        # a marker without a 3-D estimate (NaN from TRI / SBA) has no reprojection: NaN pixels, likelihood 0 - never a
+        # fabricated high-confidence detection at the projection of the world origin
+        seen = np.isfinite(P).all(axis=2) & np.isfinite(uv).all(axis=2)
+        uv = np.where(seen[..., None], uv, np.nan)
+        data = np.concatenate([uv, seen[..., None].astype(np.float64)], axis=2).reshape(N, L * 3)
         df = pd.DataFrame(data, columns=cols, index=index)
         fpath = os.path.join(out_dir, f"cam{i + 1}_{out_fname}")
         try:

@@ -31,20 +31,24 @@ from .rotations import rodrigues_to_mat, rodrigues_to_vec  # noqa: E402,F401
 # ---- problem assembly (host) -----------------------------------------------------------------------
 def create_bundle_adjustment_jacobian_sparsity_matrix(n_cameras, n_params_per_camera, camera_indices, n_points,
                                                       point_indices):
-    """calib.py:196-207, reproduced as is (including its camera-major column layout)."""
-    from scipy.sparse import lil_matrix
+    """Sparsity pattern with the reference's shape and column layout (calib.py:196-207): rows 2i, 2i+1 of observation i
+    touch the ``n_params_per_camera`` columns of a CAMERA-MAJOR block ``camera * n_params_per_camera + s`` and the three
+    columns of its point.  (The reference's parameter vector is [all rvecs | all tvecs | points], calib.py:346-351, so
+    for the extrinsics problem this pattern does not line up with it; kept for callers that pass it on - the solves
+    here use the analytic Jacobian, ``jac_points_extrinsics``.)  Built in one shot as a COO matrix."""
+    from scipy.sparse import coo_matrix
 
-    m = camera_indices.size * 2
-    n = n_cameras * n_params_per_camera + n_points * 3
-    A = lil_matrix((m, n), dtype=int)
-    i = np.arange(camera_indices.size)
-    for s in range(n_params_per_camera):
-        A[2 * i, camera_indices * n_params_per_camera + s] = 1
-        A[2 * i + 1, camera_indices * n_params_per_camera + s] = 1
-    for s in range(3):
-        A[2 * i, n_cameras * n_params_per_camera + point_indices * 3 + s] = 1
-        A[2 * i + 1, n_cameras * n_params_per_camera + point_indices * 3 + s] = 1
-    return A
+    cam = np.asarray(camera_indices, dtype=np.int64).ravel()
+    pt = np.asarray(point_indices, dtype=np.int64).ravel()
+    n_obs, npc = cam.size, int(n_params_per_camera)
+    cols = np.concatenate([cam[:, None] * npc + np.arange(npc)[None, :],
+                           n_cameras * npc + pt[:, None] * 3 + np.arange(3)[None, :]], axis=1)        # (n_obs, npc + 3)
+    rows = 2 * np.arange(n_obs)[:, None, None] + np.arange(2)[None, :, None]                               # (n_obs, 2, 1)
+    rows = np.broadcast_to(rows, (n_obs, 2, npc + 3))
+    cols = np.broadcast_to(cols[:, None, :], (n_obs, 2, npc + 3))
+    A = coo_matrix((np.ones(rows.size, dtype=int), (rows.ravel(), cols.ravel())),
+                   shape=(2 * n_obs, n_cameras * npc + n_points * 3))
+    return A.tolil()
 
 
 def prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr, r_arr, t_arr,

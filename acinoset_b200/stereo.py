@@ -64,12 +64,11 @@ def _median_relative_pose(poses):
     return rodrigues_to_mat(np.median(np.array(rv), axis=0)), np.median(np.array(tv), axis=0)
 
 
-def solve_pair(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, max_iter=100, eps=1e-10, backend=None, device=0,
+def solve_pair(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, max_iter=100, eps=1e-10, device=0,
                return_info=False, pinhole=False):
     """-> (rms, R (3,3), T (3,1)) [, info].  img_pts_* (V, M, 2) pixels of the same V views, obj_pts (M, 3).
     pinhole=True: d_* are OpenCV's standard-model coefficients (up to 12) instead of the 4 fisheye ones.
-    ``backend`` is a test hook (tests/host_harness runs the kernel source on the host to check it without a GPU); the
-    library itself has no CPU path: with the default backend a missing GPU raises AcinoError."""
+    There is no CPU path: a missing GPU raises AcinoError."""
     obj = np.ascontiguousarray(obj_pts, dtype=np.float64).reshape(-1, 3)
     M = obj.shape[0]
     img1 = np.ascontiguousarray(img_pts_1, dtype=np.float64).reshape(-1, M, 2)
@@ -80,7 +79,7 @@ def solve_pair(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, max_iter=100, 
     K1, K2 = (np.ascontiguousarray(k, dtype=np.float64).reshape(3, 3) for k in (k_1, k_2))
     nd = 14 if pinhole else 4
     D1, D2 = (np.ascontiguousarray(np.zeros(0) if d is None else np.asarray(d, dtype=np.float64).reshape(-1)[:nd]) for d in (d_1, d_2))
-    be = _GpuBackend(device) if backend is None else backend
+    be = _GpuBackend(device)
     be.set(obj, img1, img2, K1, D1, K2, D2, pinhole=pinhole)
     poses2, cost0 = be.init()
     if np.any(cost0 < 0):
@@ -119,7 +118,7 @@ def calibrate_pair_extrinsics_fisheye(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k
 
 
 def calibrate_pair_extrinsics(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2, camera_resolution=None, device=0,
-                              rational_model=False, backend=None):
+                              rational_model=False):
     """calib.py:41-49 (cv2.stereoCalibrate, flags = CALIB_FIX_INTRINSIC only): the standard-camera-model twin.
 
     Reference behaviour kept by default: without CALIB_RATIONAL_MODEL / CALIB_THIN_PRISM_MODEL in the flags OpenCV drops
@@ -133,7 +132,7 @@ def calibrate_pair_extrinsics(obj_pts, img_pts_1, img_pts_2, k_1, d_1, k_2, d_2,
         return d if rational_model else d[:5]
 
     return solve_pair(obj_pts, np.asarray(img_pts_1).reshape(n, -1, 2), np.asarray(img_pts_2).reshape(n, -1, 2), k_1, coeffs(d_1),
-                      k_2, coeffs(d_2), device=device, pinhole=True, backend=backend)
+                      k_2, coeffs(d_2), device=device, pinhole=True)
 
 
 def calibrate_pairwise_extrinsics(calib_func, img_pts_arr, fnames_arr, k_arr, d_arr, camera_resolution, board_shape,

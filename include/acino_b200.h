@@ -345,6 +345,12 @@ int64_t acino_sba_cam_bytes(void);                 /* size of one opaque device 
 int acino_sba_cams_dev(acino_handle* h, int n_cams, const double* params, const double* R,
                        const double* t, const double* K, const double* D, void* cams,
                        void* cuda_stream);
+/* Same with an explicit camera model: 0 = fisheye (n_dist = 4), 1 = OpenCV's standard model with n_dist <= 12 coefficients
+ * [k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4] per camera (cv2.projectPoints, calib.py:64-66: what app.sba_board_points passes,
+ * app.py:215-218).  D is [n_cams][n_dist]. */
+int acino_sba_cams_model_dev(acino_handle* h, int n_cams, int model, int n_dist, const double* params,
+                             const double* R, const double* t, const double* K, const double* D, void* cams,
+                             void* cuda_stream);
 /* Jp == NULL: residuals (+ cost) only; Jc == NULL: points-only problem */
 int acino_sba_eval_dev(acino_handle* h, int n_obs, const void* cams, const double* pts,
                        const float* uv, const int32_t* cam_idx, const int32_t* pt_idx, double f_scale,

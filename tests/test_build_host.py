@@ -110,3 +110,24 @@ def test_reference_module_names_are_importable():
     import numpy as np
 
     assert np.allclose(misc.rot_x(0.3) @ misc.rot_x(0.3).T, np.eye(3))
+
+
+def test_sparsity_matrix_matches_reference_golden():
+    """create_bundle_adjustment_jacobian_sparsity_matrix against the pattern the reference's own function produced
+    (tests/golden/sba.npz A_rows / A_cols, calib.py:196-207), for the extrinsics and the points-only layout."""
+    from conftest import golden
+    from oracle import sba as osba
+    from acinoset_b200 import sba
+
+    g = golden("sba.npz")
+    for tag in ("static", "rotating"):
+        n_pts = len(g[f"{tag}_points_3d"])
+        A = sba.create_bundle_adjustment_jacobian_sparsity_matrix(2, 6, g[f"{tag}_cidx"], n_pts, g[f"{tag}_pidx"])
+        assert A.shape == tuple(g[f"{tag}_A_shape"]) and A.dtype == int
+        r, c = A.tocoo().row, A.tocoo().col
+        o = np.lexsort((c, r))
+        o2 = np.lexsort((g[f"{tag}_A_cols"], g[f"{tag}_A_rows"]))
+        assert np.array_equal(r[o], g[f"{tag}_A_rows"][o2]) and np.array_equal(c[o], g[f"{tag}_A_cols"][o2])
+        assert A.tocsr().max() == 1
+        A0 = sba.create_bundle_adjustment_jacobian_sparsity_matrix(2, 0, g[f"{tag}_cidx"], n_pts, g[f"{tag}_pidx"])
+        assert np.array_equal(A0.toarray(), osba.sparsity(2, 0, g[f"{tag}_cidx"], n_pts, g[f"{tag}_pidx"]))

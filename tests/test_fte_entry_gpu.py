@@ -111,6 +111,17 @@ def test_pipeline_tri_sba_ekf_by_reference_names(tmp_path, dummy_cams):
     with open(data / "tri" / "tri.pickle", "rb") as f:
         saved = pickle.load(f)
     assert np.array_equal(np.isnan(saved["positions"]), np.isnan(pos)) and saved["start_frame"] == 0
+    # 2-D reprojection files: a marker TRI could not triangulate is NaN with likelihood 0, never a confident detection
+    # at the projection of the world origin; every other marker has likelihood 1
+    import pandas as pd
+
+    assert (~seen).any()
+    for c in range(6):
+        df = pd.read_csv(data / "tri" / f"cam{c + 1}_tri.csv", header=[0, 1, 2], index_col=0)
+        lk = df.xs("likelihood", axis=1, level=2).to_numpy()
+        xs = df.xs("x", axis=1, level=2).to_numpy()
+        assert np.array_equal(lk == 1.0, np.isfinite(xs)) and np.all((lk == 0.0) | (lk == 1.0))
+        assert np.all(lk[~seen] == 0.0) and np.all(np.isnan(xs[~seen]))
     pos_sba, residuals = ao.sba(str(data), 1, -1, 0.5)
     assert pos_sba.shape == (n, 20, 3) and set(residuals) == {"before", "after"}
     err_sba = np.linalg.norm(pos_sba[seen] - P[seen], axis=-1)
