@@ -15,11 +15,11 @@ $(LIB): $(SRCS) $(HDRS)
 ptxas-info: $(SRCS) $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -shared -o /tmp/libacino_b200_ptxas.so $(SRCS)
 
-# A/B build for scripts/bench_{variants,exp,residency,e2e_chunks}.sh: the ACINO_FTE_VARIANT / ACINO_FTE_EXP /
+# A/B build for scripts/ab_env.sh / bench_e2e_chunks.sh: the ACINO_FTE_VARIANT / ACINO_FTE_CTAS /
 # ACINO_FTE_SMEM_PAD / ACINO_E2E_CHUNK environment switches exist only in this build (the product library has none).
 experiments: $(SRCS) $(HDRS)
 	mkdir -p scratch
-	$(NVCC) $(NVCCFLAGS) -DACINO_EXPERIMENTS -shared -o scratch/libacino_b200_experiments.so $(SRCS)
+	$(NVCC) $(NVCCFLAGS) -DACINO_EXPERIMENTS -DACINO_MAXC_STAGE=6 -shared -o scratch/libacino_b200_experiments.so $(SRCS)
 
 oracle:
 	$(MAKE) -C oracle

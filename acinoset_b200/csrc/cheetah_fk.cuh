@@ -36,27 +36,36 @@ __device__ __forceinline__ Col3 operator-(Col3 a, Col3 b) { return {a.x - b.x, a
 __device__ __forceinline__ Col3 fma3(float s, Col3 a, Col3 b) {
     return {fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)};
 }
+__device__ __forceinline__ float fma3(float s, float a, float b) { return fmaf(s, a, b); }
 __device__ __forceinline__ Col3 cross(Col3 a, Col3 b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-struct Mat3 {  // body->world rotation R_k_I stored by columns
-    Col3 c0, c1, c2;
+// Body->world rotation R_k_I stored by columns.  V = Col3: the whole matrix in one thread.  V = float: ONE ROW of it
+// (c0, c1, c2 are then the three entries of row i) - right-multiplication by an elementary rotation mixes two columns,
+// so the three rows of the chain are independent and three threads can each carry one row of the same frame.
+template <typename V>
+struct Mat3T {
+    V c0, c1, c2;
 };
+using Mat3 = Mat3T<Col3>;
 // M <- M * Ry_a(th):  (c0,c2) <- (c c0 - s c2, s c0 + c c2)       [rot_y transposed, :75-82]
-__device__ __forceinline__ void rot_y(Mat3& M, float s, float c) {
-    const Col3 a = M.c0, b = M.c2;
+template <typename V>
+__device__ __forceinline__ void rot_y(Mat3T<V>& M, float s, float c) {
+    const V a = M.c0, b = M.c2;
     M.c0 = fma3(c, a, (-s) * b);
     M.c2 = fma3(s, a, c * b);
 }
 // M <- M * Rx_a(ph):  (c1,c2) <- (c c1 + s c2, -s c1 + c c2)      [rot_x transposed, :66-73]
-__device__ __forceinline__ void rot_x(Mat3& M, float s, float c) {
-    const Col3 a = M.c1, b = M.c2;
+template <typename V>
+__device__ __forceinline__ void rot_x(Mat3T<V>& M, float s, float c) {
+    const V a = M.c1, b = M.c2;
     M.c1 = fma3(c, a, s * b);
     M.c2 = fma3(-s, a, c * b);
 }
 // M <- M * Rz_a(ps):  (c0,c1) <- (c c0 + s c1, -s c0 + c c1)      [rot_z transposed, :84-91]
-__device__ __forceinline__ void rot_z(Mat3& M, float s, float c) {
-    const Col3 a = M.c0, b = M.c1;
+template <typename V>
+__device__ __forceinline__ void rot_z(Mat3T<V>& M, float s, float c) {
+    const V a = M.c0, b = M.c1;
     M.c0 = fma3(c, a, s * b);
     M.c1 = fma3(-s, a, c * b);
 }
@@ -83,15 +92,37 @@ struct FkWriter {
     }
 };
 
+// Row writer (V = float): thread i of a frame stores component i of every marker and of every rotation axis.  The
+// linear part v = pivot x omega of a twist needs all three components, so it is formed later from the stored values
+// (every pivot is a marker position: k_angle_pivot).
+struct FkRowWriter {
+    float* p;    // [NL][3] + i
+    float* tau;  // [NANG][TAU_STRIDE] + i
+    __device__ __forceinline__ void marker(int l, float v) const { p[l * 3] = v; }
+    __device__ __forceinline__ void twist(int s, float om, float) const { tau[s * TAU_STRIDE] = om; }
+    __device__ __forceinline__ void twist0(int s, float om) const { tau[s * TAU_STRIDE] = om; }
+};
+
 // angle slot ids
 enum { A_PHI0 = 0, A_PHI1 = 1, A_PHI3 = 2, A_TH0 = 3, A_PSI0 = 17, A_PSI1 = 18, A_PSI3 = 19, A_PSI4 = 20, A_PSI5 = 21 };
+
+// marker whose position is the pivot of each angle slot's rotation (-1: the head point, v = 0); matches the
+// w.twist(...) calls of cheetah_fk_t below
+constexpr int k_angle_pivot[NANG] = {-1, -1, 4,                                      // phi0 phi1 phi3
+                                     -1, -1, 3, 4, 5, 6, 8, 9, 11, 12, 14, 15, 17, 18,  // theta0..13
+                                     -1, -1, 4, 5, 6};                               // psi0 psi1 psi3 psi4 psi5
 
 // Cheetah forward kinematics of one frame: marker positions relative to the head point and the
 // world-frame twist of every angle.  Follows the chain RI_0..RI_13 (:101-128) and p_* (:138-165);
 // R_k_I = R_parent_I Ry_a(theta) Rx_a(phi) Rz_a(psi), and the world axis of each angle is the
 // matching column of the partially composed matrix (theta: column 1 before Ry; phi: column 0
-// after Ry; psi: column 2 after Rx).
-__device__ __forceinline__ void cheetah_fk(const float2* __restrict__ sc, const FkWriter& w) {
+// after Ry; psi: column 2 after Rx).  `M` enters as the identity (V = Col3) or as row i of it (V = float).
+// SEG selects which outputs are written (the arithmetic nothing written depends on is eliminated by the compiler):
+// bit 0 head / neck / torso / tail (markers 0..7 and their angles), bit 1 front legs (markers 8..13, theta6..9), bit 2 back
+// legs (markers 14..19, theta10..13) - three warps can each run one segment of the same frames.
+template <typename V, int SEG, typename W>
+__device__ __forceinline__ void cheetah_fk_t(const float2* __restrict__ sc, Mat3T<V> M, const W& w) {
+    constexpr bool S0 = SEG & 1, S1 = SEG & 2, S2 = SEG & 4;
     float sn[NANG], cs[NANG];
 #pragma unroll
     for (int i = 0; i < NANG; ++i) {
@@ -100,104 +131,113 @@ __device__ __forceinline__ void cheetah_fk(const float2* __restrict__ sc, const 
         cs[i] = v.y;
     }
 #define TH(k) sn[A_TH0 + (k)], cs[A_TH0 + (k)]
-    const Col3 zero = {0.f, 0.f, 0.f};
     // joint 0: head
-    Mat3 M = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
-    w.twist0(A_TH0 + 0, M.c1);
+    if (S0) w.twist0(A_TH0 + 0, M.c1);
     rot_y(M, TH(0));
-    w.twist0(A_PHI0, M.c0);
+    if (S0) w.twist0(A_PHI0, M.c0);
     rot_x(M, sn[A_PHI0], cs[A_PHI0]);
-    w.twist0(A_PSI0, M.c2);
+    if (S0) w.twist0(A_PSI0, M.c2);
     rot_z(M, sn[A_PSI0], cs[A_PSI0]);
-    w.marker(0, 0.03f * M.c1);                          // l_eye
-    w.marker(1, -0.03f * M.c1);                         // r_eye
-    w.marker(2, 0.055f * (M.c0 - M.c2));                // nose
+    if (S0) w.marker(0, 0.03f * M.c1);                          // l_eye
+    if (S0) w.marker(1, -0.03f * M.c1);                         // r_eye
+    if (S0) w.marker(2, 0.055f * (M.c0 - M.c2));                // nose
     // joint 1: neck
-    w.twist0(A_TH0 + 1, M.c1);
+    if (S0) w.twist0(A_TH0 + 1, M.c1);
     rot_y(M, TH(1));
-    w.twist0(A_PHI1, M.c0);
+    if (S0) w.twist0(A_PHI1, M.c0);
     rot_x(M, sn[A_PHI1], cs[A_PHI1]);
-    w.twist0(A_PSI1, M.c2);
+    if (S0) w.twist0(A_PSI1, M.c2);
     rot_z(M, sn[A_PSI1], cs[A_PSI1]);
-    const Col3 neck = -0.28f * M.c0;
-    w.marker(3, neck);
+    const V neck = -0.28f * M.c0;
+    if (S0) w.marker(3, neck);
     // joint 2: front torso (pivot neck_base)
-    w.twist(A_TH0 + 2, M.c1, neck);
+    if (S0) w.twist(A_TH0 + 2, M.c1, neck);
     rot_y(M, TH(2));
-    const Mat3 M2 = M;
-    const Col3 spine = fma3(-0.37f, M2.c0, neck);
-    w.marker(4, spine);
-    const Col3 sh_mid = fma3(-0.04f, M2.c0, fma3(-0.10f, M2.c2, neck));
-    const Col3 lsh = fma3(0.08f, M2.c1, sh_mid);
-    const Col3 rsh = fma3(-0.08f, M2.c1, sh_mid);
-    w.marker(8, lsh);
-    w.marker(11, rsh);
+    const Mat3T<V> M2 = M;
+    const V spine = fma3(-0.37f, M2.c0, neck);
+    if (S0) w.marker(4, spine);
+    const V sh_mid = fma3(-0.04f, M2.c0, fma3(-0.10f, M2.c2, neck));
+    const V lsh = fma3(0.08f, M2.c1, sh_mid);
+    const V rsh = fma3(-0.08f, M2.c1, sh_mid);
+    if (S1) w.marker(8, lsh);
+    if (S1) w.marker(11, rsh);
     // joints 6,7: left front leg; 8,9: right front leg (axis = column 1 of M2 throughout)
     {
-        Mat3 Ml = M2;
-        w.twist(A_TH0 + 6, M2.c1, lsh);
+        Mat3T<V> Ml = M2;
+        if (S1) w.twist(A_TH0 + 6, M2.c1, lsh);
         rot_y(Ml, TH(6));
-        const Col3 knee = fma3(-0.24f, Ml.c2, lsh);
-        w.marker(9, knee);
-        w.twist(A_TH0 + 7, M2.c1, knee);
+        const V knee = fma3(-0.24f, Ml.c2, lsh);
+        if (S1) w.marker(9, knee);
+        if (S1) w.twist(A_TH0 + 7, M2.c1, knee);
         rot_y(Ml, TH(7));
-        w.marker(10, fma3(-0.28f, Ml.c2, knee));
-        Mat3 Mr = M2;
-        w.twist(A_TH0 + 8, M2.c1, rsh);
+        if (S1) w.marker(10, fma3(-0.28f, Ml.c2, knee));
+        Mat3T<V> Mr = M2;
+        if (S1) w.twist(A_TH0 + 8, M2.c1, rsh);
         rot_y(Mr, TH(8));
-        const Col3 kneer = fma3(-0.24f, Mr.c2, rsh);
-        w.marker(12, kneer);
-        w.twist(A_TH0 + 9, M2.c1, kneer);
+        const V kneer = fma3(-0.24f, Mr.c2, rsh);
+        if (S1) w.marker(12, kneer);
+        if (S1) w.twist(A_TH0 + 9, M2.c1, kneer);
         rot_y(Mr, TH(9));
-        w.marker(13, fma3(-0.28f, Mr.c2, kneer));
+        if (S1) w.marker(13, fma3(-0.28f, Mr.c2, kneer));
     }
     // joint 3: back torso (pivot spine)
-    w.twist(A_TH0 + 3, M.c1, spine);
+    if (S0) w.twist(A_TH0 + 3, M.c1, spine);
     rot_y(M, TH(3));
-    w.twist(A_PHI3, M.c0, spine);
+    if (S0) w.twist(A_PHI3, M.c0, spine);
     rot_x(M, sn[A_PHI3], cs[A_PHI3]);
-    w.twist(A_PSI3, M.c2, spine);
+    if (S0) w.twist(A_PSI3, M.c2, spine);
     rot_z(M, sn[A_PSI3], cs[A_PSI3]);
-    const Mat3 M3 = M;
-    const Col3 tailb = fma3(-0.37f, M3.c0, spine);
-    w.marker(5, tailb);
-    const Col3 hip_mid = fma3(0.12f, M3.c0, fma3(-0.06f, M3.c2, tailb));
-    const Col3 lhip = fma3(0.08f, M3.c1, hip_mid);
-    const Col3 rhip = fma3(-0.08f, M3.c1, hip_mid);
-    w.marker(14, lhip);
-    w.marker(17, rhip);
+    const Mat3T<V> M3 = M;
+    const V tailb = fma3(-0.37f, M3.c0, spine);
+    if (S0) w.marker(5, tailb);
+    const V hip_mid = fma3(0.12f, M3.c0, fma3(-0.06f, M3.c2, tailb));
+    const V lhip = fma3(0.08f, M3.c1, hip_mid);
+    const V rhip = fma3(-0.08f, M3.c1, hip_mid);
+    if (S2) w.marker(14, lhip);
+    if (S2) w.marker(17, rhip);
     {
-        Mat3 Ml = M3;
-        w.twist(A_TH0 + 10, M3.c1, lhip);
+        Mat3T<V> Ml = M3;
+        if (S2) w.twist(A_TH0 + 10, M3.c1, lhip);
         rot_y(Ml, TH(10));
-        const Col3 knee = fma3(-0.32f, Ml.c2, lhip);
-        w.marker(15, knee);
-        w.twist(A_TH0 + 11, M3.c1, knee);
+        const V knee = fma3(-0.32f, Ml.c2, lhip);
+        if (S2) w.marker(15, knee);
+        if (S2) w.twist(A_TH0 + 11, M3.c1, knee);
         rot_y(Ml, TH(11));
-        w.marker(16, fma3(-0.25f, Ml.c2, knee));
-        Mat3 Mr = M3;
-        w.twist(A_TH0 + 12, M3.c1, rhip);
+        if (S2) w.marker(16, fma3(-0.25f, Ml.c2, knee));
+        Mat3T<V> Mr = M3;
+        if (S2) w.twist(A_TH0 + 12, M3.c1, rhip);
         rot_y(Mr, TH(12));
-        const Col3 kneer = fma3(-0.32f, Mr.c2, rhip);
-        w.marker(18, kneer);
-        w.twist(A_TH0 + 13, M3.c1, kneer);
+        const V kneer = fma3(-0.32f, Mr.c2, rhip);
+        if (S2) w.marker(18, kneer);
+        if (S2) w.twist(A_TH0 + 13, M3.c1, kneer);
         rot_y(Mr, TH(13));
-        w.marker(19, fma3(-0.25f, Mr.c2, kneer));
+        if (S2) w.marker(19, fma3(-0.25f, Mr.c2, kneer));
     }
     // joint 4: tail base (pivot tail_base), joint 5: tail mid (pivot tail1)
-    w.twist(A_TH0 + 4, M.c1, tailb);
+    if (S0) w.twist(A_TH0 + 4, M.c1, tailb);
     rot_y(M, TH(4));
-    w.twist(A_PSI4, M.c2, tailb);
+    if (S0) w.twist(A_PSI4, M.c2, tailb);
     rot_z(M, sn[A_PSI4], cs[A_PSI4]);
-    const Col3 tail1 = fma3(-0.28f, M.c0, tailb);
-    w.marker(6, tail1);
-    w.twist(A_TH0 + 5, M.c1, tail1);
+    const V tail1 = fma3(-0.28f, M.c0, tailb);
+    if (S0) w.marker(6, tail1);
+    if (S0) w.twist(A_TH0 + 5, M.c1, tail1);
     rot_y(M, TH(5));
-    w.twist(A_PSI5, M.c2, tail1);
+    if (S0) w.twist(A_PSI5, M.c2, tail1);
     rot_z(M, sn[A_PSI5], cs[A_PSI5]);
-    w.marker(7, fma3(-0.36f, M.c0, tail1));
-    (void)zero;
+    if (S0) w.marker(7, fma3(-0.36f, M.c0, tail1));
 #undef TH
+}
+
+// one thread per frame (fk_project, fte_jac)
+__device__ __forceinline__ void cheetah_fk(const float2* __restrict__ sc, const FkWriter& w) {
+    const Mat3 I = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    cheetah_fk_t<Col3, 7>(sc, I, w);
+}
+// thread i of a frame carries row i of the chain (fte_eval): writes component i of the markers and rotation axes
+template <int SEG>
+__device__ __forceinline__ void cheetah_fk_row(const float2* __restrict__ sc, const int i, float* p, float* tau) {
+    const Mat3T<float> I = {i == 0 ? 1.f : 0.f, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f};
+    cheetah_fk_t<float, SEG>(sc, I, FkRowWriter{p + i, tau + i});
 }
 
 }  // namespace acino

@@ -32,85 +32,179 @@
 
 namespace acino {
 
-constexpr int PREFETCH_DIST = 148 * 4;   // tiles one resident wave ahead (experiment, ACINO_FTE_EXP bit 0)
 constexpr int N_PAIR = NANG * (NANG + 1) / 2;  // 253 unordered angle pairs (incl. the diagonal)
 
-// One entry per unordered pair of angle slots.  Related pairs (one joint is an ancestor-or-self of
-// the other): H = tau_al . y_be with `be` the deeper angle.  Entry = float offsets into the frame's
-// tau / y arrays and the packed H index: bits 0-7 al*8, 8-15 be*8, 16-24 index.  Unrelated pairs
-// (disjoint subtrees) are structural zeros, sorted last: entries N_REL.. only carry the H index and are
-// written as 0 without any arithmetic.
-struct PairTable {
-    unsigned e[N_PAIR + 3];     // padded to 256 entries = 1024 bytes: one bulk copy
-    int joint[NANG];
+// Column table of the H assembly (P4).  One thread owns one angle slot `be` of one frame: it forms
+// y = I_subtree(joint(be)) tau_be in registers and from it every entry H[al][be] = tau_al . y with `al` an
+// ancestor-or-self angle of `be` (same joint: al <= be) - column `be` of the block.  Ancestors at the head and neck joints
+// ("trunk", 6 slots, 117 of the 185 related pairs) pivot on the head point: v_al = 0, so their entries are 3-term dot
+// products omega_al . y_top with omega_al loaded once per frame (broadcast).  The other ancestors (<= 8) come from a
+// per-slot list.  Unrelated pairs (disjoint subtrees, 68) are structural zeros: a list of their H indices, written without
+// arithmetic.  Task order: columns sorted by list length so that the four columns sharing a warp do similar work; the
+// two columns of the second round are light ones.
+constexpr int N_TRUNK = 6;
+constexpr int k_trunk_slot[N_TRUNK] = {0, 3, 17, 1, 4, 18};     // phi0 theta0 psi0 | phi1 theta1 psi1
+constexpr int trunk_slot(int k) { return k == 0 ? 0 : k == 1 ? 3 : k == 2 ? 17 : k == 3 ? 1 : k == 4 ? 4 : 18; }
+constexpr int MAX_ANC = 8;
+constexpr int N_ZERO = N_PAIR - 185;
+struct ColEntry {                       // 48 bytes: three 16-byte loads
+    unsigned char slot, joint, n_anc, pad0;
+    unsigned short trunk_idx[N_TRUNK];  // packed-H index of (trunk slot k, be); 0xFFFF: not a related pair in this order
+    unsigned char anc[MAX_ANC];         // non-trunk ancestor-or-self slots (unused: 0)
+    unsigned short anc_idx[MAX_ANC];    // their packed-H indices
+    unsigned pad1[2];
 };
-constexpr PairTable make_pair_table() {
-    PairTable t{};
-    int n = 0;
-    for (int pass = 0; pass < 2; ++pass)
-        for (int be = 0; be < NANG; ++be)
-            for (int al = 0; al < NANG; ++al) {
-                const int ja = k_angle_joint[al], jb = k_angle_joint[be];
-                const bool a_anc_b = joint_is_anc(ja, jb), b_anc_a = joint_is_anc(jb, ja);
-                const int sa = 3 + al, sb = 3 + be;
-                const int lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
-                const unsigned idx = (unsigned)(lo * NA - (lo * (lo - 1)) / 2 + (hi - lo));
-                if (pass == 0 && a_anc_b && (ja != jb || al <= be))
-                    t.e[n++] = (unsigned)(al * TAU_STRIDE) | ((unsigned)(be * TAU_STRIDE) << 8) | (idx << 16);
-                if (pass == 1 && !a_anc_b && !b_anc_a && al < be)
-                    t.e[n++] = (unsigned)(NANG * TAU_STRIDE) | ((unsigned)(be * TAU_STRIDE) << 8) | (idx << 16);
+static_assert(sizeof(ColEntry) == 48, "ColEntry layout");
+struct ColTable {
+    ColEntry col[NANG];
+    unsigned short zero_idx[N_ZERO + 4];
+    int n_rel;
+};
+constexpr bool is_trunk_slot(int a) {
+    for (int k = 0; k < N_TRUNK; ++k)
+        if (k_trunk_slot[k] == a) return true;
+    return false;
+}
+constexpr bool related(int al, int be) {     // H[al][be] is computed as column `be`
+    const int ja = k_angle_joint[al], jb = k_angle_joint[be];
+    return joint_is_anc(ja, jb) && (ja != jb || al <= be);
+}
+constexpr unsigned short packed_index(int al, int be) {
+    const int sa = 3 + al, sb = 3 + be;
+    const int lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
+    return (unsigned short)(lo * NA - (lo * (lo - 1)) / 2 + (hi - lo));
+}
+constexpr ColTable make_col_table() {
+    ColTable t{};
+    int n_anc[NANG] = {};
+    for (int be = 0; be < NANG; ++be)
+        for (int al = 0; al < NANG; ++al)
+            if (related(al, be) && !is_trunk_slot(al)) ++n_anc[be];
+    // slots sorted by list length (stable)
+    int order[NANG] = {};
+    for (int i = 0; i < NANG; ++i) order[i] = i;
+    for (int i = 1; i < NANG; ++i)
+        for (int j = i; j > 0 && n_anc[order[j - 1]] > n_anc[order[j]]; --j) {
+            const int tmp = order[j];
+            order[j] = order[j - 1];
+            order[j - 1] = tmp;
+        }
+    int n_rel = 0;
+    for (int q = 0; q < NANG; ++q) {
+        // first round: the four lightest columns, then the 16 heaviest; second round (q = 20, 21): two light ones
+        const int be = order[q < 4 ? q : (q < 20 ? q + 2 : q - 16)];
+        ColEntry& c = t.col[q];
+        c.slot = (unsigned char)be;
+        c.joint = (unsigned char)k_angle_joint[be];
+        for (int k = 0; k < N_TRUNK; ++k) {
+            const bool on = related(k_trunk_slot[k], be);
+            c.trunk_idx[k] = on ? packed_index(k_trunk_slot[k], be) : (unsigned short)0xFFFF;
+            n_rel += on;
+        }
+        int n = 0;
+        for (int al = 0; al < NANG; ++al)
+            if (related(al, be) && !is_trunk_slot(al)) {
+                c.anc[n] = (unsigned char)al;
+                c.anc_idx[n] = packed_index(al, be);
+                ++n;
             }
-    for (int a = 0; a < NANG; ++a) t.joint[a] = k_angle_joint[a];
+        c.n_anc = (unsigned char)n;
+        n_rel += n;
+    }
+    int nz = 0;
+    for (int be = 0; be < NANG; ++be)
+        for (int al = 0; al < be; ++al)
+            if (!related(al, be) && !related(be, al)) t.zero_idx[nz++] = packed_index(al, be);
+    t.n_rel = n_rel * 1000 + nz;
     return t;
 }
-constexpr int count_related_pairs() {
+constexpr int max_anc_len() {
+    int m = 0;
+    for (int be = 0; be < NANG; ++be) {
+        int n = 0;
+        for (int al = 0; al < NANG; ++al) n += related(al, be) && !is_trunk_slot(al);
+        m = n > m ? n : m;
+    }
+    return m;
+}
+static_assert(max_anc_len() == MAX_ANC, "kinematic tree changed: check the column table");
+static_assert(make_col_table().n_rel == 185 * 1000 + N_ZERO, "kinematic tree changed: 185 related + 68 unrelated pairs");
+__constant__ ColTable c_col = make_col_table();
+__device__ __align__(16) const ColTable d_col = make_col_table();     // global-memory copy: source of the bulk (TMA) copy
+constexpr unsigned COL_BYTES = sizeof(ColEntry) * NANG + sizeof(unsigned short) * (N_ZERO + 4);   // 1056 + 144
+static_assert(COL_BYTES % 16 == 0, "bulk copy size");
+
+// the 16 angle slots whose rotation does not pivot on the head point: (slot, pivot marker) - v = pivot x omega is formed
+// from the stored components by otherwise idle threads of the subtree-sum phase
+struct PivotTable {
+    unsigned char slot[16], marker[16];
+};
+constexpr PivotTable make_pivot_table() {
+    PivotTable t{};
     int n = 0;
-    for (int be = 0; be < NANG; ++be)
-        for (int al = 0; al < NANG; ++al) {
-            const int ja = k_angle_joint[al], jb = k_angle_joint[be];
-            if (joint_is_anc(ja, jb) && (ja != jb || al <= be)) ++n;
+    for (int a = 0; a < NANG; ++a)
+        if (k_angle_pivot[a] >= 0) {
+            t.slot[n] = (unsigned char)a;
+            t.marker[n] = (unsigned char)k_angle_pivot[a];
+            ++n;
         }
+    return t;
+}
+constexpr int count_pivoted() {
+    int n = 0;
+    for (int a = 0; a < NANG; ++a) n += k_angle_pivot[a] >= 0;
     return n;
 }
-constexpr int N_REL = count_related_pairs();   // 185 related pairs; the other 68 are structural zeros
-static_assert(N_REL == 185, "kinematic tree changed: check the pair table");
-__constant__ PairTable c_tab = make_pair_table();
-__device__ __align__(16) const PairTable d_tab = make_pair_table();     // global-memory copy: source of the bulk (TMA) copy
+static_assert(count_pivoted() == 16, "kinematic tree changed: check the pivot table");
+constexpr unsigned pivoted_mask() {
+    unsigned m = 0;
+    for (int a = 0; a < NANG; ++a) m |= (k_angle_pivot[a] >= 0 ? 1u : 0u) << a;
+    return m;
+}
+constexpr unsigned k_pivoted_mask = pivoted_mask();     // bit a: angle slot a pivots on a marker (v != 0)
+__constant__ PivotTable c_piv = make_pivot_table();
 
-// bulk-copied input tiles.  One bulk copy per frame into padded frame slots: the 20 lanes of frame f+1 continue in
-// the banks where frame f stopped (stride = 8 (mod 32) words for the float2 tile, 20 (mod 32) for the weights), so a
-// warp that straddles two frames reads conflict-free
+// bulk-copied input tiles: the measurement and weight rows of the FT frames of a tile are contiguous in global memory,
+// so each tile is ONE bulk copy (issuing a copy costs the issuing thread ~100 cycles: 2 copies per tile, not 2 per frame)
 template <int FT, int MAXC>
 struct InTiles {
-    float2 meas[FT * (MAXC * NL + 16)];   // [FT][C][NL] (u,v)
-    float w[FT * (MAXC * NL + 32)];       // [FT][C][NL]
+    float2 meas[FT * MAXC * NL];          // [FT][C][NL] (u,v)
+    float w[FT * MAXC * NL];              // [FT][C][NL]
 };
-struct NoTiles {};
-constexpr int MAXC_PERSIST = 6;           // cameras the separate (prefetchable) input buffer of the persistent kernel holds
+#ifndef ACINO_MAXC_STAGE
+#define ACINO_MAXC_STAGE (ACINO_MAX_CAMS / 2)
+#endif
+constexpr int MAXC_STAGE = ACINO_MAXC_STAGE;     // cameras the staged input tiles hold; more cameras: direct loads
 
-template <int FT, bool PERSIST>
+// Shared memory of one CTA (persistent: the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...).  Two regions are
+// re-used inside a tile, arranged so that the NEXT tile's inputs can be fetched while this tile is still being reduced:
+//   region A: per-marker inertia Il (P2 -> P3), then the staged outputs o (P4 -> bulk stores of P5, read by the TMA
+//             engine while the next tile's FK runs)
+//   region B: this tile's measurement / weight tiles (TMA -> P2), then the per-joint subtree sums Ij (P3 -> P4a); free
+//             again after P4a, when the next tile's bulk copies are issued (they land during P4b, P5 and the next FK)
+template <int FT>
 struct __align__(16) Smem {
-    float x[2][FT][NA];                // state (double buffered: the persistent kernel prefetches the next tile)
+    float x[2][FT][NA];                // state, double buffered (next tile prefetched)
     float p[FT][NL][3];                // marker positions relative to the head point
     float2 sc[FT][NANG];               // (sin, cos) of every angle
     float costp[FT][NL];               // per-(frame, marker) cost partials
-    unsigned tab[N_PAIR + 3];          // pair table (copy of c_tab.e)
-    // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads); frame stride 396 words = 12 (mod 32):
-    // the 8 frames of a quarter-warp hit 8 distinct 4-bank groups (392 gave 2-way conflicts on every LDS.128 of P4a)
-    __align__(16) float Ij[FT][NJ * (NSP + 1) + 4];
+    __align__(16) ColEntry col[NANG];  // column table of the H assembly (copy of c_col), followed by the zero list
+    unsigned short zero_idx[N_ZERO + 4];
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
-    // persistent kernel: input tiles in their own buffer, refilled for the NEXT tile while P2b..P5 of the current one run
-    __align__(16) typename std::conditional<PERSIST, InTiles<FT, MAXC_PERSIST>, NoTiles>::type in_s;
-    union {
-        __align__(16) float Il[FT * NL][NSP + 1];   // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 / LDS.64  (P2 -> P3)
-        InTiles<FT, ACINO_MAX_CAMS / 2> in_u;       // one-tile-per-CTA kernel: input tiles alias Il (kernel start -> end of the camera loop)
-        struct {                       // staged outputs in their global layout  (P4 -> P5)
+    union {                            // region A
+        __align__(16) float Il[FT * NL][NSP + 1];   // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 / LDS.64
+        struct {                       // staged outputs in their global layout
             float H[FT][NU];
             float g[FT][NA];
             float cost[FT];
-            __align__(16) float y[FT][TAUF];   // y_beta = I_subtree tau_beta, stride 8
         } o;
+    };
+    union {                            // region B
+        InTiles<FT, MAXC_STAGE> in;
+        // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads); frame stride 396 words = 12 (mod 32):
+        // the 8 frames of a quarter-warp hit 8 distinct 4-bank groups (392 gave 2-way conflicts on every LDS.128 of P4a)
+        __align__(16) float Ij[FT][NJ * (NSP + 1) + 4];
     };
 };
 
@@ -142,6 +236,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // shared -> global bulk store (TMA, 1-D) of a staged output tile; the issuing thread waits until the
 // source has been read before the CTA may retire
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
@@ -157,7 +255,15 @@ __device__ int g_phase_count;
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
-template <int FT, bool WANT_H, int NPAIR, bool PERSIST>
+// range-reduced MUFU sine / cosine: |error| < 4e-7 for any |x| up to a few hundred revolutions (the reduction is one
+// fp32 FMA; the reference's angles are bounded by pi).  The same values feed cost, gradient and H.
+__device__ __forceinline__ void fast_sincos(const float x, float& sn, float& cs) {
+    const float xr = fmaf(-6.283185307179586f, rintf(x * 0.15915494309189535f), x);
+    sn = __sinf(xr);
+    cs = __cosf(xr);
+}
+
+template <int FT, bool WANT_H>
 __device__ __forceinline__ void
 fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
               const float* __restrict__ xg, const float* __restrict__ meas,
@@ -165,117 +271,123 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
               float* __restrict__ g_out, float* __restrict__ H_out) {
     constexpr int NT = FT * NL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<FT, PERSIST>& S = *reinterpret_cast<Smem<FT, PERSIST>*>(smem_raw);
+    Smem<FT>& S = *reinterpret_cast<Smem<FT>*>(smem_raw);
     const int tid = threadIdx.x;
     const int C = scene.n_cams;
     const int n_tiles = (n_frames + FT - 1) / FT;
     // the input tiles of a full tile are contiguous, 16-byte aligned blocks of global memory: stage them with 1-D
-    // bulk async copies (TMA) that overlap the forward kinematics (and, in the persistent kernel, the previous tile)
-    const bool bulk_in = (use_bulk & 1) && C <= (PERSIST ? MAXC_PERSIST : ACINO_MAX_CAMS / 2);
-    float2* in_meas;
-    float* in_w;
-    if constexpr (PERSIST) {
-        in_meas = S.in_s.meas;
-        in_w = S.in_s.w;
-    } else {
-        in_meas = S.in_u.meas;
-        in_w = S.in_u.w;
-    }
-    // padded frame strides of the staged tiles (see InTiles): float2 units / float units
-    const int ms2 = (C * NL * 2 + ((8 - C * NL * 2) & 31)) >> 1;
-    const int ws = C * NL + ((20 - C * NL) & 31);
-    const unsigned bx = FT * NA * 4, bm = C * NL * 8, bw = C * NL * 4;     // bytes: state tile; per-frame meas / weight rows
+    // bulk async copies (TMA) issued one tile ahead
+    const bool bulk_in = (use_bulk & 1) && C <= MAXC_STAGE;
+    float2* const in_meas = S.in.meas;
+    float* const in_w = S.in.w;
+    const int ms2 = C * NL, ws = C * NL;            // frame strides of the staged tiles: float2 units / float units
+    const unsigned bx = FT * NA * 4, bm = FT * C * NL * 8, bw = FT * C * NL * 4;     // bytes: state / meas / weight tile
     auto issue_x = [&](const int t, const int buf, const bool with_tab) {
-        mbar_expect_tx(&S.mbar[0], bx + (with_tab ? (N_PAIR + 3) * 4 : 0));
+        mbar_expect_tx(&S.mbar[0], bx + (with_tab ? COL_BYTES : 0));
         bulk_g2s(&S.x[buf][0][0], xg + (size_t)t * FT * NA, bx, &S.mbar[0]);
-        if (with_tab) bulk_g2s(&S.tab[0], &d_tab.e[0], (N_PAIR + 3) * 4, &S.mbar[0]);
+        if (with_tab) bulk_g2s(&S.col[0], &d_col.col[0], COL_BYTES, &S.mbar[0]);
     };
     auto issue_mw = [&](const int t) {
-        mbar_expect_tx(&S.mbar[1], FT * (bm + bw));
-        for (int ff = 0; ff < FT; ++ff) {
-            bulk_g2s(&in_meas[ff * ms2], meas + (size_t)(t * FT + ff) * C * NL * 2, bm, &S.mbar[1]);
-            bulk_g2s(&in_w[ff * ws], wts + (size_t)(t * FT + ff) * C * NL, bw, &S.mbar[1]);
-        }
+        mbar_expect_tx(&S.mbar[1], bm + bw);
+        bulk_g2s(in_meas, meas + (size_t)t * FT * C * NL * 2, bm, &S.mbar[1]);
+        bulk_g2s(in_w, wts + (size_t)t * FT * C * NL, bw, &S.mbar[1]);
     };
 #ifdef ACINO_PHASE_TIMING
     long long _tprev = clock64();
 #endif
 
-    // ---- prologue: barriers, zero twist slot, the first tile's copies
+    // sin / cos of the 22 angles of tile t, one thread per (angle, frame); its state tile is in (or goes to) S.x[buf]
+    unsigned ph_x = 0, ph_m = 0;       // completed phases of mbar[0] / mbar[1]
+    auto sincos_tile = [&](const int t, const int buf) {
+        const int tf0 = t * FT;
+        const int tnf = min(FT, n_frames - tf0);
+        float (*X)[NA] = S.x[buf];
+        if (bulk_in && tnf == FT) {
+            mbar_wait(&S.mbar[0], ph_x & 1);
+            ++ph_x;
+            for (int k = tid; k < FT * NANG; k += NT) {
+                const int a = k / FT, f = k - a * FT;
+                float sn, cs;
+                fast_sincos(X[f][3 + a], sn, cs);
+                S.sc[f][a] = make_float2(sn, cs);
+            }
+        } else {
+            // partial tile or unaligned inputs: the state goes to shared memory by plain loads (read again by the
+            // camera loop, several barriers from here); the angles are read straight from global memory
+            for (int i = tid; i < FT * NA; i += NT) {
+                const int f = i / NA;
+                (&X[0][0])[i] = (f < tnf) ? xg[(size_t)tf0 * NA + i] : 0.f;
+            }
+            for (int k = tid; k < FT * NANG; k += NT) {
+                const int a = k / FT, f = k - a * FT;
+                float sn, cs;
+                fast_sincos(f < tnf ? xg[(size_t)(tf0 + f) * NA + 3 + a] : 0.f, sn, cs);
+                S.sc[f][a] = make_float2(sn, cs);
+            }
+        }
+    };
+
+    // ---- prologue: barriers, the constant zero entries of the twists, the first tile's copies, table and sin / cos
     int tile = blockIdx.x;
-    if (bulk_in && tid == 0) {
+    const bool first_staged = bulk_in && (tile + 1) * FT <= n_frames;
+    if (tid == 0) {
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (tile < n_tiles && (tile + 1) * FT <= n_frames) {
+        if (first_staged) {
             issue_x(tile, 0, true);
             issue_mw(tile);
         }
-        // experiment (use_bulk bit 2): pull the inputs of the tile that will run in this CTA slot one wave later into
-        // L2, so that its own bulk copies do not pay the full HBM latency at CTA start
-        if (!PERSIST && (use_bulk & 4)) {
-            const int tp = tile + PREFETCH_DIST;
-            if ((tp + 1) * FT <= n_frames) {
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xg + (size_t)tp * FT * NA), "r"(bx) : "memory");
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(meas + (size_t)tp * FT * C * NL * 2), "r"(FT * bm) : "memory");
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wts + (size_t)tp * FT * C * NL), "r"(FT * bw) : "memory");
-            }
+    }
+    // v = 0 for the angles that pivot on the head point, and the all-zero slot NANG (never written again)
+    for (int i = tid; i < FT * (NANG + 1); i += NT) {
+        const int f = i / (NANG + 1), a = i - f * (NANG + 1);
+        if (a == NANG || !((k_pivoted_mask >> a) & 1u)) {
+            float* t = &S.tau[f][a * TAU_STRIDE];
+            t[3] = 0.f; t[4] = 0.f; t[5] = 0.f;
+            if (a == NANG) { t[0] = 0.f; t[1] = 0.f; t[2] = 0.f; }
         }
     }
-    if (tid < FT * TAU_STRIDE) S.tau[tid / TAU_STRIDE][NANG * TAU_STRIDE + (tid % TAU_STRIDE)] = 0.f;
-    bool tab_ready = false;
-    unsigned ph_x = 0, ph_m = 0;       // completed phases of mbar[0] / mbar[1]
-    bool out_pending = false;          // (thread 0) bulk stores of the previous tile may still be reading `o`
+    if (!first_staged)          // (a staged first tile brings the table with its state)
+        for (int i = tid; i < (int)(COL_BYTES / 4); i += NT)
+            reinterpret_cast<unsigned*>(&S.col[0])[i] = reinterpret_cast<const unsigned*>(&c_col.col[0])[i];
+    bool out_pending = false;          // (thread 0) bulk stores of the previous tile may still be reading region A
     __syncthreads();
 
     for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
     const int f0 = tile * FT;
     const int nf = min(FT, n_frames - f0);
     const bool staged = bulk_in && nf == FT;
-    const int xb = PERSIST ? (it & 1) : 0;
+    const int xb = it & 1;
     float (*Sx)[NA] = S.x[xb];
-    // ---- P0: the tile's state (and, first time, the pair table)
-    if (staged) {
-        mbar_wait(&S.mbar[0], ph_x & 1);
-        ++ph_x;
-        tab_ready = true;
-    } else {
-        for (int i = tid; i < FT * NA; i += NT) {
-            const int f = i / NA;
-            (&Sx[0][0])[i] = (f < nf) ? xg[(size_t)f0 * NA + i] : 0.f;
-        }
-        if (!tab_ready)
-            for (int i = tid; i < N_PAIR; i += NT) S.tab[i] = c_tab.e[i];
-        tab_ready = true;
-        __syncthreads();
-    }
-    PHASE_MARK(0);
-
-    // ---- P1a: sin/cos of the 22 angles, one thread per (angle, frame)
-    for (int t = tid; t < FT * NANG; t += NT) {
-        const int a = t / FT, f = t - a * FT;
-        float sn, cs;
-        if (use_bulk & 8) {            // experiment: range-reduced MUFU sin / cos
-            const float xa = Sx[f][3 + a];
-            const float xr = fmaf(-6.283185307179586f, rintf(xa * 0.15915494309189535f), xa);
-            sn = __sinf(xr);
-            cs = __cosf(xr);
-        } else {
-            sincosf(Sx[f][3 + a], &sn, &cs);
-        }
-        S.sc[f][a] = make_float2(sn, cs);
-    }
+    const int tile_next = tile + gridDim.x;
+    // ---- P0 + P1a: the tile's state (prefetched during the previous tile) -> sin / cos of the 22 angles
+    sincos_tile(tile, xb);
     __syncthreads();
-    if (PERSIST && bulk_in && tid == 0) {          // every thread is past its wait on mbar[0]: re-arm it for the next tile
-        const int tn = tile + gridDim.x;
-        if (tn < n_tiles && (tn + 1) * FT <= n_frames) issue_x(tn, xb ^ 1, false);
-    }
     PHASE_MARK(1);
 
-    // ---- P1b: rotation chain, one thread per frame
-    if (tid < FT) {
-        FkWriter w{&S.p[tid][0][0], &S.tau[tid][0]};
-        cheetah_fk(S.sc[tid], w);
+    // ---- P1b: rotation chain, three threads per frame (one per ROW of the chain: right-multiplications keep rows
+    //      independent): component i of every marker position and rotation axis
+    //      Warp 0: head / neck / torso / tail, warp 1: front legs, warp 2: back legs (each re-derives the part of the trunk
+    //      it hangs from: cheaper than waiting for it).  Warp 3: the next tile's state (every thread is past its wait on
+    //      mbar[0]; the other buffer was last read by the previous tile)
+    {
+        const int wq = tid >> 5, ln = tid & 31;
+        if (wq < 3) {
+            if (ln < 3 * FT) {
+                const int f = ln / 3, i = ln - 3 * f;
+                if (wq == 0) cheetah_fk_row<1>(S.sc[f], i, &S.p[f][0][0], &S.tau[f][0]);
+                else if (wq == 1) cheetah_fk_row<2>(S.sc[f], i, &S.p[f][0][0], &S.tau[f][0]);
+                else cheetah_fk_row<4>(S.sc[f], i, &S.p[f][0][0], &S.tau[f][0]);
+            }
+        } else if (bulk_in && tid == 96) {
+            if (tile_next < n_tiles && (tile_next + 1) * FT <= n_frames) issue_x(tile_next, xb ^ 1, false);
+        }
+    }
+    // region A still holds the previous tile's staged outputs: its bulk stores must have read them before P2 writes Il
+    if (tid == 0 && out_pending) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        out_pending = false;
     }
     __syncthreads();
     PHASE_MARK(2);
@@ -298,12 +410,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         const f2 zero2 = bc(0.f), one2 = bc(1.f);
         f2 A00 = zero2, A01 = zero2, A02 = zero2, A11 = zero2, A12 = zero2, A22 = zero2;
         f2 B0 = zero2, B1 = zero2, B2 = zero2, CST = zero2;
-#pragma unroll
-        for (int c = 0; c < (NPAIR ? 2 * NPAIR : C); c += 2) {
-            const bool has2 = NPAIR ? true : (c + 1 < C);
+        // (two instantiations: staged tiles read shared memory, the others global memory - no per-iteration branch)
+        auto camera_loop = [&](auto staged_tag) {
+        constexpr bool STAGED = decltype(staged_tag)::value;
+        for (int c = 0; c < C; c += 2) {
+            const bool has2 = c + 1 < C;
             float2 m0 = make_float2(0.f, 0.f), m1 = make_float2(0.f, 0.f);
             float w0 = 0.f, w1 = 0.f;
-            if (staged) {
+            if (STAGED) {
                 m0 = in_meas[f * ms2 + c * NL + l];
                 w0 = in_w[f * ws + c * NL + l];
                 if (has2) {
@@ -347,9 +461,9 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             RU = pk(on0 ? lo(RU) : 0.f, on1 ? hi(RU) : 0.f);
             RV = pk(on0 ? lo(RV) : 0.f, on1 ? hi(RV) : 0.f);
             // world-frame Jacobian rows: J = diag(fx,fy)/z [m] [I | -(a,b)] R = c . G,  G_i = R_i - (a|b) R_2
-            const f2 NA = sub2(zero2, Aa), NB = sub2(zero2, Bb);
-            const f2 G00 = fma2(NA, R6, R0), G01 = fma2(NA, R7, R1), G02 = fma2(NA, R8, R2);
-            const f2 G10 = fma2(NB, R6, R3), G11 = fma2(NB, R7, R4), G12 = fma2(NB, R8, R5);
+            const f2 NA_ = sub2(zero2, Aa), NB_ = sub2(zero2, Bb);
+            const f2 G00 = fma2(NA_, R6, R0), G01 = fma2(NA_, R7, R1), G02 = fma2(NA_, R8, R2);
+            const f2 G10 = fma2(NB_, R6, R3), G11 = fma2(NB_, R7, R4), G12 = fma2(NB_, R8, R5);
             const f2 FXI = mul2(FX, IZ), FYI = mul2(FY, IZ);
             const f2 CU0 = mul2(FXI, M00), CU1 = mul2(FXI, M01), CV0 = mul2(FYI, M01), CV1 = mul2(FYI, M11);
             const f2 JU0 = fma2(CU0, G00, mul2(CU1, G10)), JU1 = fma2(CU0, G01, mul2(CU1, G11)), JU2 = fma2(CU0, G02, mul2(CU1, G12));
@@ -384,25 +498,17 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
                 A22 = fma2(TU2, JU2, fma2(TV2, JV2, A22));
             }
         }
+        };
+        if (staged) camera_loop(std::true_type{});
+        else camera_loop(std::false_type{});
         const float a00 = lo(A00) + hi(A00), a01 = lo(A01) + hi(A01), a02 = lo(A02) + hi(A02);
         const float a11 = lo(A11) + hi(A11), a12 = lo(A12) + hi(A12), a22 = lo(A22) + hi(A22);
         const float b0 = lo(B0) + hi(B0), b1 = lo(B1) + hi(B1), b2 = lo(B2) + hi(B2);
         const float cst = lo(CST) + hi(CST);
         S.costp[f][l] = cst;
-        if (PERSIST) {
-            // Il aliases the staged outputs of the previous tile: its bulk stores must have read them; then the
-            // input buffer is free and is refilled for the next tile while P2b..P5 of this one run
-            if (tid == 0 && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
-            if (bulk_in && tid == 0) {
-                const int tn = tile + gridDim.x;
-                if (tn < n_tiles && (tn + 1) * FT <= n_frames) issue_mw(tn);
-            }
-        } else if (staged) {
-            __syncthreads();           // the input tiles alias Il: every thread is done reading them
-        }
         PHASE_MARK(3);
-        // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]
+        // spatial inertia of this marker about the head point: B^T A B with B = [-[p]x  I]  (region A: free since the
+        // barrier after P1a)
         float o[NSP + 1];
 #pragma unroll
         for (int i = 0; i < NSP + 1; ++i) o[i] = 0.f;
@@ -431,68 +537,90 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
 #pragma unroll
         for (int i = (WANT_H ? 0 : 5); i < (NSP + 1) / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
-    __syncthreads();
+    __syncthreads();   // the input tiles (region B) are dead from here on
     PHASE_MARK(4);
 
-    // ---- P3: subtree sums up the kinematic tree, one thread per (component pair, frame), packed adds
+    // ---- P3: subtree sums up the kinematic tree, one thread per (component pair, frame), packed adds; the last warp
+    //      (idle otherwise) forms v = pivot x omega of the 16 pivoted angles from the components the FK rows stored
     {
         constexpr int NKP = (NSP + 1) / 2;       // 14 component pairs
         const int task = tid;
         const int f = task / NKP;
         const int kp = task - f * NKP;
-        if (task < FT * NKP && (WANT_H || kp >= 10)) {
-            f2 v[NL];
+        if (task < FT * NKP) {
+            if (WANT_H || kp >= 10) {
+                f2 v[NL];
 #pragma unroll
-            for (int l = 0; l < NL; ++l) v[l] = pk(*reinterpret_cast<const float2*>(&S.Il[f * NL + l][2 * kp]));
-            const f2 s13 = v[19], s12 = add2(v[18], s13);
-            const f2 s11 = v[16], s10 = add2(v[15], s11);
-            const f2 s5 = v[7], s4 = add2(v[6], s5);
-            const f2 s3 = add2(add2(add2(v[5], v[14]), v[17]), add2(add2(s4, s10), s12));
-            const f2 s9 = v[13], s8 = add2(v[12], s9);
-            const f2 s7 = v[10], s6 = add2(v[9], s7);
-            const f2 s2 = add2(add2(add2(v[4], v[8]), v[11]), add2(add2(s3, s6), s8));
-            const f2 s1 = add2(v[3], s2);
-            const f2 s0 = add2(add2(add2(v[0], v[1]), v[2]), s1);
-            float* d = &S.Ij[f][2 * kp];
-            constexpr int IS = NSP + 1;
+                for (int l = 0; l < NL; ++l) v[l] = pk(*reinterpret_cast<const float2*>(&S.Il[f * NL + l][2 * kp]));
+                const f2 s13 = v[19], s12 = add2(v[18], s13);
+                const f2 s11 = v[16], s10 = add2(v[15], s11);
+                const f2 s5 = v[7], s4 = add2(v[6], s5);
+                const f2 s3 = add2(add2(add2(v[5], v[14]), v[17]), add2(add2(s4, s10), s12));
+                const f2 s9 = v[13], s8 = add2(v[12], s9);
+                const f2 s7 = v[10], s6 = add2(v[9], s7);
+                const f2 s2 = add2(add2(add2(v[4], v[8]), v[11]), add2(add2(s3, s6), s8));
+                const f2 s1 = add2(v[3], s2);
+                const f2 s0 = add2(add2(add2(v[0], v[1]), v[2]), s1);
+                float* d = &S.Ij[f][2 * kp];
+                constexpr int IS = NSP + 1;
 #define ST2(j, v) *reinterpret_cast<float2*>(d + (j) * IS) = make_float2(lo(v), hi(v))
-            ST2(0, s0); ST2(1, s1); ST2(2, s2); ST2(3, s3); ST2(4, s4); ST2(5, s5); ST2(6, s6);
-            ST2(7, s7); ST2(8, s8); ST2(9, s9); ST2(10, s10); ST2(11, s11); ST2(12, s12); ST2(13, s13);
+                ST2(0, s0); ST2(1, s1); ST2(2, s2); ST2(3, s3); ST2(4, s4); ST2(5, s5); ST2(6, s6);
+                ST2(7, s7); ST2(8, s8); ST2(9, s9); ST2(10, s10); ST2(11, s11); ST2(12, s12); ST2(13, s13);
 #undef ST2
+            }
+        } else if (tid >= NT - 32) {
+            for (int t = tid - (NT - 32); t < 16 * FT; t += 32) {
+                const int k = t / FT, ff = t - k * FT;
+                const float* pv = S.p[ff][c_piv.marker[k]];
+                float* tt = &S.tau[ff][c_piv.slot[k] * TAU_STRIDE];
+                const float p0 = pv[0], p1 = pv[1], p2 = pv[2], o0 = tt[0], o1 = tt[1], o2 = tt[2];
+                tt[3] = p1 * o2 - p2 * o1;
+                tt[4] = p2 * o0 - p0 * o2;
+                tt[5] = p0 * o1 - p1 * o0;
+            }
         }
     }
     __syncthreads();   // Il is dead from here on; the staged outputs alias it
     PHASE_MARK(5);
 
-    // ---- P4a: y_beta = I_subtree(beta) tau_beta, g, translation rows.  task (beta, frame);
-    //      beta == 22 is the translation block
+    // ---- P4: column beta of H, g[beta].  One thread per (task q, frame); q == 22 is the translation block.
+    //      y = I_subtree(beta) tau_beta stays in registers (see ColEntry).
     for (int task = tid; task < FT * (NANG + 1); task += NT) {
-        const int be = task / FT;
-        const int f = task - be * FT;
+        const int q = task / FT;
+        const int f = task - q * FT;
         float* g = S.o.g[f];
         float* H = S.o.H[f];
-        if (be == NANG) {
+        if (q == NANG) {
             float c = 0.f;
 #pragma unroll
             for (int l = 0; l < NL; ++l) c += S.costp[f][l];
-            S.o.cost[f] = c;
             const float* I0 = S.Ij[f];
-            g[0] = I0[24]; g[1] = I0[25]; g[2] = I0[26];
+            const float g0 = I0[24], g1 = I0[25], g2 = I0[26];
+            const float h0 = I0[15], h1 = I0[16], h2 = I0[17], h3 = I0[18], h4 = I0[19], h5 = I0[20];
+            S.o.cost[f] = c;
+            g[0] = g0; g[1] = g1; g[2] = g2;
             if (WANT_H) {
-                H[upper_index(0, 0)] = I0[15]; H[upper_index(0, 1)] = I0[16]; H[upper_index(0, 2)] = I0[17];
-                H[upper_index(1, 1)] = I0[18]; H[upper_index(1, 2)] = I0[19]; H[upper_index(2, 2)] = I0[20];
+                H[upper_index(0, 0)] = h0; H[upper_index(0, 1)] = h1; H[upper_index(0, 2)] = h2;
+                H[upper_index(1, 1)] = h3; H[upper_index(1, 2)] = h4; H[upper_index(2, 2)] = h5;
             }
             continue;
         }
-        const float4* I4 = reinterpret_cast<const float4*>(&S.Ij[f][c_tab.joint[be] * (NSP + 1)]);
+        const uint4* ce = reinterpret_cast<const uint4*>(&S.col[q]);
+        const uint4 e0 = ce[0];            // slot, joint, n_anc | trunk_idx[0..5]
+        const int be = e0.x & 0xFFu, jb = (e0.x >> 8) & 0xFFu, n_anc = (e0.x >> 16) & 0xFFu;
+        const float4* I4 = reinterpret_cast<const float4*>(&S.Ij[f][jb * (NSP + 1)]);
         const float4 i0 = I4[0], i1 = I4[1], i2 = I4[2], i3 = I4[3], i4 = I4[4], i5 = I4[5], i6 = I4[6];
         const float I[28] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y,
                              i3.z, i3.w, i4.x, i4.y, i4.z, i4.w, i5.x, i5.y, i5.z, i5.w, i6.x, i6.y, i6.z, i6.w};
-        const float4 t0 = *reinterpret_cast<const float4*>(&S.tau[f][be * TAU_STRIDE]);
-        const float2 t1 = *reinterpret_cast<const float2*>(&S.tau[f][be * TAU_STRIDE + 4]);
+        const float* tau_f = &S.tau[f][0];
+        const float4 t0 = *reinterpret_cast<const float4*>(tau_f + be * TAU_STRIDE);
+        const float2 t1 = *reinterpret_cast<const float2*>(tau_f + be * TAU_STRIDE + 4);
         const float o0 = t0.x, o1 = t0.y, o2 = t0.z, v0 = t0.w, v1 = t1.x, v2 = t1.y;
-        g[3 + be] = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
-        if (!WANT_H) continue;
+        const float gb = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
+        if (!WANT_H) {
+            g[3 + be] = gb;
+            continue;
+        }
         // y = I tau_beta ; I = [[TL, PA],[PA^T, A]]
         const float yt0 = I[0] * o0 + I[1] * o1 + I[2] * o2 + I[6] * v0 + I[7] * v1 + I[8] * v2;
         const float yt1 = I[1] * o0 + I[3] * o1 + I[4] * o2 + I[9] * v0 + I[10] * v1 + I[11] * v2;
@@ -500,52 +628,65 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         const float yb0 = I[6] * o0 + I[9] * o1 + I[12] * o2 + I[15] * v0 + I[16] * v1 + I[17] * v2;
         const float yb1 = I[7] * o0 + I[10] * o1 + I[13] * o2 + I[16] * v0 + I[18] * v1 + I[19] * v2;
         const float yb2 = I[8] * o0 + I[11] * o1 + I[14] * o2 + I[17] * v0 + I[19] * v1 + I[20] * v2;
-        *reinterpret_cast<float4*>(&S.o.y[f][be * TAU_STRIDE]) = make_float4(yt0, yt1, yt2, yb0);
-        *reinterpret_cast<float2*>(&S.o.y[f][be * TAU_STRIDE + 4]) = make_float2(yb1, yb2);
+        // trunk rows: omega_al . y_top (the loads are the same for the four columns of a frame in this warp)
+        float ht[N_TRUNK];
+#pragma unroll
+        for (int k = 0; k < N_TRUNK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + trunk_slot(k) * TAU_STRIDE);
+            ht[k] = a0.x * yt0 + a0.y * yt1 + a0.z * yt2;
+        }
+        // the other ancestors (and beta itself): full 6-term products
+        const uint4 e1 = ce[1];            // anc[0..7] | anc_idx[0..3]
+        const uint2 e2 = *reinterpret_cast<const uint2*>(&ce[2]);     // anc_idx[4..7]
+        float ha[MAX_ANC];
+#pragma unroll
+        for (int k = 0; k < MAX_ANC; ++k) {
+            if (!__any_sync(__activemask(), k < n_anc)) break;     // (executing all 8 for every column measured 4 % slower)
+            const unsigned al = ((k < 4 ? e1.x : e1.y) >> (8 * (k & 3))) & 0xFFu;
+            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + al * TAU_STRIDE);
+            const float2 a1 = *reinterpret_cast<const float2*>(tau_f + al * TAU_STRIDE + 4);
+            ha[k] = a0.x * yt0 + a0.y * yt1 + a0.z * yt2 + a0.w * yb0 + a1.x * yb1 + a1.y * yb2;
+        }
+        // stores last: no store -> load ordering inside the task
+        g[3 + be] = gb;
         const int sb = 3 + be;  // active slot of beta: rows 0..2 (translation) of column sb
         H[sb] = yb0;
         H[NA + sb - 1] = yb1;
         H[2 * NA + sb - 3] = yb2;
+        const unsigned ti[3] = {e0.y, e0.z, e0.w};
+#pragma unroll
+        for (int k = 0; k < N_TRUNK; ++k) {
+            const unsigned idx = (ti[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if (idx != 0xFFFFu) H[idx] = ht[k];
+        }
+        const unsigned ai[4] = {e1.z, e1.w, e2.x, e2.y};
+#pragma unroll
+        for (int k = 0; k < MAX_ANC; ++k) {
+            if (k < n_anc) H[(ai[k >> 1] >> (16 * (k & 1))) & 0xFFFFu] = ha[k];
+        }
     }
-    __syncthreads();
-    PHASE_MARK(6);
-
-    // ---- P4b: one entry per (angle pair, frame): H[al][be] = tau_al . y_be.  NT / FT = 20 exactly, so a
-    //      thread keeps its frame (tid % FT) and walks the table with stride 20: p = tid / FT + 20 k.
-    //      All loads and dot products first, all stores last: no store -> load ordering between entries.
+    // structural zeros of H: N_ZERO entries per frame, no arithmetic
     if (WANT_H) {
-        constexpr int NE = (N_REL + NL - 1) / NL;    // 10 related entries per thread
-        const int f = tid % FT, p0 = tid / FT;
-        const float* tau_f = &S.tau[f][0];
-        const float* y_f = &S.o.y[f][0];
-        float* H_f = &S.o.H[f][0];
-        unsigned e[NE];
-        float hv[NE];
-#pragma unroll
-        for (int k = 0; k < NE; ++k) e[k] = S.tab[min(p0 + NL * k, N_REL - 1)];
-#pragma unroll
-        for (int k = 0; k < NE; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + (e[k] & 0xFFu));
-            const float2 a1 = *reinterpret_cast<const float2*>(tau_f + (e[k] & 0xFFu) + 4);
-            const float4 y0 = *reinterpret_cast<const float4*>(y_f + ((e[k] >> 8) & 0xFFu));
-            const float2 y1 = *reinterpret_cast<const float2*>(y_f + ((e[k] >> 8) & 0xFFu) + 4);
-            hv[k] = a0.x * y0.x + a0.y * y0.y + a0.z * y0.z + a0.w * y0.w + a1.x * y1.x + a1.y * y1.y;
-        }
-#pragma unroll
-        for (int k = 0; k < NE; ++k)
-            if (p0 + NL * k < N_REL) H_f[e[k] >> 16] = hv[k];
-        // structural zeros: (N_PAIR - N_REL) x FT stores
-#pragma unroll
-        for (int k = 0; k < ((N_PAIR - N_REL) * FT + NT - 1) / NT; ++k) {
-            const int z = p0 + NL * k;
-            if (z < N_PAIR - N_REL) H_f[S.tab[N_REL + z] >> 16] = 0.f;
+        for (int z = tid; z < N_ZERO * FT; z += NT) {
+            const int k = z / FT, f = z - k * FT;
+            S.o.H[f][S.zero_idx[k]] = 0.f;
         }
     }
-    __syncthreads();
+    __syncthreads();   // Ij (region B) is dead from here on
+    PHASE_MARK(6);
+    // ---- the next tile's measurements and weights: region B is free; the copies land while P5 and the next tile's FK run
+    if (bulk_in && tid == 32) {            // (thread 0 issues the bulk stores of P5 meanwhile)
+        const int tn = tile + gridDim.x;
+        if (tn < n_tiles && (tn + 1) * FT <= n_frames) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_mw(tn);
+        }
+    }
     PHASE_MARK(7);
 
     // ---- P5: write-out.  The staged blocks have the global layout.  Full tiles with 16-byte aligned outputs:
-    //      three bulk async stores (TMA) issued by one thread; otherwise straight vector copies
+    //      three bulk async stores (TMA) issued by one thread (they drain while the next tile starts); otherwise
+    //      straight copies
     if ((use_bulk & 2) && nf == FT) {
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -575,24 +716,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     if (tid == 0 && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// register budget by "at least MINB resident CTAs" ...
-template <int FT, bool WANT_H, int MINB, int NPAIR, bool PERSIST>
+// persistent: one wave of MINB CTAs per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+template <int FT, bool WANT_H, int MINB>
 __global__ void __launch_bounds__(FT * NL, MINB)
 fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
                 const float* __restrict__ xg, const float* __restrict__ meas, const float* __restrict__ wts,
                 float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
-    fte_eval_body<FT, WANT_H, NPAIR, PERSIST>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
+    fte_eval_body<FT, WANT_H>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
 }
-#ifdef ACINO_EXPERIMENTS
-// ... or by an explicit register cap (5 CTAs x 160 threads x 80 registers = 64 000 of the SM's 65 536)
-template <int FT, bool WANT_H, int MAXREG, int NPAIR, bool PERSIST>
-__global__ void __launch_bounds__(FT * NL) __maxnreg__(MAXREG)
-fte_eval_kernel_r(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
-                  const float* __restrict__ xg, const float* __restrict__ meas, const float* __restrict__ wts,
-                  float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
-    fte_eval_body<FT, WANT_H, NPAIR, PERSIST>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
-}
-#endif
 
 #ifdef ACINO_PHASE_TIMING
 extern "C" void acino_debug_phase_cycles(long long* out16) { cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(long long) * 16); }
@@ -658,98 +789,69 @@ using FteKernel = void (*)(const SceneF, int, int, const float*, const float*, c
 
 // per-device launch configuration (cudaFuncSetAttribute is per device; a process may drive several GPUs)
 struct FteDeviceCfg {
-    FteKernel configured[16];
+    FteKernel configured[8];
     int n_configured;
     int n_sm;
 };
 static FteDeviceCfg g_dev_cfg[64];
 
-template <int FT, bool PERSIST>
-static cudaError_t launch_fte_eval_k(FteKernel kH, FteKernel kN, int ctas_per_sm, const SceneF& scene, int n_frames,
-                                     const float* x, const float* meas, const float* w, float* cost, float* g, float* H,
-                                     cudaStream_t stream, int exp_bits, size_t smem_pad) {
+constexpr int FTE_FT = 8;        // frames per tile: 160 threads
+constexpr int FTE_CTAS = 4;      // resident CTAs per SM (96 registers, no spills; 47.9 KB of shared memory each)
+
+template <int FT, int MINB>
+static cudaError_t launch_fte_eval_k(const SceneF& scene, int n_frames, const float* x, const float* meas, const float* w,
+                                     float* cost, float* g, float* H, cudaStream_t stream, int ctas_per_sm, size_t smem_pad) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
     // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
-    int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
-                   (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
-    if ((exp_bits & 1) && (use_bulk & 1)) use_bulk |= 4;      // experiment: L2 prefetch of a later tile
-    if (exp_bits & 2) use_bulk |= 8;                          // experiment: MUFU sin / cos
+    const int use_bulk = (((((uintptr_t)x | (uintptr_t)meas | (uintptr_t)w) & 15u) == 0) ? 1 : 0) |
+                         (((((uintptr_t)cost | (uintptr_t)g | (uintptr_t)H) & 15u) == 0 && FT % 4 == 0) ? 2 : 0);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     FteDeviceCfg& cfg = g_dev_cfg[dev];
+    if (!cfg.n_sm) cudaDeviceGetAttribute(&cfg.n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (n_frames + FT - 1) / FT;
-    int grid = n_tiles;
-    if (PERSIST) {       // one wave of resident CTAs, each walking tiles blockIdx.x, blockIdx.x + grid, ...
-        if (!cfg.n_sm) cudaDeviceGetAttribute(&cfg.n_sm, cudaDevAttrMultiProcessorCount, dev);
-        grid = n_tiles < cfg.n_sm * ctas_per_sm ? n_tiles : cfg.n_sm * ctas_per_sm;
-    }
-    const size_t smem = sizeof(Smem<FT, PERSIST>) + smem_pad;
-    FteKernel k = H ? kH : kN;
+    const int grid = n_tiles < cfg.n_sm * ctas_per_sm ? n_tiles : cfg.n_sm * ctas_per_sm;
+    const size_t smem = sizeof(Smem<FT>) + smem_pad;
+    FteKernel k = H ? (FteKernel)fte_eval_kernel<FT, true, MINB> : (FteKernel)fte_eval_kernel<FT, false, MINB>;
     bool done = false;
     for (int i = 0; i < cfg.n_configured; ++i) done |= cfg.configured[i] == k;
-    if (!done) {
+    if (!done || smem_pad) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (cfg.n_configured < 16) cfg.configured[cfg.n_configured++] = k;
+        if (!done && cfg.n_configured < 8) cfg.configured[cfg.n_configured++] = k;
     }
     k<<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
     return cudaGetLastError();
 }
 
-template <int FT, int MINB, int NPAIR, bool PERSIST>
-static cudaError_t launch_fte_eval_v(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream, int exp_bits = 0,
-                                     size_t smem_pad = 0) {
-    return launch_fte_eval_k<FT, PERSIST>(fte_eval_kernel<FT, true, MINB, NPAIR, PERSIST>, fte_eval_kernel<FT, false, MINB, NPAIR, PERSIST>,
-                                          MINB, scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, smem_pad);
-}
-#ifdef ACINO_EXPERIMENTS
-template <int FT, int MAXREG, int CTAS, int NPAIR, bool PERSIST>
-static cudaError_t launch_fte_eval_r(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                                     const float* w, float* cost, float* g, float* H, cudaStream_t stream, int exp_bits,
-                                     size_t smem_pad) {
-    return launch_fte_eval_k<FT, PERSIST>(fte_eval_kernel_r<FT, true, MAXREG, NPAIR, PERSIST>, fte_eval_kernel_r<FT, false, MAXREG, NPAIR, PERSIST>,
-                                          CTAS, scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, smem_pad);
-}
-#endif
-
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
                             const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
 #ifdef ACINO_EXPERIMENTS
-    // A/B variants of scripts/bench_variants.sh (B200, 256 000 frames, profiles/r01_fte_eval.md); build with
-    // -DACINO_EXPERIMENTS to get the ACINO_FTE_VARIANT / ACINO_FTE_EXP / ACINO_FTE_SMEM_PAD switches:
-    //   0 default 6.45e8 frames/s | 1: 5 CTAs/SM, 72 regs 6.2e8 | 4: 16 frames/CTA 4.8e8 | 5/6: 4 frames/CTA 5.7e8 / 5.4e8
-    //   8: camera-pair loop unrolled 6.4e8 | 9: unrolled, 3 CTAs/SM, 128 regs 5.6e8 | 10: persistent 5.9e8
-    static int variant = -1, exp_bits = 0;
+    // A/B knobs of scripts/bench_variants.sh / bench_residency.sh (build with -DACINO_EXPERIMENTS):
+    //   ACINO_FTE_VARIANT 1: 5 CTAs/SM (<= 80 registers);  ACINO_FTE_CTAS n: grid of n CTAs per SM;
+    //   ACINO_FTE_SMEM_PAD bytes: extra dynamic shared memory per CTA (forces the residency down)
+    static int variant = -1, ctas = 0;
     static size_t pad = 0;
     if (variant < 0) {
         const char* e = getenv("ACINO_FTE_VARIANT");
         variant = e ? atoi(e) : 0;
-        e = getenv("ACINO_FTE_EXP");
-        exp_bits = e ? atoi(e) : 0;
+        e = getenv("ACINO_FTE_CTAS");
+        ctas = e ? atoi(e) : 0;
         e = getenv("ACINO_FTE_SMEM_PAD");
         pad = e ? (size_t)atol(e) : 0;
     }
-    if (variant == 1) return launch_fte_eval_v<8, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 4) return launch_fte_eval_v<16, 2, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 5) return launch_fte_eval_v<4, 9, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 6) return launch_fte_eval_v<4, 10, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 8 && scene.n_cams == 6) return launch_fte_eval_v<8, 4, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 9 && scene.n_cams == 6) return launch_fte_eval_v<8, 3, 3, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 10) return launch_fte_eval_v<8, 4, 0, true>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 11) return launch_fte_eval_r<8, 80, 5, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    if (variant == 12) return launch_fte_eval_r<8, 88, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
-    return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream, exp_bits, pad);
+    if (variant == 1) return launch_fte_eval_k<FTE_FT, 5>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : 5, pad);
+    if (variant == 3) return launch_fte_eval_k<FTE_FT, 3>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : 3, pad);
+    return launch_fte_eval_k<FTE_FT, FTE_CTAS>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : FTE_CTAS, pad);
 #else
-    // 8 frames per CTA, 4 CTAs per SM (96 registers, no spills), runtime camera-pair loop
-    return launch_fte_eval_v<8, 4, 0, false>(scene, n_frames, x, meas, w, cost, g, H, stream);
+    return launch_fte_eval_k<FTE_FT, FTE_CTAS>(scene, n_frames, x, meas, w, cost, g, H, stream, FTE_CTAS, 0);
 #endif
 }
 
-const char* fte_eval_kernel_name(int) { return "fte_eval_kernel<8, 1, 4, 0, 0>"; }
+const char* fte_eval_kernel_name(int) { return "fte_eval_kernel<8, 1, 4>"; }
 
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream) {
