@@ -11,7 +11,7 @@ import os
 import pickle
 
 from .fte import MARKERS, save_3d_cheetah_as_2d, save_fte  # noqa: F401
-from .sba import sba_board_points_fisheye, sba_points_fisheye  # noqa: F401
+from .sba import sba_board_points, sba_board_points_fisheye, sba_points_fisheye  # noqa: F401
 from .stereo import calibrate_fisheye_extrinsics_pairwise, calibrate_standard_extrinsics_pairwise  # noqa: F401
 
 

@@ -83,10 +83,16 @@ def triangulate_pairwise_dense(uv, valid, k_arr, d_arr, r_arr, t_arr, device=0):
 
 
 def get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr, triangulate_func=None, device=0):
-    """Reference signature.  ``triangulate_func`` is accepted for compatibility; the adjacent
-    pairs (i, i+1) are triangulated by one fused kernel (undistort + DLT + fixed-order mean).
+    """Reference signature (calib.py:394-423).  ``triangulate_func`` selects the camera model like in the reference:
+    ``triangulate_points_fisheye`` (or None): the adjacent pairs (i, i+1) are triangulated by one fused kernel
+    (undistort + DLT + fixed-order mean); ``triangulate_points``: the standard model, one two-view launch per adjacent
+    pair and the same fixed-order mean on the host; any other callable raises (no per-point host callback path).
     Prints the same "Found N pairwise points ..." lines as the reference."""
     import pandas as pd
+
+    from .sba import PINHOLE, camera_model
+
+    model = camera_model(None, triangulate_func)
 
     df = points_2d_df
     n_cameras = len(k_arr)
@@ -111,7 +117,20 @@ def get_pairwise_3d_points_from_df(points_2d_df, k_arr, d_arr, r_arr, t_arr, tri
             print(f"No pairwise points between camera {c} and {c + 1}")
     if N * L == 0:
         return pd.DataFrame(columns=["frame", "marker", "x", "y", "z"])
-    pos, cnt = triangulate_pairwise_dense(uv, valid, k_arr, d_arr, r_arr, t_arr, device)
+    if model == PINHOLE:
+        pos = np.zeros((N, L, 3))
+        cnt = np.zeros((N, L), np.int64)
+        for c in range(n_cameras - 1):
+            both = (valid[:, c] & valid[:, c + 1]).astype(bool)
+            if not both.any():
+                continue
+            X = triangulate_points(uv[:, c][both], uv[:, c + 1][both], k_arr[c], d_arr[c], r_arr[c], t_arr[c], k_arr[c + 1],
+                                   d_arr[c + 1], r_arr[c + 1], t_arr[c + 1], device=device)
+            pos[both] += X
+            cnt[both] += 1
+        pos = np.where(cnt[..., None] > 0, pos / np.maximum(cnt, 1)[..., None], np.nan)
+    else:
+        pos, cnt = triangulate_pairwise_dense(uv, valid, k_arr, d_arr, r_arr, t_arr, device)
     fi, mi = np.nonzero(cnt > 0)
     return pd.DataFrame({"frame": frames[fi], "marker": markers[mi],
                          "x": pos[fi, mi, 0], "y": pos[fi, mi, 1], "z": pos[fi, mi, 2]})

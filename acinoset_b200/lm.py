@@ -429,7 +429,7 @@ class FTESolver:
         F0 = float(self.ctl_host[CTL_F])
         launches0 = self.h.launch_count
         cap = max_iter * max_attempts + 2
-        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        evs = []                                      # one timing event after every enqueued attempt
 
         def enqueue(k):
             if self._graph is not None and k > 0:
@@ -456,10 +456,11 @@ class FTESolver:
         k = 0
         while k < cap and max_iter > 0:
             enqueue(k)
-            evs[k & 1].record()
+            evs.append(torch.cuda.Event(enable_timing=True))
+            evs[k].record()
             k += 1
             if k >= 2:
-                evs[k & 1].synchronize()              # attempt k-2 has finished
+                evs[k - 2].synchronize()              # attempt k-2 has finished
                 done_at = int(self.ctl_host[CTL_DONE_AT])
                 if done_at >= 0:
                     while k < done_at + 2:
@@ -469,6 +470,8 @@ class FTESolver:
         torch.cuda.synchronize(self.dev)
         ctl = self.ctl.cpu().numpy()
         n_att = int(ctl[CTL_N_ATTEMPT])
+        # device time of the graph-replayed attempts that did work (attempt 0 is eager + capture, attempts >= n_att idle)
+        att_ms = [evs[i - 1].elapsed_time(evs[i]) for i in range(2, min(n_att, len(evs)))]
         hist = self.hist[:min(n_att, self.HIST_CAP)].cpu().numpy()
         if verbose and self.rank == 0:
             it = 0
@@ -484,5 +487,6 @@ class FTESolver:
                     bcr_info=int(self.info.item()), launches=self.h.launch_count - self.n_launch0,
                     graph=self._graph is not None, attempts_enqueued=k,
                     collectives_per_attempt=0 if self.world == 1 else 2, host_syncs_per_attempt=0,
-                    step=float(ctl[CTL_STEP]))
+                    step=float(ctl[CTL_STEP]),
+                    attempt_ms_steady=float(np.median(att_ms)) if att_ms else None)
         return x, info

@@ -14,7 +14,10 @@ The reference minimises  0.5 sum C^2 ln(1 + (f/C)^2)  (SciPy least_squares, loss
 f_scale=C) with a finite-difference Jacobian over one OpenCV call per observation; here the
 residuals, analytic Jacobian blocks, the per-point Schur complement and the 6C x 6C solve run in
 libacino_b200.so (csrc/sba.cu) inside a Levenberg-Marquardt loop.  ``project_func`` /
-``triangulate_func`` arguments are accepted for signature compatibility.
+``triangulate_func`` select the camera model like in the reference: the fisheye pair
+(``project_points_fisheye`` / ``triangulate_points_fisheye``, also the default) or the standard-model pair
+(``project_points`` / ``triangulate_points``: what ``app.sba_board_points`` passes, app.py:215-218); any other callable
+raises - there is no per-observation host callback path.
 """
 import time
 
@@ -26,6 +29,46 @@ from . import _lib
 
 
 from .rotations import rodrigues_to_mat, rodrigues_to_vec  # noqa: E402,F401
+
+
+# ---- camera model dispatch -------------------------------------------------------------------------------
+FISHEYE, PINHOLE = 0, 1
+
+
+def camera_model(project_func=None, triangulate_func=None):
+    """Camera model the reference's function arguments stand for: FISHEYE (k1..k4, cv2.fisheye) for
+    ``*_fisheye`` or None, PINHOLE (OpenCV's standard model, up to 12 coefficients) for ``project_points`` /
+    ``triangulate_points``.  Matching is by function name, so the reference's own functions select the same model."""
+    names = {getattr(f, "__name__", repr(f)) for f in (project_func, triangulate_func) if f is not None}
+    fish = {"project_points_fisheye", "triangulate_points_fisheye"}
+    pin = {"project_points", "triangulate_points"}
+    if names <= fish:
+        return FISHEYE
+    if names <= pin:
+        return PINHOLE
+    raise NotImplementedError(
+        f"camera functions {sorted(names)}: the GPU bundle adjustment carries the fisheye and the standard OpenCV model "
+        "(calib.project_points[_fisheye] / triangulate_points[_fisheye]); pass one of those pairs")
+
+
+def _triangulate(model):
+    return _calib.triangulate_points if model == PINHOLE else _calib.triangulate_points_fisheye
+
+
+def _dist_table(d_arr, n_cams, model):
+    """(C, n_dist) fp64 coefficient table: 4 fisheye coefficients, or the standard model's up to 12
+    [k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4] zero-padded to the longest camera (tilt terms must be zero)."""
+    if model == FISHEYE:
+        return np.array([np.asarray(d, dtype=np.float64).reshape(-1)[:4] for d in d_arr]).reshape(n_cams, 4)
+    ds = [np.zeros(0) if d is None else np.asarray(d, dtype=np.float64).reshape(-1) for d in d_arr]
+    for d in ds:
+        if d.size > 12 and np.any(d[12:] != 0):
+            raise ValueError("tilted-sensor distortion terms (tauX, tauY) are not supported")
+    nd = max(4, min(12, max(d.size for d in ds)))
+    out = np.zeros((n_cams, nd))
+    for i, d in enumerate(ds):
+        out[i, :min(d.size, nd)] = d[:nd]
+    return out
 
 
 # ---- problem assembly (host) -----------------------------------------------------------------------
@@ -57,6 +100,7 @@ def prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, boar
     estimate triangulated from the FIRST TWO cameras that see the view.  All views of one camera pair
     are triangulated by a single kernel launch.  View order = sorted names (the reference iterates a
     Python set; the cost is order-invariant)."""
+    tri = _triangulate(camera_model(None, triangulate_func))
     n_cam = len(img_pts_arr)
     fnames_arr = [list(f) for f in fnames_arr]
     counts = {}
@@ -79,8 +123,7 @@ def prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, boar
     for (a, b), vs in pair_views.items():
         pa = np.concatenate([np.asarray(img_pts_arr[a][lookup[a][views[v]]], dtype=np.float64).reshape(ppi, 2) for v in vs])
         pb = np.concatenate([np.asarray(img_pts_arr[b][lookup[b][views[v]]], dtype=np.float64).reshape(ppi, 2) for v in vs])
-        X = _calib.triangulate_points_fisheye(pa, pb, k_arr[a], d_arr[a], r_arr[a], t_arr[a], k_arr[b], d_arr[b],
-                                              r_arr[b], t_arr[b])
+        X = tri(pa, pb, k_arr[a], d_arr[a], r_arr[a], t_arr[a], k_arr[b], d_arr[b], r_arr[b], t_arr[b])
         for j, v in enumerate(vs):
             points_3d[v * ppi:(v + 1) * ppi] = X[j * ppi:(j + 1) * ppi]
     if not views:
@@ -91,6 +134,7 @@ def prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, boar
 
 def prepare_manual_points_for_bundle_adjustment(img_pts_arr, k_arr, d_arr, r_arr, t_arr, triangulate_func=None):
     """calib.py:266-304: img_pts_arr (n_points, n_cameras, 2) with NaN where unseen."""
+    tri = _triangulate(camera_model(None, triangulate_func))
     pts = np.asarray(img_pts_arr, dtype=np.float64).swapaxes(0, 1)
     n_cam, n_pts = pts.shape[0], pts.shape[1]
     seen = ~np.isnan(pts).any(axis=2)                       # (n_cam, n_pts)
@@ -108,8 +152,8 @@ def prepare_manual_points_for_bundle_adjustment(img_pts_arr, k_arr, d_arr, r_arr
     for (a, b), lst in first_two.items():
         idx_new = [x[0] for x in lst]
         idx_old = [x[1] for x in lst]
-        X = _calib.triangulate_points_fisheye(pts[a, idx_old], pts[b, idx_old], k_arr[a], d_arr[a], r_arr[a], t_arr[a],
-                                              k_arr[b], d_arr[b], r_arr[b], t_arr[b])
+        X = tri(pts[a, idx_old], pts[b, idx_old], k_arr[a], d_arr[a], r_arr[a], t_arr[a], k_arr[b], d_arr[b], r_arr[b],
+                t_arr[b])
         points_3d[idx_new] = X
     return (np.array(points_2d, dtype=np.float32).reshape(-1, 2), points_3d.astype(np.float32),
             np.array(point_3d_indices, dtype=np.int64), np.array(camera_indices, dtype=np.int64))
@@ -179,7 +223,7 @@ class SBAProblem:
     """Observations + cameras resident on one GPU; evaluates residuals / Jacobian blocks and runs LM."""
 
     def __init__(self, points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, device=0,
-                 with_extrinsics=True, f_scale=1.0, rank=0, world=1, group=None):
+                 with_extrinsics=True, f_scale=1.0, rank=0, world=1, group=None, model=FISHEYE):
         import torch
 
         self.torch = torch
@@ -205,7 +249,10 @@ class SBAProblem:
         self.obs = torch.as_tensor(order).to(dev)
         self.pt_ptr = torch.as_tensor(ptr).to(dev)
         self.K = torch.as_tensor(np.asarray(k_arr, dtype=np.float64).reshape(self.C, 9)).to(dev)
-        self.D = torch.as_tensor(np.asarray(d_arr, dtype=np.float64).reshape(self.C, 4)).to(dev)
+        self.model = int(model)
+        dtab = _dist_table(d_arr, self.C, self.model)
+        self.n_dist = dtab.shape[1]
+        self.D = torch.as_tensor(dtab).to(dev)
         cam_bytes = int(_lib.lib.acino_sba_cam_bytes())
         self.cams = [torch.zeros(self.C * cam_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
         n = self.n_obs
@@ -229,8 +276,9 @@ class SBAProblem:
 
     def set_fixed_cameras(self, r_arr, t_arr):
         t_ = self.torch
-        # the reference's project_func converts every r to a Rodrigues vector and back (calib.py:134):
-        # a slightly non-orthonormal scene matrix is projected onto SO(3) exactly like cv2.Rodrigues does
+        # the reference's project_func converts every r to a Rodrigues vector and back (calib.py:134; cv2.projectPoints
+        # does the same with a matrix argument): a slightly non-orthonormal scene matrix is projected onto SO(3) exactly
+        # like cv2.Rodrigues does
         r_arr = np.array([rodrigues_to_mat(rodrigues_to_vec(r)) for r in np.asarray(r_arr, dtype=np.float64).reshape(-1, 3, 3)])
         self.Rfix = t_.as_tensor(np.asarray(r_arr, dtype=np.float64).reshape(self.C, 9)).to(self.dev)
         self.tfix = t_.as_tensor(np.asarray(t_arr, dtype=np.float64).reshape(self.C, 3)).to(self.dev)
@@ -238,9 +286,11 @@ class SBAProblem:
     # -- evaluation
     def _eval(self, s, want_j=True):
         if self.with_ext:
-            self.h.call_dev("acino_sba_cams_dev", self.C, s["params"], None, None, self.K, self.D, s["cams"])
+            self.h.call_dev("acino_sba_cams_model_dev", self.C, self.model, self.n_dist, s["params"], None, None, self.K,
+                            self.D, s["cams"])
         else:
-            self.h.call_dev("acino_sba_cams_dev", self.C, None, self.Rfix, self.tfix, self.K, self.D, s["cams"])
+            self.h.call_dev("acino_sba_cams_model_dev", self.C, self.model, self.n_dist, None, self.Rfix, self.tfix, self.K,
+                            self.D, s["cams"])
         self.h.call_dev("acino_sba_eval_dev", self.n_obs, s["cams"], s["pts"], self.uv, self.cam_idx, self.pt_idx,
                         self.f_scale, s["res"], (s["Jc"] if self.with_ext else None) if want_j else None,
                         s["Jp"] if want_j else None, s["wgt"] if want_j else None, s["cost"])
@@ -359,19 +409,21 @@ def _dist_ctx():
 
 
 def _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, x_cam0, fixed_rt, f_scale,
-                   max_nfev, ftol, verbose):
+                   max_nfev, ftol, verbose, model=FISHEYE, device=None):
     """Common driver: shard the points over the ranks of the process group (if any), solve, and
-    return the full-size result on every rank."""
+    return the full-size result on every rank.  ``device``: CUDA device index; None = LOCAL_RANK under a process
+    group, else 0."""
     import torch
 
-    rank, world, device = _dist_ctx()
+    rank, world, dev_ctx = _dist_ctx()
+    device = dev_ctx if device is None else int(device)
     n_points = len(points_3d)
     pidx = np.asarray(point_3d_indices, dtype=np.int64)
     cidx = np.asarray(camera_indices, dtype=np.int64)
     p2 = np.asarray(points_2d, dtype=np.float32).reshape(-1, 2)
     p0, npl, ids = shard_points(pidx, n_points, world)[rank]
     prob = SBAProblem(p2[ids], pidx[ids] - p0, cidx[ids], k_arr, d_arr, npl, device=device,
-                      with_extrinsics=fixed_rt is None, f_scale=f_scale, rank=rank, world=world)
+                      with_extrinsics=fixed_rt is None, f_scale=f_scale, rank=rank, world=world, model=model)
     if fixed_rt is not None:
         prob.set_fixed_cameras(*fixed_rt)
     out = prob.solve(x_cam0, np.asarray(points_3d, dtype=np.float64)[p0:p0 + npl], max_nfev=max_nfev, ftol=ftol,
@@ -388,27 +440,30 @@ def _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr
 
 
 def cost_func_points_only(params, n_points, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr, points_2d,
-                          project_func=None):
-    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, with_extrinsics=False)
+                          project_func=None, device=0):
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, with_extrinsics=False,
+                      model=camera_model(project_func), device=device)
     prob.set_fixed_cameras(r_arr, t_arr)
     return prob.residuals(None, params_to_points_only(params, n_points))
 
 
 def cost_func_points_extrinsics(params, n_cameras, n_points, point_3d_indices, camera_indices, k_arr, d_arr, points_2d,
-                                project_func=None):
+                                project_func=None, device=0):
     params = np.asarray(params, dtype=np.float64)
-    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points)
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, model=camera_model(project_func),
+                      device=device)
     return prob.residuals(params[:6 * n_cameras], params[6 * n_cameras:])
 
 
 def jac_points_extrinsics(params, n_cameras, n_points, point_3d_indices, camera_indices, k_arr, d_arr, points_2d,
-                          project_func=None):
+                          project_func=None, device=0):
     """Analytic Jacobian of cost_func_points_extrinsics as a scipy.sparse CSR matrix in the reference's
     parameter layout - a drop-in ``jac=`` for scipy.optimize.least_squares."""
     from scipy.sparse import csr_matrix
 
     params = np.asarray(params, dtype=np.float64)
-    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points)
+    prob = SBAProblem(points_2d, point_3d_indices, camera_indices, k_arr, d_arr, n_points, model=camera_model(project_func),
+                      device=device)
     _, Jc, Jp, _ = prob.jacobian_blocks(params[:6 * n_cameras], params[6 * n_cameras:])
     n = len(point_3d_indices)
     ci = np.asarray(camera_indices, dtype=np.int64)
@@ -426,25 +481,26 @@ def jac_points_extrinsics(params, n_cameras, n_points, point_3d_indices, camera_
 
 
 def bundle_adjust_points_only(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr,
-                              project_func=None, f_scale=50, verbose=0):
+                              project_func=None, f_scale=50, verbose=0, device=None):
     """calib.py:327-341: cauchy f_scale=50, ftol=1e-15, max_nfev=500 -> (obj_pts, residuals)."""
     t0 = time.time()
     out = _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, None, (r_arr, t_arr),
-                         f_scale, 500, 1e-15, verbose)
+                         f_scale, 500, 1e-15, verbose, model=camera_model(project_func), device=device)
     print("Optimization took {0:.0f} seconds".format(time.time() - t0))
     residuals = dict(before=out["f0"], after=out["fun"])
     return out["pts"], residuals
 
 
 def bundle_adjust_board_points_only(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr, r_arr, t_arr, triangulate_func=None,
-                                    project_func=None):
+                                    project_func=None, device=None):
+    camera_model(project_func, triangulate_func)          # one model for both
     p2, p3, pi, ci = prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr,
                                                                     r_arr, t_arr, triangulate_func)
-    return bundle_adjust_points_only(p2, p3, pi, ci, k_arr, d_arr, r_arr, t_arr, project_func)
+    return bundle_adjust_points_only(p2, p3, pi, ci, k_arr, d_arr, r_arr, t_arr, project_func, device=device)
 
 
 def bundle_adjust_points_and_extrinsics(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr, r_arr, t_arr,
-                                        project_func=None, verbose=0, return_info=False):
+                                        project_func=None, verbose=0, return_info=False, device=None):
     """calib.py:369-390: cauchy f_scale=1, ftol=1e-10, max_nfev=1000
     -> (obj_pts (n,3), r_arr (C,3,3), t_arr (C,3,1), residuals dict(before, after))."""
     n_points = len(points_3d)
@@ -453,7 +509,8 @@ def bundle_adjust_points_and_extrinsics(points_2d, points_3d, point_3d_indices, 
     t_vecs = np.asarray(t_arr, dtype=np.float64).flatten()
     t0 = time.time()
     out = _solve_sharded(points_2d, points_3d, point_3d_indices, camera_indices, k_arr, d_arr,
-                         np.concatenate([r_vecs, t_vecs]), None, 1.0, 1000, 1e-10, verbose)
+                         np.concatenate([r_vecs, t_vecs]), None, 1.0, 1000, 1e-10, verbose, model=camera_model(project_func),
+                         device=device)
     print("Optimization took {0:.0f} seconds".format(time.time() - t0))
     obj_pts, r_new, t_new = params_to_points_extrinsics(np.concatenate([out["params"], out["pts"].ravel()]), n_cameras,
                                                         n_points)
@@ -464,15 +521,40 @@ def bundle_adjust_points_and_extrinsics(points_2d, points_3d, point_3d_indices, 
 
 
 def bundle_adjust_board_points_and_extrinsics(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr, r_arr, t_arr,
-                                              triangulate_func=None, project_func=None):
+                                              triangulate_func=None, project_func=None, device=None):
+    camera_model(project_func, triangulate_func)          # one model for both
     p2, p3, pi, ci = prepare_calib_board_data_for_bundle_adjustment(img_pts_arr, fnames_arr, board_shape, k_arr, d_arr,
                                                                     r_arr, t_arr, triangulate_func)
-    return bundle_adjust_points_and_extrinsics(p2, p3, pi, ci, k_arr, d_arr, r_arr, t_arr, project_func)
+    return bundle_adjust_points_and_extrinsics(p2, p3, pi, ci, k_arr, d_arr, r_arr, t_arr, project_func, device=device)
+
+
+def _sba_board_points(scene_fpath, points_fpaths, out_fpath, triangulate_func, project_func, device=None):
+    """app.py:201-213: load points + scene, refine points and extrinsics, save the ``*_sba.json`` scene."""
+    from . import utils
+
+    img_pts_arr, fnames_arr = [], []
+    board_shape = None
+    for fp in points_fpaths:
+        points, fnames, board_shape, _, _ = utils.load_points(fp)
+        img_pts_arr.append(points)
+        fnames_arr.append(fnames)
+    k_arr, d_arr, r_arr, t_arr, cam_res = utils.load_scene(scene_fpath)
+    assert len(k_arr) == len(points_fpaths)
+    obj_pts, r_new, t_new, res = bundle_adjust_board_points_and_extrinsics(img_pts_arr, fnames_arr, board_shape, k_arr,
+                                                                           d_arr, r_arr, t_arr, triangulate_func,
+                                                                           project_func, device=device)
+    utils.save_scene(out_fpath, k_arr, d_arr, r_new, t_new, cam_res)
+    return res
+
+
+def sba_board_points(scene_fpath, points_fpaths, out_fpath, device=None):
+    """app.py:215-218: the standard-camera-model bundle adjustment (cv2.projectPoints / cv2.undistortPoints model)."""
+    return _sba_board_points(scene_fpath, points_fpaths, out_fpath, _calib.triangulate_points, _calib.project_points, device)
 
 
 def sba_board_points_fisheye(scene_fpath, points_fpaths, out_fpath, manual_points_fpath=None,
-                             manual_points_only=False):
-    """app.py:201-223: load points + scene, refine extrinsics, save the ``*_sba.json`` scene."""
+                             manual_points_only=False, device=None):
+    """app.py:220-223 (fisheye model)."""
     from . import utils
 
     img_pts_arr, fnames_arr = [], []
@@ -484,7 +566,7 @@ def sba_board_points_fisheye(scene_fpath, points_fpaths, out_fpath, manual_point
     k_arr, d_arr, r_arr, t_arr, cam_res = utils.load_scene(scene_fpath)
     assert len(k_arr) == len(img_pts_arr)
     obj_pts, r_new, t_new, res = bundle_adjust_board_points_and_extrinsics(img_pts_arr, fnames_arr, board_shape, k_arr,
-                                                                           d_arr, r_arr, t_arr)
+                                                                           d_arr, r_arr, t_arr, device=device)
     utils.save_scene(out_fpath, k_arr, d_arr, r_new, t_new, cam_res)
     return res
 
@@ -509,6 +591,6 @@ def sba_points_fisheye(scene_fpath, points_2d_df, device=0):
     camera_indices = points_df["camera"].to_numpy(dtype=np.int64)
     points_3d = points_3d_df[["x", "y", "z"]].to_numpy(dtype=np.float32)
     pts, residuals = bundle_adjust_points_only(points_2d, points_3d, point_indices, camera_indices, k_arr, d_arr, r_arr,
-                                               t_arr)
+                                               t_arr, device=device)
     points_3d_df[["x", "y", "z"]] = pts
     return points_3d_df, residuals

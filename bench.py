@@ -168,6 +168,10 @@ def lm_solve_block(handle, n_frames, rank, world, dev, with_rms=True, max_iter=6
     dt = _max_over_ranks(time.perf_counter() - t0, dev, world)
     out = {"frames": n_frames, "gpus": world, "frames_per_gpu": n, "lm_iters_per_sec": info["n_solve"] / dt,
            "attempts_per_sec": info["n_solve"] / dt, "ms_per_attempt": 1e3 * dt / info["n_solve"],
+           "ms_per_attempt_steady": _max_over_ranks(info.get("attempt_ms_steady") or 0.0, dev, world),
+           "ms_per_attempt_how": "ms_per_attempt = wall time of the whole solve (first eager attempt and graph capture "
+                                 "included) / attempts; _steady = median device time (CUDA events) of the graph-replayed "
+                                 "attempts, max over ranks",
            "attempts": info["n_solve"], "accepted_iterations": info["iters"], "seconds_to_converge": dt,
            "F": info["F"], "converged": bool(info["converged"]), "bcr_info": info["bcr_info"],
            "collectives_per_attempt": info.get("collectives_per_attempt"), "cuda_graph": info.get("graph"),
@@ -704,9 +708,15 @@ def run_ours(args):
             except Exception as e:  # the baseline is a reported extra, never the measured path
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
     h.close()
+    if world > 1:
+        # every rank is done (the JSON line is out): leave without NCCL's communicator teardown, which has been seen to block
+        # after graph-captured collectives (tests/_mgpu_worker.py) - a hung bench would cost the whole scaling record
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -242,3 +242,35 @@ def test_fte_solve_matches_cpu_restatement(handle, dummy_cams, N):
     assert np.sqrt(((P - Pt) ** 2).sum(-1).mean()) < 0.01
     lo, hi = skeleton.active_bounds()
     assert (x >= lo - 1e-12).all() and (x <= hi + 1e-12).all()
+
+
+@pytest.mark.parametrize("N,seed", [(48, 5), (100, 6)])
+def test_fte_solve_reaches_independent_optimum(handle, dummy_cams, N, seed):
+    """Solve pin against an INDEPENDENT optimiser (tests/golden/solves.npz: SciPy's More-Sorensen trust-region Newton on
+    the oracle's fp64 objective from the same start, tests/golden/make_golden_solves.py): the GPU's end point, judged by
+    the same fp64 objective, is at least as low (1e-6 relative) and its markers agree to 1e-3 m."""
+    import synth
+    from conftest import golden
+    from acinoset_b200 import lm
+    from oracle import fisheye, fte as ofte, skeleton
+
+    g = golden("solves.npz")
+    assert int(g[f"fte{N}_seed"]) == seed
+    p = synth.make_fte_problem(N, skeleton.cheetah_fk_active, fisheye.project, seed=seed, cams=dummy_cams)
+    sol = lm.FTESolver(handle, p["meas"], p["w"], p["Ts"])
+    x, info = sol.solve(p["x0"], max_iter=60)
+    assert info["bcr_info"] == 0 and info["converged"]
+    K, D, R, t, _ = dummy_cams
+    meas = p["meas"].astype(np.float32).astype(np.float64)
+    w = p["w"].astype(np.float32).astype(np.float64)
+    q = ofte.model_weights_active()
+
+    def F64(xx):
+        c, _, _ = ofte.fte_eval(xx, meas, w, K, D, R, t)
+        return float(c.sum()) + ofte.smooth_cost(xx, p["Ts"], q)
+
+    F_scipy = float(g[f"fte{N}_F"])
+    assert abs(F64(g[f"fte{N}_x"]) - F_scipy) < 1e-9 * F_scipy          # the fixture is what the script computed
+    assert F64(x) <= F_scipy * (1 + 1e-6), (F64(x), F_scipy)
+    P, Ps = skeleton.cheetah_fk_active(x), skeleton.cheetah_fk_active(g[f"fte{N}_x"])
+    assert np.abs(P - Ps).max() < 1e-3, np.abs(P - Ps).max()
