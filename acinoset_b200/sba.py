@@ -268,11 +268,17 @@ class SBAProblem:
         self.Sr = buf(n6 * n6 + n6)                 # [S | rhs]: one buffer = one all_reduce when sharded
         self.S = self.Sr[:n6 * n6].view(n6, n6)
         self.dc = self.Sr[n6 * n6:]
-        self.sc4 = buf(4)
         self.partial = buf(int(_lib.lib.acino_sba_schur_partial_size(self.n_pts, self.C)))
-        self.out5 = buf(5)
+        self.scal = buf(9)                          # [lm_reduce out5 | step / state norms]: ONE device->host copy per attempt
+        self.out5 = self.scal[:5]
+        self.sc4 = self.scal[5:]
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         self.Rfix = self.tfix = None
+        # pinned host mirrors of the solve's results (residuals before / after: 16 bytes per observation - pageable
+        # copies of these were two thirds of the wall time of a configs[3] solve)
+        self._host = dict(f0=torch.empty((n, 2), dtype=f64).pin_memory(), fun=torch.empty((n, 2), dtype=f64).pin_memory(),
+                          pts=torch.empty((self.n_pts, 3), dtype=f64).pin_memory(),
+                          params=torch.empty(6 * self.C, dtype=f64).pin_memory())
 
     def set_fixed_cameras(self, r_arr, t_arr):
         t_ = self.torch
@@ -295,12 +301,29 @@ class SBAProblem:
                         self.f_scale, s["res"], (s["Jc"] if self.with_ext else None) if want_j else None,
                         s["Jp"] if want_j else None, s["wgt"] if want_j else None, s["cost"])
 
-    def _sum(self, a1, a2=None):
-        """Fixed-order local sums (+ one small all_reduce when the points are sharded)."""
+    def _sum(self, a1, a2=None, norms_of=None):
+        """Fixed-order local sums (+ one small all_reduce when the points are sharded) -> (sum a1, sum a2[, |dp|^2,
+        |pts|^2, |dc|^2, |params|^2 of the trial state ``norms_of``]) with a single device->host copy."""
         self.h.call_dev("acino_lm_reduce_dev", self.n_obs, None, a1, a2, None, None, self.out5)
-        allreduce_scalars(self.out5[1:3], self.world, self.group)
-        o = self.out5.cpu().numpy()
-        return float(o[1]), float(o[2])
+        if norms_of is not None:
+            t_ = self.torch
+            t_.sum(self.dp * self.dp, dim=None, out=self.sc4[0])
+            t_.sum(norms_of["pts"] * norms_of["pts"], dim=None, out=self.sc4[1])
+            if self.with_ext:
+                t_.sum(self.dc * self.dc, dim=None, out=self.sc4[2])
+                t_.sum(norms_of["params"] * norms_of["params"], dim=None, out=self.sc4[3])
+            if self.world > 1:
+                self._allreduce_scal()
+        else:
+            allreduce_scalars(self.out5[1:3], self.world, self.group)
+        o = self.scal.cpu().numpy()
+        return (float(o[1]), float(o[2])) if norms_of is None else (float(o[1]), float(o[2]), o[5:9].copy())
+
+    def _allreduce_scal(self):
+        """cost / pred / point-step / point-state sums are sharded over the ranks; the camera norms are replicated."""
+        v = self.scal[[1, 2, 5, 6]]
+        allreduce_scalars(v, self.world, self.group)
+        self.scal[[1, 2, 5, 6]] = v
 
     def residuals(self, params_c, pts):
         """f (2 n_obs,) at the given parameters (no Jacobian)."""
@@ -331,8 +354,8 @@ class SBAProblem:
             s["params"].copy_(t_.as_tensor(np.asarray(params_c0, dtype=np.float64)).to(self.dev))
         s["pts"].copy_(t_.as_tensor(np.asarray(pts0, dtype=np.float64).reshape(-1, 3)).to(self.dev))
         self._eval(s)
+        self._host["f0"].copy_(s["res"], non_blocking=True)       # lands before the first host sync below
         F, _ = self._sum(s["cost"])
-        f0 = s["res"].cpu().numpy().ravel().copy()
         F0 = F
         lam = lam0
         nfev, it = 1, 0
@@ -358,18 +381,15 @@ class SBAProblem:
                     t_.add(s["params"], self.dc.view(self.C, 2, 3).transpose(0, 1).reshape(-1), out=t["params"])
                 self._eval(t)
                 nfev += 1
-                Ft, pred = self._sum(t["cost"], self.pred)
+                Ft, pred, nrm = self._sum(t["cost"], self.pred, norms_of=t)
                 rho = (F - Ft) / pred if pred > 0 else -1.0
                 if verbose >= 2:
                     print(f"   it {it:4d} nfev {nfev:4d} lam {lam:9.2e} cost {F:.6e} -> {Ft:.6e} pred {pred:9.2e} rho {rho:6.3f}")
                 if Ft < F and rho > 1e-4:
                     accepted = True
                     dF = F - Ft
-                    self.sc4[0] = (self.dp ** 2).sum()
-                    self.sc4[1] = (t["pts"] ** 2).sum()
-                    allreduce_scalars(self.sc4[:2], self.world, self.group)      # point parts are sharded
-                    xs = float(t_.sqrt(self.sc4[0] + ((self.dc ** 2).sum() if self.with_ext else 0.0)).item())
-                    xn = float(t_.sqrt(self.sc4[1] + ((t["params"] ** 2).sum() if self.with_ext else 0.0)).item())
+                    xs = float(np.sqrt(nrm[0] + (nrm[2] if self.with_ext else 0.0)))
+                    xn = float(np.sqrt(nrm[1] + (nrm[3] if self.with_ext else 0.0)))
                     F = Ft
                     s, t = t, s
                     lam = max(lam / 3, 1e-15) if rho > 0.75 else (lam * 2 if rho < 0.25 else lam)
@@ -387,9 +407,16 @@ class SBAProblem:
                 status = "xtol"
                 break
         self.st = [s, t]
+        hb = self._host
+        hb["params"].copy_(s["params"], non_blocking=True)
+        hb["pts"].copy_(s["pts"], non_blocking=True)
+        hb["fun"].copy_(s["res"], non_blocking=True)
+        info = int(self.info.item())                                # (synchronises the stream: the copies above are done)
         t_.cuda.synchronize(self.dev)
-        return dict(params=s["params"].cpu().numpy(), pts=s["pts"].cpu().numpy(), fun=s["res"].cpu().numpy().ravel(),
-                    f0=f0, cost0=F0, cost=F, nfev=nfev, iters=it, status=status, info=int(self.info.item()))
+        # the arrays handed out ARE the pinned mirrors (no second host copy of 16 bytes per observation): they stay valid
+        # until the next solve() of this object overwrites them - the reference-named entry points build one object per call
+        return dict(params=hb["params"].numpy().copy(), pts=hb["pts"].numpy(), fun=hb["fun"].numpy().ravel(),
+                    f0=hb["f0"].numpy().ravel(), cost0=F0, cost=F, nfev=nfev, iters=it, status=status, info=info)
 
 
 # ---- reference-named entry points ------------------------------------------------------------------

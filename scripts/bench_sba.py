@@ -57,3 +57,23 @@ print(json.dumps({"views": p["n_views"], "n_obs": n_obs, "n_pts": n_pts, "eval_m
                   "eval_GBps_at_176B_per_obs": n_obs * 176 / (ms_eval * 1e-3) / 1e9, "solve_s": dt, "nfev": out["nfev"], "iters": out["iters"],
                   "lm_iters_per_sec": out["nfev"] / dt, "cost0": out["cost0"], "cost": out["cost"], "status": out["status"],
                   "max_rel_rot_err_deg": [err_rot0, err_rot], "max_rel_trans_err_m": [err_t0, err_t]}))
+# ---- per-kernel device times of one LM attempt (CUDA events, 20 repetitions each, state after the solve)
+def timed(fn, reps=20):
+    for _ in range(2): fn()
+    torch.cuda.synchronize(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return 1e3 * a.elapsed_time(b) / reps
+s, t = prob.st
+n6 = 6 * prob.C
+lam = 1e-3
+ph = {
+    "sba_schur (+reduce)": lambda: prob.h.call_dev("acino_sba_schur_dev", prob.n_pts, prob.C, prob.pt_ptr, prob.obs, prob.cam_idx, s["res"], s["Jc"], s["Jp"], s["wgt"], lam, prob.partial, prob.S, prob.dc),
+    "sba_dense_solve": lambda: prob.h.call_dev("acino_sba_dense_solve_dev", n6, prob.S, prob.dc, prob.info),
+    "sba_backsub": lambda: prob.h.call_dev("acino_sba_backsub_dev", prob.n_pts, prob.C, prob.pt_ptr, prob.obs, prob.cam_idx, s["res"], s["Jc"], s["Jp"], s["wgt"], lam, prob.dc, s["pts"], t["pts"], prob.dp),
+    "sba_pred": lambda: prob.h.call_dev("acino_sba_pred_dev", prob.n_obs, prob.cam_idx, prob.pt_idx, s["res"], s["Jc"], s["Jp"], s["wgt"], prob.dc, prob.dp, prob.pred),
+    "sba_cams + sba_eval": lambda: prob._eval(t),
+    "lm_reduce + norms + D2H": lambda: prob._sum(t["cost"], prob.pred, norms_of=t),
+}
+print(json.dumps({"phase_us": {k: round(timed(v), 1) for k, v in ph.items()}}))
