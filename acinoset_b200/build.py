@@ -32,9 +32,11 @@ from . import calib, skeleton, utils
 from . import fte as _fte
 from .skeleton import load_skeleton  # noqa: F401
 
-MODEL_WEIGHT = 0.002
-MEAS_SIGMA_R = 3.0
-LIK_THRESH = 0.4
+from .config import SKELETON  # noqa: E402
+
+MODEL_WEIGHT = SKELETON.model_weight
+MEAS_SIGMA_R = SKELETON.meas_sigma_px
+LIK_THRESH = SKELETON.lik_thresh
 
 
 @dataclass

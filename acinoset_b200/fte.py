@@ -22,7 +22,9 @@ MARKERS = [
 ]
 # indices of the 25 active slots in the reference's 45-vector [x,y,z,*phi(14),*theta(14),*psi(14)]
 ACTIVE_IDX = np.array([0, 1, 2, 3, 4, 6] + list(range(17, 31)) + [31, 32, 34, 35, 36])
-MEAS_SIGMA_R = 5.0  # all_optimizations.py:243
+from .config import CHEETAH  # noqa: E402
+
+MEAS_SIGMA_R = CHEETAH.meas_sigma_px  # all_optimizations.py:243
 
 _handles = {}
 

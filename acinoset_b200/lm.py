@@ -35,27 +35,16 @@ from . import _lib
 NA = _lib.N_ACTIVE
 SB = _bcr.SB
 
-# measurement-model std-devs (all_optimizations.py:245-252), active slots only; weight = 1/sigma^2
-Q_SIGMA_ACTIVE = np.array([4, 7, 5, 13, 32, 10, 9, 18, 43, 53, 90, 118, 247, 186, 194, 164, 295, 243, 334, 149,
-                           26, 12, 34, 43, 51], dtype=np.float64)
-_P6, _P15, _P2, _PI = np.pi / 6, np.pi / 1.5, np.pi / 2, np.pi
+from .config import CHEETAH
+
+# model std-devs (all_optimizations.py:245-252), active slots only; weight = 1/sigma^2 (one definition: config.py)
+Q_SIGMA_ACTIVE = CHEETAH.q_sigma
 
 
 def default_bounds():
     """(lo, hi)[25] of all_optimizations.py:403-483 in the active ordering; +-inf where free."""
-    lo = np.full(NA, -np.inf)
-    hi = np.full(NA, np.inf)
-    for i in (3, 4, 5, 6, 7, 8, 9, 21, 22):          # phi0 phi1 phi3 theta0..3 psi1 psi3
-        lo[i], hi[i] = -_P6, _P6
-    for i in (10, 11, 23, 24):                        # theta4 theta5 psi4 psi5
-        lo[i], hi[i] = -_P15, _P15
-    for i in (12, 14, 16, 18):                        # shoulders / hips
-        lo[i], hi[i] = -_P2, _P2
-    for i in (13, 15):                                # front knees
-        lo[i], hi[i] = -_PI, 0.0
-    for i in (17, 19):                                # back knees
-        lo[i], hi[i] = 0.0, _PI
-    return lo, hi
+    lo, hi = CHEETAH.bounds
+    return lo.copy(), hi.copy()
 
 
 def shard_frames(n_global, world):
@@ -399,8 +388,9 @@ class FTESolver:
         return 1e3 * e0.elapsed_time(e1) / reps
 
     # -- the loop -------------------------------------------------------------------------------
-    def solve(self, x0, max_iter=60, lam0=1e-3, tol_step=1e-6, tol_rel=1e-7, max_attempts=12, verbose=False,
-              tol_noise=5e-8):
+    def solve(self, x0, max_iter=CHEETAH.lm_max_iter, lam0=CHEETAH.lm_lam0, tol_step=CHEETAH.lm_tol_step,
+              tol_rel=CHEETAH.lm_tol_rel, max_attempts=CHEETAH.lm_max_attempts, verbose=False,
+              tol_noise=CHEETAH.lm_tol_noise):
         """Stops when an accepted step moves no variable by more than tol_step, or lowers F by less than tol_rel * F,
         or when two consecutive REJECTED trial points differ from F by less than tol_noise * F (the measurement term
         is evaluated in fp32: ~6e-8 relative resolution per frame), or after max_attempts rejections in a row, or

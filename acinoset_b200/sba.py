@@ -276,9 +276,7 @@ class SBAProblem:
         self.Rfix = self.tfix = None
         # pinned host mirrors of the solve's results (residuals before / after: 16 bytes per observation - pageable
         # copies of these were two thirds of the wall time of a configs[3] solve)
-        self._host = dict(f0=torch.empty((n, 2), dtype=f64).pin_memory(), fun=torch.empty((n, 2), dtype=f64).pin_memory(),
-                          pts=torch.empty((self.n_pts, 3), dtype=f64).pin_memory(),
-                          params=torch.empty(6 * self.C, dtype=f64).pin_memory())
+        self._host = None                           # allocated by the first solve (residuals() / jacobian_blocks() need none)
 
     def set_fixed_cameras(self, r_arr, t_arr):
         t_ = self.torch
@@ -350,6 +348,12 @@ class SBAProblem:
     def solve(self, params_c0, pts0, max_nfev=1000, ftol=1e-10, xtol=1e-8, lam0=1e-3, verbose=0):
         t_ = self.torch
         s, t = self.st
+        if self._host is None:
+            f64 = t_.float64
+            self._host = dict(f0=t_.empty((self.n_obs, 2), dtype=f64).pin_memory(),
+                              fun=t_.empty((self.n_obs, 2), dtype=f64).pin_memory(),
+                              pts=t_.empty((self.n_pts, 3), dtype=f64).pin_memory(),
+                              params=t_.empty(6 * self.C, dtype=f64).pin_memory())
         if self.with_ext:
             s["params"].copy_(t_.as_tensor(np.asarray(params_c0, dtype=np.float64)).to(self.dev))
         s["pts"].copy_(t_.as_tensor(np.asarray(pts0, dtype=np.float64).reshape(-1, 3)).to(self.dev))
