@@ -162,6 +162,12 @@ __device__ __forceinline__ float fast_rsqrt(float x) {   // MUFU.RSQ, no denorma
     return y;
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {     // MUFU.EX2 without exp2f's denormal-range rescaling
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // atan(r) for r >= 0 given ir = 1/r: degree-7 polynomial in z^2 on z = min(r, 1/r) in [0,1]
 // (Chebyshev-node fit, max abs error 1.2e-7), atan(r) = pi/2 - atan(1/r) for r > 1.
 __device__ __forceinline__ float atan_pos(float r, float ir) {
@@ -268,7 +274,7 @@ __device__ __forceinline__ f2 atan_pos2(f2 r, f2 ir) {
 // redescending_fast on a pair of e values in [tiny, 40]
 __device__ __forceinline__ void redescending_fast2(const LossF& L, const f2 e, f2& rho, f2& psi_raw, f2& floor_) {
     const f2 ne = mul2(e, bc(-1.4426950408889634f));
-    const f2 E = pk(exp2f(lo(ne)), exp2f(hi(ne)));
+    const f2 E = pk(fast_ex2(lo(ne)), fast_ex2(hi(ne)));       // e <= 40: 2^-58, far from the denormal range exp2f guards
     const f2 one = bc(1.0f);
     const f2 sa = rcp2(fma2(E, bc(L.ea), one));
     const f2 sb = rcp2(fma2(E, bc(L.eb), one));

@@ -47,14 +47,15 @@ constexpr int k_trunk_slot[N_TRUNK] = {0, 3, 17, 1, 4, 18};     // phi0 theta0 p
 constexpr int trunk_slot(int k) { return k == 0 ? 0 : k == 1 ? 3 : k == 2 ? 17 : k == 3 ? 1 : k == 4 ? 4 : 18; }
 constexpr int MAX_ANC = 8;
 constexpr int N_ZERO = N_PAIR - 185;
-struct ColEntry {                       // 48 bytes: three 16-byte loads
-    unsigned char slot, joint, n_anc, pad0;
-    unsigned short trunk_idx[N_TRUNK];  // packed-H index of (trunk slot k, be); 0xFFFF: not a related pair in this order
-    unsigned char anc[MAX_ANC];         // non-trunk ancestor-or-self slots (unused: 0)
-    unsigned short anc_idx[MAX_ANC];    // their packed-H indices
-    unsigned pad1[2];
+constexpr unsigned NO_ENTRY = 0xFFFFu;
+struct ColEntry {                       // 112 bytes of ready-to-use 32-bit words: seven 16-byte loads, no field extraction
+    unsigned tau_off, ij_off, n_anc, slot;   // be * TAU_STRIDE, joint * (NSP + 1) (float offsets), list length, be
+    unsigned trunk_idx[N_TRUNK];        // packed-H index of (trunk slot k, be); NO_ENTRY: not a related pair in this order
+    unsigned pad0[2];
+    unsigned anc_off[MAX_ANC];          // non-trunk ancestor-or-self slots as float offsets al * TAU_STRIDE (unused: 0)
+    unsigned anc_idx[MAX_ANC];          // their packed-H indices
 };
-static_assert(sizeof(ColEntry) == 48, "ColEntry layout");
+static_assert(sizeof(ColEntry) == 112, "ColEntry layout");
 struct ColTable {
     ColEntry col[NANG];
     unsigned short zero_idx[N_ZERO + 4];
@@ -94,21 +95,22 @@ constexpr ColTable make_col_table() {
         // first round: the four lightest columns, then the 16 heaviest; second round (q = 20, 21): two light ones
         const int be = order[q < 4 ? q : (q < 20 ? q + 2 : q - 16)];
         ColEntry& c = t.col[q];
-        c.slot = (unsigned char)be;
-        c.joint = (unsigned char)k_angle_joint[be];
+        c.slot = (unsigned)be;
+        c.tau_off = (unsigned)(be * TAU_STRIDE);
+        c.ij_off = (unsigned)(k_angle_joint[be] * (NSP + 1));
         for (int k = 0; k < N_TRUNK; ++k) {
             const bool on = related(k_trunk_slot[k], be);
-            c.trunk_idx[k] = on ? packed_index(k_trunk_slot[k], be) : (unsigned short)0xFFFF;
+            c.trunk_idx[k] = on ? packed_index(k_trunk_slot[k], be) : NO_ENTRY;
             n_rel += on;
         }
         int n = 0;
         for (int al = 0; al < NANG; ++al)
             if (related(al, be) && !is_trunk_slot(al)) {
-                c.anc[n] = (unsigned char)al;
+                c.anc_off[n] = (unsigned)(al * TAU_STRIDE);
                 c.anc_idx[n] = packed_index(al, be);
                 ++n;
             }
-        c.n_anc = (unsigned char)n;
+        c.n_anc = (unsigned)n;
         n_rel += n;
     }
     int nz = 0;
@@ -131,7 +133,7 @@ static_assert(max_anc_len() == MAX_ANC, "kinematic tree changed: check the colum
 static_assert(make_col_table().n_rel == 185 * 1000 + N_ZERO, "kinematic tree changed: 185 related + 68 unrelated pairs");
 __constant__ ColTable c_col = make_col_table();
 __device__ __align__(16) const ColTable d_col = make_col_table();     // global-memory copy: source of the bulk (TMA) copy
-constexpr unsigned COL_BYTES = sizeof(ColEntry) * NANG + sizeof(unsigned short) * (N_ZERO + 4);   // 1056 + 144
+constexpr unsigned COL_BYTES = sizeof(ColEntry) * NANG + sizeof(unsigned short) * (N_ZERO + 4);   // 2464 + 144
 static_assert(COL_BYTES % 16 == 0, "bulk copy size");
 
 // the 16 angle slots whose rotation does not pivot on the head point: (slot, pivot marker) - v = pivot x omega is formed
@@ -606,15 +608,15 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             continue;
         }
         const uint4* ce = reinterpret_cast<const uint4*>(&S.col[q]);
-        const uint4 e0 = ce[0];            // slot, joint, n_anc | trunk_idx[0..5]
-        const int be = e0.x & 0xFFu, jb = (e0.x >> 8) & 0xFFu, n_anc = (e0.x >> 16) & 0xFFu;
-        const float4* I4 = reinterpret_cast<const float4*>(&S.Ij[f][jb * (NSP + 1)]);
+        const uint4 e0 = ce[0];            // tau offset, Ij offset, list length, slot
+        const int be = e0.w, n_anc = e0.z;
+        const float4* I4 = reinterpret_cast<const float4*>(&S.Ij[f][e0.y]);
         const float4 i0 = I4[0], i1 = I4[1], i2 = I4[2], i3 = I4[3], i4 = I4[4], i5 = I4[5], i6 = I4[6];
         const float I[28] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y,
                              i3.z, i3.w, i4.x, i4.y, i4.z, i4.w, i5.x, i5.y, i5.z, i5.w, i6.x, i6.y, i6.z, i6.w};
         const float* tau_f = &S.tau[f][0];
-        const float4 t0 = *reinterpret_cast<const float4*>(tau_f + be * TAU_STRIDE);
-        const float2 t1 = *reinterpret_cast<const float2*>(tau_f + be * TAU_STRIDE + 4);
+        const float4 t0 = *reinterpret_cast<const float4*>(tau_f + e0.x);
+        const float2 t1 = *reinterpret_cast<const float2*>(tau_f + e0.x + 4);
         const float o0 = t0.x, o1 = t0.y, o2 = t0.z, v0 = t0.w, v1 = t1.x, v2 = t1.y;
         const float gb = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
         if (!WANT_H) {
@@ -636,15 +638,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             ht[k] = a0.x * yt0 + a0.y * yt1 + a0.z * yt2;
         }
         // the other ancestors (and beta itself): full 6-term products
-        const uint4 e1 = ce[1];            // anc[0..7] | anc_idx[0..3]
-        const uint2 e2 = *reinterpret_cast<const uint2*>(&ce[2]);     // anc_idx[4..7]
+        const uint4 a0_ = ce[3], a1_ = ce[4];           // anc_off[0..7]
+        const unsigned ao[MAX_ANC] = {a0_.x, a0_.y, a0_.z, a0_.w, a1_.x, a1_.y, a1_.z, a1_.w};
         float ha[MAX_ANC];
 #pragma unroll
         for (int k = 0; k < MAX_ANC; ++k) {
             if (!__any_sync(__activemask(), k < n_anc)) break;     // (executing all 8 for every column measured 4 % slower)
-            const unsigned al = ((k < 4 ? e1.x : e1.y) >> (8 * (k & 3))) & 0xFFu;
-            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + al * TAU_STRIDE);
-            const float2 a1 = *reinterpret_cast<const float2*>(tau_f + al * TAU_STRIDE + 4);
+            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + ao[k]);
+            const float2 a1 = *reinterpret_cast<const float2*>(tau_f + ao[k] + 4);
             ha[k] = a0.x * yt0 + a0.y * yt1 + a0.z * yt2 + a0.w * yb0 + a1.x * yb1 + a1.y * yb2;
         }
         // stores last: no store -> load ordering inside the task
@@ -653,17 +654,17 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         H[sb] = yb0;
         H[NA + sb - 1] = yb1;
         H[2 * NA + sb - 3] = yb2;
-        const unsigned ti[3] = {e0.y, e0.z, e0.w};
+        const uint4 t0_ = ce[1];
+        const uint2 t1_ = *reinterpret_cast<const uint2*>(&ce[2]);
+        const unsigned ti[N_TRUNK] = {t0_.x, t0_.y, t0_.z, t0_.w, t1_.x, t1_.y};
 #pragma unroll
-        for (int k = 0; k < N_TRUNK; ++k) {
-            const unsigned idx = (ti[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            if (idx != 0xFFFFu) H[idx] = ht[k];
-        }
-        const unsigned ai[4] = {e1.z, e1.w, e2.x, e2.y};
+        for (int k = 0; k < N_TRUNK; ++k)
+            if (ti[k] != NO_ENTRY) H[ti[k]] = ht[k];
+        const uint4 i0_ = ce[5], i1_ = ce[6];           // anc_idx[0..7]
+        const unsigned ai[MAX_ANC] = {i0_.x, i0_.y, i0_.z, i0_.w, i1_.x, i1_.y, i1_.z, i1_.w};
 #pragma unroll
-        for (int k = 0; k < MAX_ANC; ++k) {
-            if (k < n_anc) H[(ai[k >> 1] >> (16 * (k & 1))) & 0xFFFFu] = ha[k];
-        }
+        for (int k = 0; k < MAX_ANC; ++k)
+            if (k < n_anc) H[ai[k]] = ha[k];
     }
     // structural zeros of H: N_ZERO entries per frame, no arithmetic
     if (WANT_H) {
