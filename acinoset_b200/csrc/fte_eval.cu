@@ -6,11 +6,12 @@
 // automatic differentiation IPOPT's ASL performs on those expression trees each iteration.
 //
 // Layout / mapping (B200, CUDA cores only - the contraction is tiny, irregular and sparse):
-//   one CTA = FT frames.  Phases, separated by __syncthreads():
-//   P1  FK            thread <-> frame           22 sincos, rotation chain in registers,
-//                                                writes marker positions (relative to the head)
-//                                                and one twist (omega, pivot x omega) per angle
-//   P2  projection    thread <-> (frame, marker) loops over cameras: fisheye projection, 2x3
+//   persistent CTAs (one wave, 4 per SM), one tile = FT frames = FT * 20 threads.  Phases, separated by __syncthreads():
+//   P1a sin / cos     thread <-> (angle, frame)
+//   P1b FK            3 threads <-> frame        one thread per ROW of the rotation chain (right-multiplications keep the
+//                                                rows independent), on three warps (trunk + tail / front legs / back legs):
+//                                                component i of every marker position and rotation axis
+//   P2  projection    thread <-> (frame, marker) loops over camera pairs: fisheye projection, 2x3
 //                                                Jacobian, redescending loss; accumulates the
 //                                                marker's 3x3 normal block A_l, 3-vector b_l and
 //                                                cost in registers (no cross-thread reduction),
@@ -18,9 +19,10 @@
 //                                                B_l^T A_l B_l and wrench B_l^T b_l, B_l=[-[p]x I]
 //   P3  subtree sums  thread <-> (frame, comp)   composite-rigid-body style accumulation of the
 //                                                27 components up the kinematic tree (fixed order)
-//   P4  blocks        thread <-> (frame, angle)  y = I_subtree tau_beta; H[a][b] = tau_a . y for
+//   P4  columns       thread <-> (frame, angle)  y = I_subtree tau_beta in registers; H[a][b] = tau_a . y for
 //                                                every ancestor angle a; g[b] = tau_b . wrench
-//   P5  write-out     coalesced copy of {cost, g[25], H[325]} from shared memory
+//   P5  write-out     bulk async stores (TMA) of {cost, g[25], H[325]} from shared memory; the next tile's inputs are
+//                     requested before / during it and land while this tile is still being reduced
 // d p_l / d angle = omega x (p_l - pivot) = B_l tau (twist about the head point), so
 // H = sum_l J_l^T A_l J_l collapses to tau_a^T I_{deeper subtree} tau_b: ~4 kFMA instead of
 // ~8 kFMA per frame for the chain rule and no 60x25 Jacobian is ever materialised.
