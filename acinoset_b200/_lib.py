@@ -210,6 +210,18 @@ class Handle:
         self._check(lib.acino_set_cameras(self._h, C, _np_ptr(K), _np_ptr(D), _np_ptr(R), _np_ptr(t)),
                     "acino_set_cameras")
         self.n_cams = C
+        # same table again (every TRI / SBA call re-installs its scene): not a change; solvers that live across calls
+        # (lm.FTESolver, ekf) remember the version they were built for and refuse to run against another scene
+        sig = (K.tobytes(), D.tobytes(), R.tobytes(), t.tobytes())
+        if sig != getattr(self, "_scene_sig", None):
+            self._scene_sig = sig
+            self.scene_version = getattr(self, "scene_version", 0) + 1
+
+    def check_scene(self, version, who):
+        if version != getattr(self, "scene_version", 0):
+            raise AcinoError(f"{who}: the camera table of the handle on cuda:{self.device} was replaced (scene version "
+                             f"{getattr(self, 'scene_version', 0)}, expected {version}) - a handle holds ONE scene; use one "
+                             "handle per scene (acinoset_b200.Handle(device)) or re-create the solver")
 
     def set_redescending(self, a, b, c):
         self._check(lib.acino_set_redescending(self._h, float(a), float(b), float(c)), "acino_set_redescending")

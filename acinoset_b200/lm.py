@@ -219,6 +219,7 @@ class FTESolver:
         import torch
 
         self.h = handle
+        self._scene_version = getattr(handle, "scene_version", 0)   # the captured graph holds THIS scene by value
         self.torch = torch
         self.dev = torch.device("cuda", handle.device)
         self.N = int(meas.shape[0])
@@ -398,6 +399,7 @@ class FTESolver:
         torch = self.torch
         N = self.N
         s = self.st[0]
+        self.h.check_scene(self._scene_version, "FTESolver.solve")
         x0 = np.clip(np.asarray(x0, dtype=np.float64), self.lo.cpu().numpy(), self.hi.cpu().numpy())
         s["x_ext"].zero_()
         s["x_ext"][3:3 + N] = torch.as_tensor(x0).to(self.dev)

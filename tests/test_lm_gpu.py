@@ -274,3 +274,26 @@ def test_fte_solve_reaches_independent_optimum(handle, dummy_cams, N, seed):
     assert F64(x) <= F_scipy * (1 + 1e-6), (F64(x), F_scipy)
     P, Ps = skeleton.cheetah_fk_active(x), skeleton.cheetah_fk_active(g[f"fte{N}_x"])
     assert np.abs(P - Ps).max() < 1e-3, np.abs(P - Ps).max()
+
+
+def test_solver_refuses_a_replaced_scene(dummy_cams):
+    """A handle holds ONE camera table; a solver (whose captured graph carries the scene by value) must not silently run
+    against another one that a TRI / SBA call installed in between."""
+    import acinoset_b200 as ab
+    import synth
+    from acinoset_b200 import lm
+    from oracle import fisheye, skeleton
+
+    K, D, R, t, _ = dummy_cams
+    h = ab.Handle(0)
+    h.set_cameras(K, D, R, t)
+    p = synth.make_fte_problem(12, skeleton.cheetah_fk_active, fisheye.project, seed=1, cams=dummy_cams)
+    sol = lm.FTESolver(h, p["meas"], p["w"], p["Ts"])
+    sol.solve(p["x0"], max_iter=2)
+    h.set_cameras(K, D, R, t)                      # the same table again is not a change
+    sol.solve(p["x0"], max_iter=2)
+    h.set_cameras(K, D, R, t + 0.01)
+    with pytest.raises(ab.AcinoError, match="camera table"):
+        sol.solve(p["x0"], max_iter=2)
+    sol.close()
+    h.close()
