@@ -442,7 +442,7 @@ def cpu_baseline_time(x, meas, w, cams, target_s=12.0, threads=0):
         c_port.fte_eval(x[:n], meas[:n], w[:n], K, D, R, t, n_threads=threads)
     dt = time.perf_counter() - t0
     return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} pass(es) over {n} frames of the same batch, fp64 C restatement (oracle/c/fte_oracle.c), "
+            "sample": f"{reps} pass(es) over {n} frames of the same batch, fp64 C restatement (oracle/c/fte_oracle.c, gcc -O2 without -march=native), "
                       f"OpenMP over frames, {dt:.1f} s; reference Pyomo+IPOPT path not runnable in this image"}
 
 
@@ -484,7 +484,7 @@ def run_reference(args):
         "config": config_dict(args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"each step = {sample_seqs} of the {SEQS} sequences ({n} frames), fp64 C restatement "
-                                   f"of the reference path (oracle/c/fte_oracle.c), OpenMP {cores} threads; the "
+                                   f"of the reference path (oracle/c/fte_oracle.c, gcc -O2 without -march=native), OpenMP {cores} threads; the "
                                    f"reference's own Pyomo+IPOPT evaluation cannot run here (pyomo/ipopt absent)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
