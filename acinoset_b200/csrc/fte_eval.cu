@@ -197,7 +197,11 @@ struct __align__(16) Smem {
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
     union {                            // region A
-        __align__(16) float Il[FT * NL][NSP + 1];   // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 / LDS.64
+        // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 (P2) / LDS.64 (P3).  Frame stride 572 words =
+        // 28 (mod 32): in P3 a warp covers 14 + 14 + 4 (component pair, frame) lanes and the lanes of the next frame
+        // continue in the banks where the previous frame's stop - with the natural stride 560 = 16 (mod 32) every one of
+        // P3's loads was a 2-way conflict
+        __align__(16) float Il[FT][NL * (NSP + 1) + 12];
         struct {                       // staged outputs in their global layout
             float H[FT][NU];
             float g[FT][NA];
@@ -206,9 +210,10 @@ struct __align__(16) Smem {
     };
     union {                            // region B
         InTiles<FT, MAXC_STAGE> in;
-        // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads); frame stride 396 words = 12 (mod 32):
-        // the 8 frames of a quarter-warp hit 8 distinct 4-bank groups (392 gave 2-way conflicts on every LDS.128 of P4a)
-        __align__(16) float Ij[FT][NJ * (NSP + 1) + 4];
+        // subtree spatial inertia + wrench per joint (27 padded to 28: float4 loads); frame stride 412 words = 28 (mod 32):
+        // the 8 frames of a quarter-warp hit 8 distinct 4-bank groups in P4's LDS.128 (392 gave 2-way conflicts there) and
+        // P3's STS.64 of neighbouring frames do not collide either (396 = 12 (mod 32) did)
+        __align__(16) float Ij[FT][NJ * (NSP + 1) + 20];
     };
 };
 
@@ -404,6 +409,18 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         const float px = S.p[f][l][0], py = S.p[f][l][1], pz = S.p[f][l][2];
         const float wx = Sx[f][0] + px, wy = Sx[f][1] + py, wz = Sx[f][2] + pz;
         const size_t base = ((size_t)(f0 + f) * C) * NL + l;
+        // v = pivot x omega of the 16 pivoted angles, from the components the FK rows stored: one per thread, while the
+        // input tiles may still be landing (read by P4, two barriers from here; on one warp inside P3 it was that phase's
+        // critical path)
+        if (tid < 16 * FT) {
+            const int k = tid / FT, ff = tid - k * FT;
+            const float* pv = S.p[ff][c_piv.marker[k]];
+            float* tt = &S.tau[ff][c_piv.slot[k] * TAU_STRIDE];
+            const float q0 = pv[0], q1 = pv[1], q2 = pv[2], o0 = tt[0], o1 = tt[1], o2 = tt[2];
+            tt[3] = q1 * o2 - q2 * o1;
+            tt[4] = q2 * o0 - q0 * o2;
+            tt[5] = q0 * o1 - q1 * o0;
+        }
         if (staged) {
             mbar_wait(&S.mbar[1], ph_m & 1);
             ++ph_m;
@@ -537,15 +554,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         o[22] = pz * b0 - px * b2;
         o[23] = px * b1 - py * b0;
         o[24] = b0; o[25] = b1; o[26] = b2;
-        float4* dst = reinterpret_cast<float4*>(S.Il[tid]);
+        float4* dst = reinterpret_cast<float4*>(&S.Il[f][l * (NSP + 1)]);
 #pragma unroll
         for (int i = (WANT_H ? 0 : 5); i < (NSP + 1) / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
     __syncthreads();   // the input tiles (region B) are dead from here on
     PHASE_MARK(4);
 
-    // ---- P3: subtree sums up the kinematic tree, one thread per (component pair, frame), packed adds; the last warp
-    //      (idle otherwise) forms v = pivot x omega of the 16 pivoted angles from the components the FK rows stored
+    // ---- P3: subtree sums up the kinematic tree, one thread per (component pair, frame), packed adds
     {
         constexpr int NKP = (NSP + 1) / 2;       // 14 component pairs
         const int task = tid;
@@ -555,7 +571,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             if (WANT_H || kp >= 10) {
                 f2 v[NL];
 #pragma unroll
-                for (int l = 0; l < NL; ++l) v[l] = pk(*reinterpret_cast<const float2*>(&S.Il[f * NL + l][2 * kp]));
+                for (int l = 0; l < NL; ++l) v[l] = pk(*reinterpret_cast<const float2*>(&S.Il[f][l * (NSP + 1) + 2 * kp]));
                 const f2 s13 = v[19], s12 = add2(v[18], s13);
                 const f2 s11 = v[16], s10 = add2(v[15], s11);
                 const f2 s5 = v[7], s4 = add2(v[6], s5);
@@ -571,16 +587,6 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
                 ST2(0, s0); ST2(1, s1); ST2(2, s2); ST2(3, s3); ST2(4, s4); ST2(5, s5); ST2(6, s6);
                 ST2(7, s7); ST2(8, s8); ST2(9, s9); ST2(10, s10); ST2(11, s11); ST2(12, s12); ST2(13, s13);
 #undef ST2
-            }
-        } else if (tid >= NT - 32) {
-            for (int t = tid - (NT - 32); t < 16 * FT; t += 32) {
-                const int k = t / FT, ff = t - k * FT;
-                const float* pv = S.p[ff][c_piv.marker[k]];
-                float* tt = &S.tau[ff][c_piv.slot[k] * TAU_STRIDE];
-                const float p0 = pv[0], p1 = pv[1], p2 = pv[2], o0 = tt[0], o1 = tt[1], o2 = tt[2];
-                tt[3] = p1 * o2 - p2 * o1;
-                tt[4] = p2 * o0 - p0 * o2;
-                tt[5] = p0 * o1 - p1 * o0;
             }
         }
     }

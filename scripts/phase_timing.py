@@ -23,7 +23,7 @@ h.fte_eval_dev(xd, md, wd, c, g, H); torch.cuda.synchronize()
 out = (ctypes.c_longlong * 16)()
 L.lib.acino_debug_phase_cycles(out)
 cy = np.array(list(out)[:9], dtype=np.float64) / (n / 8)
-names = ["prologue", "-", "P1b", "P2 loop", "P2b+split barrier", "P3", "P4", "next-tile issue", "P5"]
+names = ["-", "P0+P1a", "P1b", "P2 loop", "P2b", "P3", "P4", "next-tile issue", "P5"]
 tot = cy.sum()
 for nm, v in zip(names, cy): print(f"{nm:10s} {v:9.0f} cycles/CTA  {v / tot * 100:5.1f}%")
 print("total", tot)
