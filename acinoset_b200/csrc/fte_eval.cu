@@ -362,6 +362,9 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             reinterpret_cast<unsigned*>(&S.col[0])[i] = reinterpret_cast<const unsigned*>(&c_col.col[0])[i];
     bool out_pending = false;          // (thread 0) bulk stores of the previous tile may still be reading region A
     __syncthreads();
+    sincos_tile(tile, 0);              // P0 + P1a of the first tile
+    __syncthreads();
+    PHASE_MARK(1);
 
     for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
     const int f0 = tile * FT;
@@ -370,16 +373,13 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     const int xb = it & 1;
     float (*Sx)[NA] = S.x[xb];
     const int tile_next = tile + gridDim.x;
-    // ---- P0 + P1a: the tile's state (prefetched during the previous tile) -> sin / cos of the 22 angles
-    sincos_tile(tile, xb);
-    __syncthreads();
-    PHASE_MARK(1);
+    // (P0 + P1a, the sin / cos of this tile's angles, ran before the barrier that follows the previous tile's camera loop)
 
     // ---- P1b: rotation chain, three threads per frame (one per ROW of the chain: right-multiplications keep rows
     //      independent): component i of every marker position and rotation axis
     //      Warp 0: head / neck / torso / tail, warp 1: front legs, warp 2: back legs (each re-derives the part of the trunk
-    //      it hangs from: cheaper than waiting for it).  Warp 3: the next tile's state (every thread is past its wait on
-    //      mbar[0]; the other buffer was last read by the previous tile)
+    //      it hangs from: cheaper than waiting for it).  Warp 3: the next tile's state (every thread passed its wait on
+    //      mbar[0] during the previous tile, whose camera loop was the last reader of the other buffer)
     {
         const int wq = tid >> 5, ln = tid & 31;
         if (wq < 3) {
@@ -558,6 +558,10 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
 #pragma unroll
         for (int i = (WANT_H ? 0 : 5); i < (NSP + 1) / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
+    // ---- P0 + P1a of the NEXT tile, ahead of the barrier: the warps of the camera loop finish hundreds of cycles apart, and
+    //      whoever is early spends the wait on the next tile's sin / cos (its state tile was requested during this tile's
+    //      FK; sc was last read there) instead of at a barrier of its own at the top of the tile
+    if (tile_next < n_tiles) sincos_tile(tile_next, xb ^ 1);
     __syncthreads();   // the input tiles (region B) are dead from here on
     PHASE_MARK(4);
 
