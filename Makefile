@@ -15,7 +15,7 @@ $(LIB): $(SRCS) $(HDRS)
 ptxas-info: $(SRCS) $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -shared -o /tmp/libacino_b200_ptxas.so $(SRCS)
 
-# A/B build for scripts/ab_env.sh / bench_e2e_chunks.sh: the ACINO_FTE_VARIANT / ACINO_FTE_CTAS /
+# A/B build for scripts/ab_env.sh / ab_e2e.sh: the ACINO_FTE_VARIANT / ACINO_FTE_CTAS /
 # ACINO_FTE_SMEM_PAD / ACINO_E2E_CHUNK environment switches exist only in this build (the product library has none).
 experiments: $(SRCS) $(HDRS)
 	mkdir -p scratch
