@@ -10,7 +10,7 @@
 
 namespace acino {
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                            const float* w, float* cost, float* g, float* H, cudaStream_t stream);
+                            const float* w, float* cost, float* g, float* H, cudaStream_t stream, int* sched);
 const char* fte_eval_kernel_name(int n_frames);
 cudaError_t launch_fk_project(const SceneF& scene, int n_frames, const float* x, float* pos, float* uv,
                               cudaStream_t stream);
@@ -140,6 +140,8 @@ int acino_create(acino_handle** out, int device) {
     set_loss(h->scene.loss, 3.0, 10.0, 20.0);   // all_optimizations.py:25-27
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->sched, 2 * acino_handle::kSchedSlots * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->sched, 0, 2 * acino_handle::kSchedSlots * sizeof(int));
     if (e != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "acino_create");
         delete h;
@@ -154,6 +156,7 @@ int acino_destroy(acino_handle* h) {
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->red_ws) cudaFree(h->red_ws);
+    if (h->sched) cudaFree(h->sched);
     if (h->d_skel) cudaFree(h->d_skel);
     if (h->st_buf) cudaFree(h->st_buf);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -217,7 +220,7 @@ int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const floa
     if (n_frames == 0) return ACINO_OK;
     if (((uintptr_t)meas & 7u) != 0) return fail(h, ACINO_ERR_ARG, "acino_fte_eval_dev: meas must be 8-byte aligned");
     CK(cudaSetDevice(h->device));
-    CK(launch_fte_eval(h->scene, n_frames, x, meas, w, cost, g, H, (cudaStream_t)cuda_stream));
+    CK(launch_fte_eval(h->scene, n_frames, x, meas, w, cost, g, H, (cudaStream_t)cuda_stream, h->next_sched()));
     h->launches += 1;
     return ACINO_OK;
 }
@@ -280,7 +283,7 @@ int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* m
         CK(cudaEventRecord(h->ev_in[i], h->s_h2d));
         CK(cudaStreamWaitEvent(h->stream, h->ev_in[i], 0));
         CK(launch_fte_eval(h->scene, (int)nf, dx + f0 * NA, dm + f0 * C * NL * 2, dw + f0 * C * NL, cost ? dc + f0 : nullptr,
-                           g ? dg + f0 * NA : nullptr, H ? dH + f0 * NU : nullptr, h->stream));
+                           g ? dg + f0 * NA : nullptr, H ? dH + f0 * NU : nullptr, h->stream, h->next_sched()));
         h->launches += 1;
         CK(cudaEventRecord(h->ev_done[i], h->stream));
         CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[i], 0));

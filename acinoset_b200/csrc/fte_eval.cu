@@ -48,6 +48,13 @@ constexpr int N_TRUNK = 6;
 constexpr int k_trunk_slot[N_TRUNK] = {0, 3, 17, 1, 4, 18};     // phi0 theta0 psi0 | phi1 theta1 psi1
 constexpr int trunk_slot(int k) { return k == 0 ? 0 : k == 1 ? 3 : k == 2 ? 17 : k == 3 ? 1 : k == 4 ? 4 : 18; }
 constexpr int MAX_ANC = 8;
+#ifndef ACINO_UNROLL_PAIRS
+#define ACINO_UNROLL_PAIRS 3             // the camera loop is unrolled for this many camera pairs (the reference's six cameras)
+#endif
+#ifndef ACINO_ANC_B
+#define ACINO_ANC_B 4
+#endif
+constexpr int ANC_B = ACINO_ANC_B;       // ancestors per batch of the column assembly (divides MAX_ANC)
 constexpr int N_ZERO = N_PAIR - 185;
 constexpr unsigned NO_ENTRY = 0xFFFFu;
 struct ColEntry {                       // 112 bytes of ready-to-use 32-bit words: seven 16-byte loads, no field extraction
@@ -196,6 +203,7 @@ struct __align__(16) Smem {
     unsigned short zero_idx[N_ZERO + 4];
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
+    int next_tile;                     // dynamic schedule: the tile this CTA takes next (published by the claiming thread)
     union {                            // region A
         // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 (P2) / LDS.64 (P3).  Frame stride 572 words =
         // 28 (mod 32): in P3 a warp covers 14 + 14 + 4 (component pair, frame) lanes and the lanes of the next frame
@@ -260,8 +268,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned by
 __device__ long long g_phase_cycles[16];
 __device__ int g_phase_count;
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_phase_cycles[i], (unsigned long long)(_t - _tprev)); _tprev = _t; } } while (0)
+// camera-loop intervals of the first 128 tiles of every CTA (SM clock: comparable between the CTAs of one SM) - scripts/p2_overlap.py
+__device__ long long g_p2_trace[1024 * 128 * 2];
+__device__ int g_p2_smid[1024];
+#define P2_TRACE(it, which) do { if (threadIdx.x == 0 && (it) < 128 && blockIdx.x < 1024) g_p2_trace[(blockIdx.x * 128 + (it)) * 2 + (which)] = clock64(); } while (0)
 #else
 #define PHASE_MARK(i) do { } while (0)
+#define P2_TRACE(it, which) do { } while (0)
 #endif
 
 // range-reduced MUFU sine / cosine: |error| < 4e-7 for any |x| up to a few hundred revolutions (the reduction is one
@@ -277,7 +290,7 @@ __device__ __forceinline__ void
 fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
               const float* __restrict__ xg, const float* __restrict__ meas,
               const float* __restrict__ wts, float* __restrict__ cost_out,
-              float* __restrict__ g_out, float* __restrict__ H_out) {
+              float* __restrict__ g_out, float* __restrict__ H_out, int* __restrict__ sched) {
     constexpr int NT = FT * NL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<FT>& S = *reinterpret_cast<Smem<FT>*>(smem_raw);
@@ -303,6 +316,11 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     };
 #ifdef ACINO_PHASE_TIMING
     long long _tprev = clock64();
+    if (tid == 0 && blockIdx.x < 1024) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_p2_smid[blockIdx.x] = (int)smid;
+    }
 #endif
 
     // sin / cos of the 22 angles of tile t, one thread per (angle, frame); its state tile is in (or goes to) S.x[buf]
@@ -360,19 +378,33 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     if (!first_staged)          // (a staged first tile brings the table with its state)
         for (int i = tid; i < (int)(COL_BYTES / 4); i += NT)
             reinterpret_cast<unsigned*>(&S.col[0])[i] = reinterpret_cast<const unsigned*>(&c_col.col[0])[i];
-    bool out_pending = false;          // (thread 0) bulk stores of the previous tile may still be reading region A
+    // The bulk copies are issued by threads of warps 3 and 4, which have nothing to do while warps 0-2 run the FK chain of the
+    // next tile (issuing one costs its thread ~100 cycles: on warps 0 / 1 the FK chain started ~600 cycles late)
+    constexpr int ST_TID = NT > 128 ? 128 : 0;     // output stores (and the wait for them)
+    constexpr int MW_TID = NT > 97 ? 97 : 32;      // next tile's measurement / weight tiles (thread 96: next tile's state)
+    bool out_pending = false;          // (thread ST_TID) bulk stores of the previous tile may still be reading region A
     __syncthreads();
     sincos_tile(tile, 0);              // P0 + P1a of the first tile
     __syncthreads();
     PHASE_MARK(1);
 
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    // Tile schedule.  Static (tile, tile + grid, ...) when every CTA has one tile, or no counter was given.  Otherwise
+    // dynamic: the first tile is blockIdx.x, every further one is claimed from a global ticket counter one tile ahead (the
+    // atomic's latency hides behind the FK phase).  The CTAs of a persistent wave do not run at the same speed - with the
+    // static schedule the fast ones had exited while the slow ones still had tiles left (17.2 of 20 warps active on
+    // average); the last CTA to leave resets the counter pair for the next launch.
+#ifdef ACINO_STATIC_SCHED
+    const bool dynamic = false;
+#else
+    const bool dynamic = sched != nullptr && n_tiles > (int)gridDim.x;
+#endif
+    for (int it = 0; tile < n_tiles; ++it) {
     const int f0 = tile * FT;
     const int nf = min(FT, n_frames - f0);
     const bool staged = bulk_in && nf == FT;
     const int xb = it & 1;
     float (*Sx)[NA] = S.x[xb];
-    const int tile_next = tile + gridDim.x;
+    int tile_next = tile + gridDim.x;      // (dynamic: replaced after the FK barrier by what thread 96 claimed)
     // (P0 + P1a, the sin / cos of this tile's angles, ran before the barrier that follows the previous tile's camera loop)
 
     // ---- P1b: rotation chain, three threads per frame (one per ROW of the chain: right-multiplications keep rows
@@ -389,17 +421,23 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
                 else if (wq == 1) cheetah_fk_row<2>(S.sc[f], i, &S.p[f][0][0], &S.tau[f][0]);
                 else cheetah_fk_row<4>(S.sc[f], i, &S.p[f][0][0], &S.tau[f][0]);
             }
-        } else if (bulk_in && tid == 96) {
-            if (tile_next < n_tiles && (tile_next + 1) * FT <= n_frames) issue_x(tile_next, xb ^ 1, false);
+        } else if (tid == 96) {
+            if (dynamic) {
+                tile_next = (int)gridDim.x + atomicAdd(sched, 1);
+                S.next_tile = tile_next;
+            }
+            if (bulk_in && tile_next < n_tiles && (tile_next + 1) * FT <= n_frames) issue_x(tile_next, xb ^ 1, false);
         }
     }
     // region A still holds the previous tile's staged outputs: its bulk stores must have read them before P2 writes Il
-    if (tid == 0 && out_pending) {
+    if (tid == ST_TID && out_pending) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         out_pending = false;
     }
     __syncthreads();
+    if (dynamic) tile_next = S.next_tile;
     PHASE_MARK(2);
+    P2_TRACE(it, 0);
 
     // ---- P2: projection + loss, one thread per (frame, marker), loop over cameras
     {
@@ -432,10 +470,16 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         f2 A00 = zero2, A01 = zero2, A02 = zero2, A11 = zero2, A12 = zero2, A22 = zero2;
         f2 B0 = zero2, B1 = zero2, B2 = zero2, CST = zero2;
         // (two instantiations: staged tiles read shared memory, the others global memory - no per-iteration branch)
-        auto camera_loop = [&](auto staged_tag) {
+        // NPC > 0: the camera count is 2 * NPC and the loop is unrolled - the camera constants are then immediate offsets
+        // into the parameter bank (uniform loads / operands) instead of 28 indexed LDC.64 into vector registers per pair
+        auto camera_loop = [&](auto staged_tag, auto np_tag) {
         constexpr bool STAGED = decltype(staged_tag)::value;
-        for (int c = 0; c < C; c += 2) {
-            const bool has2 = c + 1 < C;
+        constexpr int NPC = decltype(np_tag)::value;
+        const int n_pairs = NPC > 0 ? NPC : (C + 1) / 2;
+#pragma unroll(NPC > 0 ? NPC : 1)
+        for (int k = 0; k < n_pairs; ++k) {
+            const int c = 2 * k;
+            const bool has2 = NPC > 0 ? true : c + 1 < C;
             float2 m0 = make_float2(0.f, 0.f), m1 = make_float2(0.f, 0.f);
             float w0 = 0.f, w1 = 0.f;
             if (STAGED) {
@@ -453,7 +497,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
                     w1 = __ldg(wts + base + (size_t)(c + 1) * NL);
                 }
             }
-            const CamPairF& cp = scene.pair[c >> 1];
+            const CamPairF& cp = scene.pair[k];
             const f2 R0 = pk(cp.R[0]), R1 = pk(cp.R[1]), R2 = pk(cp.R[2]), R3 = pk(cp.R[3]), R4 = pk(cp.R[4]),
                      R5 = pk(cp.R[5]), R6 = pk(cp.R[6]), R7 = pk(cp.R[7]), R8 = pk(cp.R[8]);
             const f2 XC = fma2(R0, WX, fma2(R1, WY, fma2(R2, WZ, pk(cp.t[0]))));
@@ -520,8 +564,12 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
             }
         }
         };
-        if (staged) camera_loop(std::true_type{});
-        else camera_loop(std::false_type{});
+        if (staged) {
+            if (C == 2 * ACINO_UNROLL_PAIRS) camera_loop(std::true_type{}, std::integral_constant<int, ACINO_UNROLL_PAIRS>{});
+            else camera_loop(std::true_type{}, std::integral_constant<int, 0>{});
+        } else {
+            camera_loop(std::false_type{}, std::integral_constant<int, 0>{});
+        }
         const float a00 = lo(A00) + hi(A00), a01 = lo(A01) + hi(A01), a02 = lo(A02) + hi(A02);
         const float a11 = lo(A11) + hi(A11), a12 = lo(A12) + hi(A12), a22 = lo(A22) + hi(A22);
         const float b0 = lo(B0) + hi(B0), b1 = lo(B1) + hi(B1), b2 = lo(B2) + hi(B2);
@@ -564,6 +612,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     if (tile_next < n_tiles) sincos_tile(tile_next, xb ^ 1);
     __syncthreads();   // the input tiles (region B) are dead from here on
     PHASE_MARK(4);
+    P2_TRACE(it, 1);
 
     // ---- P3: subtree sums up the kinematic tree, one thread per (component pair, frame), packed adds
     {
@@ -652,13 +701,24 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         // the other ancestors (and beta itself): full 6-term products
         const uint4 a0_ = ce[3], a1_ = ce[4];           // anc_off[0..7]
         const unsigned ao[MAX_ANC] = {a0_.x, a0_.y, a0_.z, a0_.w, a1_.x, a1_.y, a1_.z, a1_.w};
+        // in batches of ANC_B with the loads of a batch in flight together (one vote per warp and column round: a loop with a
+        // vote and a break per ancestor ran them one load latency after the other; executing all 8 for every column measured
+        // 4 % slower).  Unused list entries point at slot 0: a valid address, the product is not stored
         float ha[MAX_ANC];
+        const int n_max = (int)__reduce_max_sync(__activemask(), (unsigned)n_anc);
 #pragma unroll
-        for (int k = 0; k < MAX_ANC; ++k) {
-            if (!__any_sync(__activemask(), k < n_anc)) break;     // (executing all 8 for every column measured 4 % slower)
-            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + ao[k]);
-            const float2 a1 = *reinterpret_cast<const float2*>(tau_f + ao[k] + 4);
-            ha[k] = a0.x * yt0 + a0.y * yt1 + a0.z * yt2 + a0.w * yb0 + a1.x * yb1 + a1.y * yb2;
+        for (int b = 0; b < MAX_ANC; b += ANC_B) {
+            if (b >= n_max) break;
+            float4 a0[ANC_B];
+            float2 a1[ANC_B];
+#pragma unroll
+            for (int k = 0; k < ANC_B; ++k) {
+                a0[k] = *reinterpret_cast<const float4*>(tau_f + ao[b + k]);
+                a1[k] = *reinterpret_cast<const float2*>(tau_f + ao[b + k] + 4);
+            }
+#pragma unroll
+            for (int k = 0; k < ANC_B; ++k)
+                ha[b + k] = a0[k].x * yt0 + a0[k].y * yt1 + a0[k].z * yt2 + a0[k].w * yb0 + a1[k].x * yb1 + a1[k].y * yb2;
         }
         // stores last: no store -> load ordering inside the task
         g[3 + be] = gb;
@@ -688,8 +748,8 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     __syncthreads();   // Ij (region B) is dead from here on
     PHASE_MARK(6);
     // ---- the next tile's measurements and weights: region B is free; the copies land while P5 and the next tile's FK run
-    if (bulk_in && tid == 32) {            // (thread 0 issues the bulk stores of P5 meanwhile)
-        const int tn = tile + gridDim.x;
+    if (bulk_in && tid == MW_TID) {        // (thread ST_TID issues the bulk stores of P5 meanwhile)
+        const int tn = tile_next;
         if (tn < n_tiles && (tn + 1) * FT <= n_frames) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue_mw(tn);
@@ -701,7 +761,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     //      three bulk async stores (TMA) issued by one thread (they drain while the next tile starts); otherwise
     //      straight copies
     if ((use_bulk & 2) && nf == FT) {
-        if (tid == 0) {
+        if (tid == ST_TID) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (cost_out) bulk_s2g(cost_out + f0, &S.o.cost[0], FT * 4);
             if (g_out) bulk_s2g(g_out + (size_t)f0 * NA, &S.o.g[0][0], FT * NA * 4);
@@ -725,8 +785,15 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         }
     }
     PHASE_MARK(8);
+    tile = tile_next;
     }   // tiles
-    if (tid == 0 && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (tid == ST_TID && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (dynamic && tid == 0) {             // every ticket of this CTA has been drawn: the last CTA out re-arms the counters
+        if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+        }
+    }
 }
 
 // persistent: one wave of MINB CTAs per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -734,12 +801,21 @@ template <int FT, bool WANT_H, int MINB>
 __global__ void __launch_bounds__(FT * NL, MINB)
 fte_eval_kernel(const __grid_constant__ SceneF scene, const int n_frames, const int use_bulk,
                 const float* __restrict__ xg, const float* __restrict__ meas, const float* __restrict__ wts,
-                float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out) {
-    fte_eval_body<FT, WANT_H>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out);
+                float* __restrict__ cost_out, float* __restrict__ g_out, float* __restrict__ H_out, int* __restrict__ sched) {
+    fte_eval_body<FT, WANT_H>(scene, n_frames, use_bulk, xg, meas, wts, cost_out, g_out, H_out, sched);
 }
 
 #ifdef ACINO_PHASE_TIMING
 extern "C" void acino_debug_phase_cycles(long long* out16) { cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(long long) * 16); }
+extern "C" void acino_debug_p2_trace(long long* trace, int* smid) {
+    cudaMemcpyFromSymbol(trace, g_p2_trace, sizeof(long long) * 1024 * 128 * 2);
+    cudaMemcpyFromSymbol(smid, g_p2_smid, sizeof(int) * 1024);
+}
+extern "C" void acino_debug_p2_trace_reset() {
+    void* p = nullptr;
+    cudaGetSymbolAddress(&p, g_p2_trace);
+    cudaMemset(p, 0, sizeof(long long) * 1024 * 128 * 2);
+}
 extern "C" void acino_debug_phase_reset() { long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
 #endif
 
@@ -798,7 +874,7 @@ fk_project_kernel(const __grid_constant__ SceneF scene, const int n_frames, cons
 }
 
 // ------------------------------------------------------------------------------------------
-using FteKernel = void (*)(const SceneF, int, int, const float*, const float*, const float*, float*, float*, float*);
+using FteKernel = void (*)(const SceneF, int, int, const float*, const float*, const float*, float*, float*, float*, int*);
 
 // per-device launch configuration (cudaFuncSetAttribute is per device; a process may drive several GPUs)
 struct FteDeviceCfg {
@@ -813,7 +889,8 @@ constexpr int FTE_CTAS = 4;      // resident CTAs per SM (96 registers, no spill
 
 template <int FT, int MINB>
 static cudaError_t launch_fte_eval_k(const SceneF& scene, int n_frames, const float* x, const float* meas, const float* w,
-                                     float* cost, float* g, float* H, cudaStream_t stream, int ctas_per_sm, size_t smem_pad) {
+                                     float* cost, float* g, float* H, cudaStream_t stream, int ctas_per_sm, size_t smem_pad,
+                                     int* sched) {
     // bulk (TMA) staging needs 16-byte aligned tiles: frame tiles are multiples of 16 bytes, so it is the
     // base pointers that decide
     // bit 0: inputs, bit 1: outputs (cost tiles are FT * 4 = 32 bytes, g / H tiles multiples of 16 bytes)
@@ -835,12 +912,14 @@ static cudaError_t launch_fte_eval_k(const SceneF& scene, int n_frames, const fl
         if (e != cudaSuccess) return e;
         if (!done && cfg.n_configured < 8) cfg.configured[cfg.n_configured++] = k;
     }
-    k<<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H);
+    k<<<grid, FT * NL, smem, stream>>>(scene, n_frames, use_bulk, x, meas, w, cost, g, H, sched);
     return cudaGetLastError();
 }
 
+// sched: device pointer to a zero-initialised {ticket, finished} counter pair owned by the caller (one per launch in flight;
+// the kernel leaves it zeroed), or nullptr for the static tile schedule
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas,
-                            const float* w, float* cost, float* g, float* H, cudaStream_t stream) {
+                            const float* w, float* cost, float* g, float* H, cudaStream_t stream, int* sched) {
     if (n_frames <= 0) return cudaSuccess;
 #ifdef ACINO_EXPERIMENTS
     // A/B knobs of scripts/bench_variants.sh / bench_residency.sh (build with -DACINO_EXPERIMENTS):
@@ -856,11 +935,11 @@ cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, c
         e = getenv("ACINO_FTE_SMEM_PAD");
         pad = e ? (size_t)atol(e) : 0;
     }
-    if (variant == 1) return launch_fte_eval_k<FTE_FT, 5>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : 5, pad);
-    if (variant == 3) return launch_fte_eval_k<FTE_FT, 3>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : 3, pad);
-    return launch_fte_eval_k<FTE_FT, FTE_CTAS>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : FTE_CTAS, pad);
+    if (variant == 1) return launch_fte_eval_k<FTE_FT, 5>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : 5, pad, sched);
+    if (variant == 3) return launch_fte_eval_k<FTE_FT, 3>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : 3, pad, sched);
+    return launch_fte_eval_k<FTE_FT, FTE_CTAS>(scene, n_frames, x, meas, w, cost, g, H, stream, ctas ? ctas : FTE_CTAS, pad, sched);
 #else
-    return launch_fte_eval_k<FTE_FT, FTE_CTAS>(scene, n_frames, x, meas, w, cost, g, H, stream, FTE_CTAS, 0);
+    return launch_fte_eval_k<FTE_FT, FTE_CTAS>(scene, n_frames, x, meas, w, cost, g, H, stream, FTE_CTAS, 0, sched);
 #endif
 }
 

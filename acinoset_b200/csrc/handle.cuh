@@ -19,6 +19,12 @@ struct acino_handle {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     double* red_ws = nullptr;          // partials + ticket counter of lm_reduce (zero-initialised once)
+    // tile-schedule counters of fte_eval ({ticket, finished} pairs, zero-initialised once, left zeroed by every launch): a ring,
+    // so that launches of this handle that are in flight at the same time (different streams) do not share a pair
+    static constexpr int kSchedSlots = 32;
+    int* sched = nullptr;
+    unsigned sched_next = 0;
+    int* next_sched() { return sched ? sched + 2 * (sched_next++ % kSchedSlots) : nullptr; }
     cudaStream_t stream = nullptr;
     // host-API pipeline: H2D / compute / D2H on three streams, chunked, chained with events
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;

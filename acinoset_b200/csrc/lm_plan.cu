@@ -12,7 +12,7 @@
 
 namespace acino {
 cudaError_t launch_fte_eval(const SceneF& scene, int n_frames, const float* x, const float* meas, const float* w,
-                            float* cost, float* g, float* H, cudaStream_t stream);
+                            float* cost, float* g, float* H, cudaStream_t stream, int* sched);
 cudaError_t launch_lm_prepare(int n_frames, long long frame0, long long ng, const double* x_ext, const float* g,
                               const double* sw, const double* lo, const double* hi, double* gtot, unsigned char* fixed,
                               double* cost_s, cudaStream_t s);
@@ -263,6 +263,7 @@ __global__ void lm_commit_kernel(const double* __restrict__ ctl, const CommitJob
 
 struct acino_lm_plan {
     acino_lm_desc d;
+    int* tile_sched = nullptr;          // two {ticket, finished} pairs for the plan's two fte_eval launches (captured in its graph)
     std::vector<int> lvl, clvl;         // (n_elim, n_surv) per level: local chain / interface chain
 };
 
@@ -297,6 +298,10 @@ int acino_lm_plan_create(acino_handle* h, const acino_lm_desc* desc, acino_lm_pl
     }
     acino_lm_plan* p = new acino_lm_plan();
     p->d = d;
+    if (cudaMalloc((void**)&p->tile_sched, 4 * sizeof(int)) != cudaSuccess || cudaMemset(p->tile_sched, 0, 4 * sizeof(int)) != cudaSuccess) {
+        delete p;
+        return fail(h, ACINO_ERR_CUDA, "acino_lm_plan_create: cannot allocate the tile-schedule counters");
+    }
     p->lvl.assign(d.level_counts, d.level_counts + 2 * (size_t)d.n_levels);
     if (d.world > 1) p->clvl.assign(d.clevel_counts, d.clevel_counts + 2 * (size_t)d.n_clevels);
     p->d.level_counts = nullptr;
@@ -306,6 +311,7 @@ int acino_lm_plan_create(acino_handle* h, const acino_lm_desc* desc, acino_lm_pl
 }
 
 int acino_lm_plan_destroy(acino_lm_plan* plan) {
+    if (plan && plan->tile_sched) cudaFree(plan->tile_sched);
     delete plan;
     return ACINO_OK;
 }
@@ -338,8 +344,8 @@ static int chain_backsub(acino_handle* h, const std::vector<int>& lvl, const int
     return ACINO_OK;
 }
 
-static int eval_state(acino_handle* h, const acino_lm_desc& d, int i, bool with_step, cudaStream_t s) {
-    CK(launch_fte_eval(h->scene, d.n_frames, d.x32[i], d.meas, d.w, d.cost[i], d.g[i], d.H[i], s));
+static int eval_state(acino_handle* h, const acino_lm_desc& d, int i, bool with_step, cudaStream_t s, int* tile_sched) {
+    CK(launch_fte_eval(h->scene, d.n_frames, d.x32[i], d.meas, d.w, d.cost[i], d.g[i], d.H[i], s, tile_sched + 2 * i));
     CK(launch_lm_prepare(d.n_frames, d.frame0, d.n_global, d.x_ext[i], d.g[i], d.sw, d.lo, d.hi, d.gtot[i], d.fixed[i],
                          d.cost_s[i], s));
     CK(launch_lm_reduce(d.n_frames, d.cost[i], d.cost_s[i], with_step ? d.pred : nullptr, nullptr,
@@ -359,7 +365,7 @@ int acino_lm_enqueue(acino_handle* h, acino_lm_plan* plan, int phase, void* cuda
     int rc;
     switch (phase) {
     case ACINO_LM_INIT_EVAL:
-        return eval_state(h, d, 0, false, s);
+        return eval_state(h, d, 0, false, s, plan->tile_sched);
     case ACINO_LM_INIT_FINISH:
         lm_init_finish_kernel<<<1, 32, 0, s>>>(d.world, d.sums_all, d.ctl);
         CK(cudaGetLastError());
@@ -402,7 +408,7 @@ int acino_lm_enqueue(acino_handle* h, acino_lm_plan* plan, int phase, void* cuda
                                                                       d.hi, d.x_ext[1], d.x32[1], d.pred, d.step);
         CK(cudaGetLastError());
         h->launches += 1;
-        return eval_state(h, d, 1, true, s);
+        return eval_state(h, d, 1, true, s, plan->tile_sched);
     }
     case ACINO_LM_DECIDE: {
         lm_decide_kernel<<<1, 32, 0, s>>>(d.world, d.sums_all, d.ctl, d.hist);
