@@ -203,7 +203,7 @@ struct __align__(16) Smem {
     unsigned short zero_idx[N_ZERO + 4];
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
     unsigned long long mbar[2];        // [0] state tile landed, [1] measurement + weight tiles landed
-    int next_tile;                     // dynamic schedule: the tile this CTA takes next (published by the claiming thread)
+    int next_tile;                     // dynamic schedule: the tile after this CTA's next one (published by the claiming thread)
     union {                            // region A
         // per-marker spatial inertia + wrench, 27 padded to 28: STS.128 (P2) / LDS.64 (P3).  Frame stride 572 words =
         // 28 (mod 32): in P3 a warp covers 14 + 14 + 4 (component pair, frame) lanes and the lanes of the next frame
@@ -389,8 +389,9 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     PHASE_MARK(1);
 
     // Tile schedule.  Static (tile, tile + grid, ...) when every CTA has one tile, or no counter was given.  Otherwise
-    // dynamic: the first tile is blockIdx.x, every further one is claimed from a global ticket counter one tile ahead (the
-    // atomic's latency hides behind the FK phase).  The CTAs of a persistent wave do not run at the same speed - with the
+    // dynamic: the first two tiles are blockIdx.x and blockIdx.x + grid, every further one is claimed from a global ticket
+    // counter TWO tiles ahead: the atomic is issued during the FK phase and its result is first touched after the camera loop
+    // (claimed one tile ahead, the ~1500-cycle round trip under load sat on the FK phase's critical path).  The CTAs of a persistent wave do not run at the same speed - with the
     // static schedule the fast ones had exited while the slow ones still had tiles left (17.2 of 20 warps active on
     // average); the last CTA to leave resets the counter pair for the next launch.
 #ifdef ACINO_STATIC_SCHED
@@ -398,13 +399,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
 #else
     const bool dynamic = sched != nullptr && n_tiles > (int)gridDim.x;
 #endif
+    int tile_next = tile + gridDim.x;
+    int claimed = 0;                   // (thread 96) ticket drawn during this tile's FK phase
     for (int it = 0; tile < n_tiles; ++it) {
     const int f0 = tile * FT;
     const int nf = min(FT, n_frames - f0);
     const bool staged = bulk_in && nf == FT;
     const int xb = it & 1;
     float (*Sx)[NA] = S.x[xb];
-    int tile_next = tile + gridDim.x;      // (dynamic: replaced after the FK barrier by what thread 96 claimed)
     // (P0 + P1a, the sin / cos of this tile's angles, ran before the barrier that follows the previous tile's camera loop)
 
     // ---- P1b: rotation chain, three threads per frame (one per ROW of the chain: right-multiplications keep rows
@@ -422,10 +424,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
                 else cheetah_fk_row<4>(S.sc[f], i, &S.p[f][0][0], &S.tau[f][0]);
             }
         } else if (tid == 96) {
-            if (dynamic) {
-                tile_next = (int)gridDim.x + atomicAdd(sched, 1);
-                S.next_tile = tile_next;
-            }
+            if (dynamic) claimed = atomicAdd(sched, 1);
             if (bulk_in && tile_next < n_tiles && (tile_next + 1) * FT <= n_frames) issue_x(tile_next, xb ^ 1, false);
         }
     }
@@ -435,7 +434,6 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         out_pending = false;
     }
     __syncthreads();
-    if (dynamic) tile_next = S.next_tile;
     PHASE_MARK(2);
     P2_TRACE(it, 0);
 
@@ -609,8 +607,10 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     // ---- P0 + P1a of the NEXT tile, ahead of the barrier: the warps of the camera loop finish hundreds of cycles apart, and
     //      whoever is early spends the wait on the next tile's sin / cos (its state tile was requested during this tile's
     //      FK; sc was last read there) instead of at a barrier of its own at the top of the tile
+    if (dynamic && tid == 96) S.next_tile = 2 * (int)gridDim.x + claimed;
     if (tile_next < n_tiles) sincos_tile(tile_next, xb ^ 1);
     __syncthreads();   // the input tiles (region B) are dead from here on
+    const int tile_next2 = dynamic ? S.next_tile : tile_next + (int)gridDim.x;
     PHASE_MARK(4);
     P2_TRACE(it, 1);
 
@@ -786,6 +786,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     }
     PHASE_MARK(8);
     tile = tile_next;
+    tile_next = tile_next2;
     }   // tiles
     if (tid == ST_TID && out_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (dynamic && tid == 0) {             // every ticket of this CTA has been drawn: the last CTA out re-arms the counters

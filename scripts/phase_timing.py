@@ -3,7 +3,7 @@ import ctypes, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import acinoset_b200._lib as L
-L.LIB_PATH = os.path.join(os.path.dirname(L.LIB_PATH), "..", "scratch", "libacino_timing.so")
+L.LIB_PATH = os.path.join(os.path.dirname(L.LIB_PATH), "..", "scratch", os.environ.get("ACINO_TIMING_LIB", "libacino_timing.so"))
 L.lib = L._load()
 import acinoset_b200 as ab, synth, torch
 K, D, R, t, _ = synth.load_dummy_scene()
