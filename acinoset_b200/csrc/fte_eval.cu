@@ -6,12 +6,13 @@
 // automatic differentiation IPOPT's ASL performs on those expression trees each iteration.
 //
 // Layout / mapping (B200, CUDA cores only - the contraction is tiny, irregular and sparse):
-//   persistent CTAs (one wave, 4 per SM), one tile = FT frames = FT * 20 threads.  Phases, separated by __syncthreads():
+//   persistent CTAs (one wave, 4 per SM), one tile = FT frames = FT * 20 threads; tiles are drawn from a global ticket
+//   counter (the CTAs of an SM do not run at the same speed).  Phases, separated by __syncthreads():
 //   P1a sin / cos     thread <-> (angle, frame)
 //   P1b FK            3 threads <-> frame        one thread per ROW of the rotation chain (right-multiplications keep the
 //                                                rows independent), on three warps (trunk + tail / front legs / back legs):
 //                                                component i of every marker position and rotation axis
-//   P2  projection    thread <-> (frame, marker) loops over camera pairs: fisheye projection, 2x3
+//   P2  projection    thread <-> (frame, marker) loops over camera pairs (unrolled for six cameras): fisheye projection, 2x3
 //                                                Jacobian, redescending loss; accumulates the
 //                                                marker's 3x3 normal block A_l, 3-vector b_l and
 //                                                cost in registers (no cross-thread reduction),
