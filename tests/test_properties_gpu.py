@@ -184,3 +184,59 @@ def test_sba_larger_scene_properties(dummy_cams):
         Rb, tb = rel(r_new, t_new, c)
         ang = np.degrees(np.arccos(np.clip((np.trace(Ra @ Rb.T) - 1) / 2, -1, 1)))
         assert ang < 0.02, ang
+
+
+def test_fte_eval_tile_schedule_is_invisible(dummy_cams):
+    """The dynamic tile schedule of the persistent kernel (tiles drawn from a ticket counter once a launch has more than one
+    wave of tiles) must not show in the results: launches just below / above one and two waves of 8-frame tiles, with a
+    partial last tile, with and without H, back to back and on two streams at once, equal the same frames evaluated in
+    single-wave launches (static schedule) bit for bit."""
+    import torch
+    import acinoset_b200 as ab
+    import synth
+
+    K, D, R, t, _ = dummy_cams
+    h = ab.Handle(0)
+    h.set_cameras(K, D, R, t)
+    dev = torch.device("cuda:0")
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    wave = 8 * 4 * n_sm                                   # frames of one wave of tiles (4 CTAs per SM)
+    N = 2 * wave + 8 * 37 + 3
+    rng = np.random.default_rng(5)
+    x = synth.make_trajectory(N, rng).astype(np.float32)
+    _, uv = h.fk_project(x)
+    meas = (uv + rng.normal(0, 3, uv.shape)).astype(np.float32)
+    w = rng.uniform(0.05, 0.4, (N, 6, 20)).astype(np.float32)
+    w[rng.random(w.shape) < 0.1] = 0.0
+    xd, md, wd = (torch.from_numpy(a).to(dev) for a in (x, meas, w))
+
+    def run(a, b, want_H=True, stream=None):
+        n = b - a
+        c = torch.full((n,), np.nan, device=dev)
+        g = torch.full((n, 25), np.nan, device=dev)
+        H = torch.full((n, 325), np.nan, device=dev) if want_H else None
+        h.fte_eval_dev(xd[a:b], md[a:b], wd[a:b], c, g, H, stream=stream)
+        return c, g, H
+
+    # reference: single-wave launches (at most `wave` frames each, tile-aligned starts)
+    parts = [run(a, min(a + wave - 8, N)) for a in range(0, N, wave - 8)]
+    torch.cuda.synchronize()
+    c_ref, g_ref, H_ref = (torch.cat([p[i] for p in parts]) for i in range(3))
+    assert torch.isfinite(H_ref).all()
+    for n in (wave - 8, wave, wave + 5, wave + 8, 2 * wave - 3, 2 * wave + 8, N):
+        for rep in range(2):                              # the second launch re-uses a counter pair the first one re-armed
+            c, g, H = run(0, n)
+            torch.cuda.synchronize()
+            assert torch.equal(c, c_ref[:n]) and torch.equal(g, g_ref[:n]) and torch.equal(H, H_ref[:n]), (n, rep)
+    c, g, _ = run(0, N, want_H=False)
+    torch.cuda.synchronize()
+    assert torch.equal(c, c_ref) and torch.equal(g, g_ref)
+    # an offset start (tiles no longer aligned with the reference's) and two launches in flight on two streams
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    r1 = run(3, N, stream=s1.cuda_stream)
+    r2 = run(0, N - 11, stream=s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(r1[2], H_ref[3:]) and torch.equal(r1[1], g_ref[3:]) and torch.equal(r1[0], c_ref[3:])
+    assert torch.equal(r2[2], H_ref[:N - 11]) and torch.equal(r2[0], c_ref[:N - 11])
+    h.close()
