@@ -69,7 +69,10 @@ int acino_set_redescending(acino_handle* h, double a, double b, double c);
  *   g    [N][25]        d cost / d x_n
  *   H    [N][325]       packed upper triangle of sum psi(w r) w^2 J^T J  (psi = max(rho'/e, 1-sigma_a))
  * Any of cost/g/H may be NULL (not written).  meas must be 8-byte aligned (ACINO_ERR_ARG otherwise); with every
- * pointer 16-byte aligned the tiles move by bulk async copies (TMA), otherwise by plain loads / stores - same bits. */
+ * pointer 16-byte aligned the tiles move by bulk async copies (TMA), otherwise by plain loads / stores - same bits.
+ * Launches of more than one wave of 8-frame tiles draw their tiles from a device counter pair taken from a ring of 32 that
+ * the handle owns (results do not depend on the schedule): at most 32 such launches of ONE handle may be in flight at the
+ * same time (different streams, or captured into graphs that run concurrently); use one handle per stream beyond that. */
 int acino_fte_eval_dev(acino_handle* h, int n_frames, const float* x, const float* meas,
                        const float* w, float* cost, float* g, float* H, void* cuda_stream);
 int acino_fte_eval(acino_handle* h, int n_frames, const float* x, const float* meas,
