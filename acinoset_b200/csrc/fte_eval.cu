@@ -741,10 +741,14 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     }
     // structural zeros of H: N_ZERO entries per frame, no arithmetic
     if (WANT_H) {
-        for (int z = tid; z < N_ZERO * FT; z += NT) {
-            const int k = z / FT, f = z - k * FT;
-            S.o.H[f][S.zero_idx[k]] = 0.f;
-        }
+        // (unrolled: the list index of pass i is (tid / FT) + i * NL, an immediate offset; the rolled loop spent 9 instructions
+        // per entry on its own bookkeeping)
+        static_assert(NT % FT == 0, "a thread keeps its frame across the passes");
+        const int zf = tid % FT, zk = tid / FT;
+        float* const Hz = S.o.H[zf];
+#pragma unroll
+        for (int i = 0; i < (N_ZERO * FT + NT - 1) / NT; ++i)
+            if ((i + 1) * NT <= N_ZERO * FT || zk + i * (NT / FT) < N_ZERO) Hz[S.zero_idx[zk + i * (NT / FT)]] = 0.f;
     }
     __syncthreads();   // Ij (region B) is dead from here on
     PHASE_MARK(6);
