@@ -43,12 +43,13 @@ constexpr int N_PAIR = NANG * (NANG + 1) / 2;  // 253 unordered angle pairs (inc
 // ("trunk", 6 slots, 117 of the 185 related pairs) pivot on the head point: v_al = 0, so their entries are 3-term dot
 // products omega_al . y_top with omega_al loaded once per frame (broadcast).  The other ancestors (<= 8) come from a
 // per-slot list.  Unrelated pairs (disjoint subtrees, 68) are structural zeros: a list of their H indices, written without
-// arithmetic.  Task order: columns sorted by list length so that the four columns sharing a warp do similar work; the
-// two columns of the second round are light ones.
+// arithmetic.  Task order: the 16 columns that have non-trunk ancestors, sorted by list length so that the four columns
+// sharing a warp do similar work; then the six trunk columns (empty lists, v = 0: a shorter code path of their own).
 constexpr int N_TRUNK = 6;
 constexpr int k_trunk_slot[N_TRUNK] = {0, 3, 17, 1, 4, 18};     // phi0 theta0 psi0 | phi1 theta1 psi1
 constexpr int trunk_slot(int k) { return k == 0 ? 0 : k == 1 ? 3 : k == 2 ? 17 : k == 3 ? 1 : k == 4 ? 4 : 18; }
 constexpr int MAX_ANC = 8;
+constexpr int N_GENERIC = NANG - N_TRUNK;      // 16 columns with non-trunk ancestors-or-self
 #ifndef ACINO_UNROLL_PAIRS
 #define ACINO_UNROLL_PAIRS 3             // the camera loop is unrolled for this many camera pairs (the reference's six cameras)
 #endif
@@ -102,8 +103,9 @@ constexpr ColTable make_col_table() {
         }
     int n_rel = 0;
     for (int q = 0; q < NANG; ++q) {
-        // first round: the four lightest columns, then the 16 heaviest; second round (q = 20, 21): two light ones
-        const int be = order[q < 4 ? q : (q < 20 ? q + 2 : q - 16)];
+        // tasks 0 .. 15: the columns with non-trunk ancestors, lightest first (the six trunk slots have empty lists and sort
+        // first); tasks 16 .. 21: the trunk columns
+        const int be = order[q < N_GENERIC ? q + N_TRUNK : q - N_GENERIC];
         ColEntry& c = t.col[q];
         c.slot = (unsigned)be;
         c.tau_off = (unsigned)(be * TAU_STRIDE);
@@ -140,6 +142,15 @@ constexpr int max_anc_len() {
     return m;
 }
 static_assert(max_anc_len() == MAX_ANC, "kinematic tree changed: check the column table");
+constexpr bool trunk_tasks_ok() {
+    const ColTable t = make_col_table();
+    for (int q = 0; q < NANG; ++q) {
+        const bool trunk = is_trunk_slot((int)t.col[q].slot);
+        if (trunk != (q >= N_GENERIC) || (trunk && (t.col[q].n_anc != 0 || k_angle_pivot[t.col[q].slot] >= 0))) return false;
+    }
+    return true;
+}
+static_assert(trunk_tasks_ok(), "tasks 16..21 must be the trunk columns: head-point pivot, no non-trunk ancestor");
 static_assert(make_col_table().n_rel == 185 * 1000 + N_ZERO, "kinematic tree changed: 185 related + 68 unrelated pairs");
 __constant__ ColTable c_col = make_col_table();
 __device__ __align__(16) const ColTable d_col = make_col_table();     // global-memory copy: source of the bulk (TMA) copy
@@ -647,28 +658,13 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
     __syncthreads();   // Il is dead from here on; the staged outputs alias it
     PHASE_MARK(5);
 
-    // ---- P4: column beta of H, g[beta].  One thread per (task q, frame); q == 22 is the translation block.
-    //      y = I_subtree(beta) tau_beta stays in registers (see ColEntry).
-    for (int task = tid; task < FT * (NANG + 1); task += NT) {
-        const int q = task / FT;
-        const int f = task - q * FT;
+    // ---- P4: column beta of H, g[beta].  One thread per (column task, frame).  y = I_subtree(beta) tau_beta stays in registers
+    //      (see ColEntry).  Threads 0 .. 16 FT - 1: the 16 columns with non-trunk ancestors (tasks 0..15 of the table, four
+    //      per warp, sorted by list length).  The last 4 FT threads: the six trunk columns (v = 0, every ancestor a trunk slot:
+    //      half the arithmetic, no ancestor list) - four, then two beside the translation block.
+    auto column_task = [&](const int q, const int f) {
         float* g = S.o.g[f];
         float* H = S.o.H[f];
-        if (q == NANG) {
-            float c = 0.f;
-#pragma unroll
-            for (int l = 0; l < NL; ++l) c += S.costp[f][l];
-            const float* I0 = S.Ij[f];
-            const float g0 = I0[24], g1 = I0[25], g2 = I0[26];
-            const float h0 = I0[15], h1 = I0[16], h2 = I0[17], h3 = I0[18], h4 = I0[19], h5 = I0[20];
-            S.o.cost[f] = c;
-            g[0] = g0; g[1] = g1; g[2] = g2;
-            if (WANT_H) {
-                H[upper_index(0, 0)] = h0; H[upper_index(0, 1)] = h1; H[upper_index(0, 2)] = h2;
-                H[upper_index(1, 1)] = h3; H[upper_index(1, 2)] = h4; H[upper_index(2, 2)] = h5;
-            }
-            continue;
-        }
         const uint4* ce = reinterpret_cast<const uint4*>(&S.col[q]);
         const uint4 e0 = ce[0];            // tau offset, Ij offset, list length, slot
         const int be = e0.w, n_anc = e0.z;
@@ -683,7 +679,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         const float gb = o0 * I[21] + o1 * I[22] + o2 * I[23] + v0 * I[24] + v1 * I[25] + v2 * I[26];
         if (!WANT_H) {
             g[3 + be] = gb;
-            continue;
+            return;
         }
         // y = I tau_beta ; I = [[TL, PA],[PA^T, A]]
         const float yt0 = I[0] * o0 + I[1] * o1 + I[2] * o2 + I[6] * v0 + I[7] * v1 + I[8] * v2;
@@ -738,6 +734,72 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
 #pragma unroll
         for (int k = 0; k < MAX_ANC; ++k)
             if (k < n_anc) H[ai[k]] = ha[k];
+    };
+    // a trunk column: tau_beta = (omega, 0), so y = I[:, 0:3] omega (18 products instead of 36), the wrench part of g needs
+    // components 21..23 only, and the ancestors-or-self are all among the six trunk slots (the table's trunk_idx)
+    auto trunk_task = [&](const int q, const int f) {
+        float* g = S.o.g[f];
+        float* H = S.o.H[f];
+        const uint4* ce = reinterpret_cast<const uint4*>(&S.col[q]);
+        const uint4 e0 = ce[0];
+        const int be = e0.w;
+        const float4* I4 = reinterpret_cast<const float4*>(&S.Ij[f][e0.y]);
+        const float* tau_f = &S.tau[f][0];
+        const float4 t0 = *reinterpret_cast<const float4*>(tau_f + e0.x);
+        const float o0 = t0.x, o1 = t0.y, o2 = t0.z;
+        const float4 i5 = I4[5];           // components 20..23
+        const float gb = o0 * i5.y + o1 * i5.z + o2 * i5.w;
+        g[3 + be] = gb;
+        if (!WANT_H) return;
+        const float4 i0 = I4[0], i1 = I4[1], i2 = I4[2], i3 = I4[3];
+        const float I[16] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y, i3.z, i3.w};
+        const float yt0 = I[0] * o0 + I[1] * o1 + I[2] * o2;
+        const float yt1 = I[1] * o0 + I[3] * o1 + I[4] * o2;
+        const float yt2 = I[2] * o0 + I[4] * o1 + I[5] * o2;
+        const float yb0 = I[6] * o0 + I[9] * o1 + I[12] * o2;
+        const float yb1 = I[7] * o0 + I[10] * o1 + I[13] * o2;
+        const float yb2 = I[8] * o0 + I[11] * o1 + I[14] * o2;
+        float ht[N_TRUNK];
+#pragma unroll
+        for (int k = 0; k < N_TRUNK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(tau_f + trunk_slot(k) * TAU_STRIDE);
+            ht[k] = a0.x * yt0 + a0.y * yt1 + a0.z * yt2;
+        }
+        const int sb = 3 + be;
+        H[sb] = yb0;
+        H[NA + sb - 1] = yb1;
+        H[2 * NA + sb - 3] = yb2;
+        const uint4 t0_ = ce[1];
+        const uint2 t1_ = *reinterpret_cast<const uint2*>(&ce[2]);
+        const unsigned ti[N_TRUNK] = {t0_.x, t0_.y, t0_.z, t0_.w, t1_.x, t1_.y};
+#pragma unroll
+        for (int k = 0; k < N_TRUNK; ++k)
+            if (ti[k] != NO_ENTRY) H[ti[k]] = ht[k];
+    };
+    // the translation block, the translation part of g and the frame's cost
+    auto translation_task = [&](const int f) {
+        float* g = S.o.g[f];
+        float* H = S.o.H[f];
+        float c = 0.f;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) c += S.costp[f][l];
+        const float* I0 = S.Ij[f];
+        const float g0 = I0[24], g1 = I0[25], g2 = I0[26];
+        const float h0 = I0[15], h1 = I0[16], h2 = I0[17], h3 = I0[18], h4 = I0[19], h5 = I0[20];
+        S.o.cost[f] = c;
+        g[0] = g0; g[1] = g1; g[2] = g2;
+        if (WANT_H) {
+            H[upper_index(0, 0)] = h0; H[upper_index(0, 1)] = h1; H[upper_index(0, 2)] = h2;
+            H[upper_index(1, 1)] = h3; H[upper_index(1, 2)] = h4; H[upper_index(2, 2)] = h5;
+        }
+    };
+    if (tid < N_GENERIC * FT) {
+        column_task(tid / FT, tid % FT);
+    } else {
+        const int u = tid - N_GENERIC * FT;          // 0 .. 4 FT - 1
+        trunk_task(N_GENERIC + u / FT, u % FT);
+        if (u < 2 * FT) trunk_task(N_GENERIC + 4 + u / FT, u % FT);
+        else if (u < 3 * FT) translation_task(u - 2 * FT);
     }
     // structural zeros of H: N_ZERO entries per frame, no arithmetic
     if (WANT_H) {
