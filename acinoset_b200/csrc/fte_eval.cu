@@ -147,10 +147,14 @@ constexpr bool trunk_tasks_ok() {
     for (int q = 0; q < NANG; ++q) {
         const bool trunk = is_trunk_slot((int)t.col[q].slot);
         if (trunk != (q >= N_GENERIC) || (trunk && (t.col[q].n_anc != 0 || k_angle_pivot[t.col[q].slot] >= 0))) return false;
+        if (!trunk)
+            for (int k = 0; k < N_TRUNK; ++k)
+                if (t.col[q].trunk_idx[k] == NO_ENTRY) return false;
     }
     return true;
 }
-static_assert(trunk_tasks_ok(), "tasks 16..21 must be the trunk columns: head-point pivot, no non-trunk ancestor");
+static_assert(trunk_tasks_ok(), "tasks 16..21 must be the trunk columns (head-point pivot, no non-trunk ancestor), and every trunk "
+                                "slot an ancestor of tasks 0..15");
 static_assert(make_col_table().n_rel == 185 * 1000 + N_ZERO, "kinematic tree changed: 185 related + 68 unrelated pairs");
 __constant__ ColTable c_col = make_col_table();
 __device__ __align__(16) const ColTable d_col = make_col_table();     // global-memory copy: source of the bulk (TMA) copy
@@ -210,7 +214,7 @@ struct __align__(16) Smem {
     float x[2][FT][NA];                // state, double buffered (next tile prefetched)
     float p[FT][NL][3];                // marker positions relative to the head point
     float2 sc[FT][NANG];               // (sin, cos) of every angle
-    float costp[FT][NL];               // per-(frame, marker) cost partials
+    __align__(16) float costp[FT][NL]; // per-(frame, marker) cost partials
     __align__(16) ColEntry col[NANG];  // column table of the H assembly (copy of c_col), followed by the zero list
     unsigned short zero_idx[N_ZERO + 4];
     __align__(16) float tau[FT][TAUF]; // (omega, v = pivot x omega) per angle, stride 8
@@ -703,19 +707,27 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         // 4 % slower).  Unused list entries point at slot 0: a valid address, the product is not stored
         float ha[MAX_ANC];
         const int n_max = (int)__reduce_max_sync(__activemask(), (unsigned)n_anc);
+        auto anc_batch = [&](auto b_tag, auto n_tag) {
+            constexpr int B0 = decltype(b_tag)::value, NB = decltype(n_tag)::value;
+            float4 a0[NB];
+            float2 a1[NB];
 #pragma unroll
-        for (int b = 0; b < MAX_ANC; b += ANC_B) {
-            if (b >= n_max) break;
-            float4 a0[ANC_B];
-            float2 a1[ANC_B];
-#pragma unroll
-            for (int k = 0; k < ANC_B; ++k) {
-                a0[k] = *reinterpret_cast<const float4*>(tau_f + ao[b + k]);
-                a1[k] = *reinterpret_cast<const float2*>(tau_f + ao[b + k] + 4);
+            for (int k = 0; k < NB; ++k) {
+                a0[k] = *reinterpret_cast<const float4*>(tau_f + ao[B0 + k]);
+                a1[k] = *reinterpret_cast<const float2*>(tau_f + ao[B0 + k] + 4);
             }
 #pragma unroll
-            for (int k = 0; k < ANC_B; ++k)
-                ha[b + k] = a0[k].x * yt0 + a0[k].y * yt1 + a0[k].z * yt2 + a0[k].w * yb0 + a1[k].x * yb1 + a1[k].y * yb2;
+            for (int k = 0; k < NB; ++k)
+                ha[B0 + k] = a0[k].x * yt0 + a0[k].y * yt1 + a0[k].z * yt2 + a0[k].w * yb0 + a1[k].x * yb1 + a1[k].y * yb2;
+        };
+        using std::integral_constant;
+        // the four warps of the generic columns have list lengths up to 2 / 4 / 6 / 8 (sorted table): 2 or 4 per batch
+        if (n_max <= 2) {
+            anc_batch(integral_constant<int, 0>{}, integral_constant<int, 2>{});
+        } else {
+            anc_batch(integral_constant<int, 0>{}, integral_constant<int, 4>{});
+            if (n_max > 6) anc_batch(integral_constant<int, 4>{}, integral_constant<int, 4>{});
+            else if (n_max > 4) anc_batch(integral_constant<int, 4>{}, integral_constant<int, 2>{});
         }
         // stores last: no store -> load ordering inside the task
         g[3 + be] = gb;
@@ -727,8 +739,7 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         const uint2 t1_ = *reinterpret_cast<const uint2*>(&ce[2]);
         const unsigned ti[N_TRUNK] = {t0_.x, t0_.y, t0_.z, t0_.w, t1_.x, t1_.y};
 #pragma unroll
-        for (int k = 0; k < N_TRUNK; ++k)
-            if (ti[k] != NO_ENTRY) H[ti[k]] = ht[k];
+        for (int k = 0; k < N_TRUNK; ++k) H[ti[k]] = ht[k];      // (every trunk slot is an ancestor of a generic column)
         const uint4 i0_ = ce[5], i1_ = ce[6];           // anc_idx[0..7]
         const unsigned ai[MAX_ANC] = {i0_.x, i0_.y, i0_.z, i0_.w, i1_.x, i1_.y, i1_.z, i1_.w};
 #pragma unroll
@@ -781,8 +792,15 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         float* g = S.o.g[f];
         float* H = S.o.H[f];
         float c = 0.f;
+        static_assert(NL % 4 == 0, "cost partials are read four at a time");
 #pragma unroll
-        for (int l = 0; l < NL; ++l) c += S.costp[f][l];
+        for (int l = 0; l < NL; l += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(&S.costp[f][l]);
+            c += v.x;
+            c += v.y;
+            c += v.z;
+            c += v.w;
+        }
         const float* I0 = S.Ij[f];
         const float g0 = I0[24], g1 = I0[25], g2 = I0[26];
         const float h0 = I0[15], h1 = I0[16], h2 = I0[17], h3 = I0[18], h4 = I0[19], h5 = I0[20];
