@@ -53,10 +53,6 @@ constexpr int N_GENERIC = NANG - N_TRUNK;      // 16 columns with non-trunk ance
 #ifndef ACINO_UNROLL_PAIRS
 #define ACINO_UNROLL_PAIRS 3             // the camera loop is unrolled for this many camera pairs (the reference's six cameras)
 #endif
-#ifndef ACINO_ANC_B
-#define ACINO_ANC_B 4
-#endif
-constexpr int ANC_B = ACINO_ANC_B;       // ancestors per batch of the column assembly (divides MAX_ANC)
 constexpr int N_ZERO = N_PAIR - 185;
 constexpr unsigned NO_ENTRY = 0xFFFFu;
 struct ColEntry {                       // 112 bytes of ready-to-use 32-bit words: seven 16-byte loads, no field extraction
@@ -702,9 +698,9 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
         // the other ancestors (and beta itself): full 6-term products
         const uint4 a0_ = ce[3], a1_ = ce[4];           // anc_off[0..7]
         const unsigned ao[MAX_ANC] = {a0_.x, a0_.y, a0_.z, a0_.w, a1_.x, a1_.y, a1_.z, a1_.w};
-        // in batches of ANC_B with the loads of a batch in flight together (one vote per warp and column round: a loop with a
-        // vote and a break per ancestor ran them one load latency after the other; executing all 8 for every column measured
-        // 4 % slower).  Unused list entries point at slot 0: a valid address, the product is not stored
+        // in batches with the loads of a batch in flight together (one warp-wide maximum of the list lengths decides which
+        // batches run: a loop with a vote and a break per ancestor ran them one load latency after the other; executing all 8
+        // for every column measured 4 % slower).  Unused list entries point at slot 0: a valid address, the product is not stored
         float ha[MAX_ANC];
         const int n_max = (int)__reduce_max_sync(__activemask(), (unsigned)n_anc);
         auto anc_batch = [&](auto b_tag, auto n_tag) {
