@@ -402,10 +402,12 @@ fte_eval_body(const SceneF& scene, const int n_frames, const int use_bulk,
 
     // Tile schedule.  Static (tile, tile + grid, ...) when every CTA has one tile, or no counter was given.  Otherwise
     // dynamic: the first two tiles are blockIdx.x and blockIdx.x + grid, every further one is claimed from a global ticket
-    // counter TWO tiles ahead: the atomic is issued during the FK phase and its result is first touched after the camera loop
-    // (claimed one tile ahead, the ~1500-cycle round trip under load sat on the FK phase's critical path).  The CTAs of a persistent wave do not run at the same speed - with the
-    // static schedule the fast ones had exited while the slow ones still had tiles left (17.2 of 20 warps active on
-    // average); the last CTA to leave resets the counter pair for the next launch.
+    // counter TWO tiles ahead: the atomic is issued during the FK phase and its result is first touched after the camera
+    // loop (claimed one tile ahead, the ~1500-cycle round trip under load sat on the FK phase's critical path).  The CTAs
+    // of a persistent wave do not run at the same speed - with the static schedule the fast ones had exited while the slow
+    // ones still had tiles left (17.2 of 20 warps active on average); the last CTA to leave resets the counter pair for
+    // the next launch.
+    static_assert(NT > 128, "threads 96 / 97 / 128 issue the copies and draw the tickets");
 #ifdef ACINO_STATIC_SCHED
     const bool dynamic = false;
 #else
